@@ -1,0 +1,149 @@
+"""ctypes binding of the C ABI in include/m3tsz_b200.h (libm3tsz_b200.so).
+
+There is no CPU fallback anywhere in this package: if the shared library has
+not been built, or no CUDA device is present, the calls below raise.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libm3tsz_b200.so")
+
+OK = 0
+ERR_EOF = 1
+ERR_DOD_OVERFLOW = 4
+ERR_NO_TIME_SCHEME = 5
+ERR_UNRECOGNIZED_UNIT = 6
+ERR_INVALID_MULT = 7
+ERR_CAPACITY = 100
+ERR_INVALID_ARG = 101
+ERR_CUDA = 102
+ERR_NO_DEVICE = 103
+
+UNIT_NONE, UNIT_S, UNIT_MS, UNIT_US, UNIT_NS, UNIT_MIN, UNIT_HOUR, UNIT_DAY, UNIT_YEAR = range(9)
+
+
+class Options(C.Structure):
+    """m3tsz_options: intOptimized flag + encoding.Options.DefaultTimeUnit."""
+    _fields_ = [("int_optimized", C.c_int32), ("default_time_unit", C.c_int32)]
+
+
+class AnnotationRef(C.Structure):
+    _fields_ = [("bit_offset", C.c_uint64), ("length", C.c_uint32), ("count", C.c_uint32)]
+
+
+class AnnotationEntry(C.Structure):
+    _fields_ = [("dp_index", C.c_uint32), ("length", C.c_uint32), ("byte_offset", C.c_uint64)]
+
+
+class M3tszError(RuntimeError):
+    def __init__(self, status, what=""):
+        self.status = status
+        msg = status_string(status)
+        super().__init__("m3tsz_b200: %s (status %d)%s" % (msg, status, (": " + what) if what else ""))
+
+
+_lib = None
+
+# every symbol include/m3tsz_b200.h declares (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = [
+    "m3tsz_version", "m3tsz_status_string", "m3tsz_ctx_create", "m3tsz_ctx_destroy",
+    "m3tsz_last_cuda_error", "m3tsz_ctx_launch_count", "m3tsz_decode_batch",
+    "m3tsz_decode_batch_host", "m3tsz_encode_batch", "m3tsz_encode_bound",
+    "m3tsz_compact_streams", "m3tsz_encode_batch_host", "m3tsz_decode_downsample_batch",
+    "m3tsz_decode_downsample_batch_host",
+]
+
+
+def lib():
+    """Loads libm3tsz_b200.so.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "m3_b200: %s is missing - build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  This package has no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i64, i32, u32 = C.c_void_p, C.c_uint64, C.c_int64, C.c_int32, C.c_uint32
+    po = C.POINTER(Options)
+    L.m3tsz_version.restype = C.c_int
+    L.m3tsz_version.argtypes = []
+    L.m3tsz_status_string.restype = C.c_char_p
+    L.m3tsz_status_string.argtypes = [C.c_int]
+    L.m3tsz_ctx_create.restype = C.c_int
+    L.m3tsz_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.m3tsz_ctx_destroy.restype = None
+    L.m3tsz_ctx_destroy.argtypes = [vp]
+    L.m3tsz_last_cuda_error.restype = C.c_char_p
+    L.m3tsz_last_cuda_error.argtypes = [vp]
+    L.m3tsz_ctx_launch_count.restype = u64
+    L.m3tsz_ctx_launch_count.argtypes = [vp]
+    L.m3tsz_encode_bound.restype = u64
+    L.m3tsz_encode_bound.argtypes = [u64]
+    L.m3tsz_decode_batch.restype = C.c_int
+    L.m3tsz_decode_batch.argtypes = [vp, po, vp, u64, vp, u64, vp, vp, u64, vp, vp, vp, vp, vp]
+    L.m3tsz_decode_batch_host.restype = C.c_int
+    L.m3tsz_decode_batch_host.argtypes = [vp, po, vp, u64, vp, u64, vp, vp, u64, vp, vp, vp, vp]
+    L.m3tsz_encode_batch.restype = C.c_int
+    L.m3tsz_encode_batch.argtypes = [vp, po, vp, vp, u64, u64, vp, vp, i32, vp, vp, vp, vp, vp, u64,
+                                     vp, vp, vp]
+    L.m3tsz_encode_batch_host.restype = C.c_int
+    L.m3tsz_encode_batch_host.argtypes = [vp, po, vp, vp, u64, u64, vp, vp, i32, vp, vp, vp, vp, u64,
+                                          vp, u64, vp, vp]
+    L.m3tsz_compact_streams.restype = C.c_int
+    L.m3tsz_compact_streams.argtypes = [vp, vp, u64, vp, u64, u32, vp, u64, vp, vp]
+    L.m3tsz_decode_downsample_batch.restype = C.c_int
+    L.m3tsz_decode_downsample_batch.argtypes = [vp, po, vp, u64, vp, u64, i64, i64, u32, vp, vp, vp,
+                                                vp, vp, vp, vp]
+    L.m3tsz_decode_downsample_batch_host.restype = C.c_int
+    L.m3tsz_decode_downsample_batch_host.argtypes = [vp, po, vp, u64, vp, u64, i64, i64, u32, vp, vp,
+                                                     vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def status_string(status):
+    try:
+        return lib().m3tsz_status_string(int(status)).decode()
+    except Exception:  # library missing: still produce a message
+        return "status %d" % status
+
+
+class Context:
+    """m3tsz_ctx: owns the device binding and the scratch used by *_host calls."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().m3tsz_ctx_create(int(device), C.byref(self._h))
+        if rc != OK:
+            raise M3tszError(rc, "m3tsz_ctx_create(device=%d)" % device)
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def launch_count(self):
+        return int(lib().m3tsz_ctx_launch_count(self._h))
+
+    def last_cuda_error(self):
+        return lib().m3tsz_last_cuda_error(self._h).decode()
+
+    def check(self, rc, what=""):
+        if rc != OK:
+            extra = what
+            if rc == ERR_CUDA:
+                extra = (what + " " + self.last_cuda_error()).strip()
+            raise M3tszError(rc, extra)
+
+    def close(self):
+        if self._h:
+            lib().m3tsz_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,184 @@
+"""Batch codec over the C ABI, with torch tensors as device memory.
+
+torch is plumbing here (device allocations, streams, torch.distributed); every
+codec operation is one call into libm3tsz_b200.so (hand-written sm_100a
+kernels).  Nothing in this module computes on the CPU.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import capi
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _cuda_stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@dataclass
+class DecodeResult:
+    ts: torch.Tensor        # int64  [S, max_points]
+    values: torch.Tensor    # float64 [S, max_points]
+    n_points: torch.Tensor  # int32 (uint32 bits) [S]
+    status: torch.Tensor    # int32 [S]
+    unit: torch.Tensor      # uint8 [S]
+    annotations: Optional[torch.Tensor]  # uint8 view of m3tsz_annotation_ref [S, 16] or None
+
+
+@dataclass
+class EncodeResult:
+    out: torch.Tensor      # uint8 [S, out_stride] slots
+    out_len: torch.Tensor  # int64 [S]
+    status: torch.Tensor   # int32 [S]
+
+
+@dataclass
+class DownsampleResult:
+    sum: torch.Tensor    # float64 [W, S] (window-major)
+    count: torch.Tensor  # int64 [W, S]
+    min: torch.Tensor    # float64 [W, S]
+    max: torch.Tensor    # float64 [W, S]
+    n_points: torch.Tensor
+    status: torch.Tensor
+
+
+class BatchCodec:
+    """Device-resident batch encode / decode (the drop-in for the per-series
+    loops at the reference's batch sites)."""
+
+    def __init__(self, device=0, int_optimized=True, default_unit=capi.UNIT_S):
+        if not torch.cuda.is_available():
+            raise capi.M3tszError(capi.ERR_NO_DEVICE, "torch sees no CUDA device")
+        self.device = torch.device("cuda", device if isinstance(device, int) else device.index)
+        self.ctx = capi.Context(self.device.index)
+        self.opts = capi.Options(int(bool(int_optimized)), int(default_unit))
+        self.int_optimized = bool(int_optimized)
+        self.default_unit = int(default_unit)
+
+    # ------------------------------------------------------------------ decode
+    def decode(self, streams: torch.Tensor, offsets: torch.Tensor, max_points: int,
+               want_annotations=False, out: Optional[DecodeResult] = None) -> DecodeResult:
+        """streams: uint8 [total] on device; offsets: int64 [S+1] on device (byte offsets)."""
+        assert streams.dtype == torch.uint8 and streams.is_cuda and streams.is_contiguous()
+        assert offsets.dtype == torch.int64 and offsets.is_cuda and offsets.is_contiguous()
+        S = offsets.numel() - 1
+        dev = self.device
+        if out is None:
+            out = DecodeResult(
+                ts=torch.empty((S, max_points), dtype=torch.int64, device=dev),
+                values=torch.empty((S, max_points), dtype=torch.float64, device=dev),
+                n_points=torch.empty(S, dtype=torch.int32, device=dev),
+                status=torch.empty(S, dtype=torch.int32, device=dev),
+                unit=torch.empty(S, dtype=torch.uint8, device=dev),
+                annotations=(torch.empty((S, 16), dtype=torch.uint8, device=dev)
+                             if want_annotations else None))
+        rc = capi.lib().m3tsz_decode_batch(
+            self.ctx.handle, C.byref(self.opts), _ptr(streams), streams.numel(), _ptr(offsets), S,
+            _ptr(out.ts), _ptr(out.values), max_points, _ptr(out.n_points), _ptr(out.status),
+            _ptr(out.unit), _ptr(out.annotations), _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_decode_batch")
+        return out
+
+    def decode_downsample(self, streams, offsets, range_start_ns, window_ns, n_windows,
+                          out: Optional[DownsampleResult] = None) -> DownsampleResult:
+        assert streams.dtype == torch.uint8 and streams.is_cuda
+        assert offsets.dtype == torch.int64 and offsets.is_cuda
+        S = offsets.numel() - 1
+        dev = self.device
+        if out is None:
+            out = DownsampleResult(
+                sum=torch.empty((n_windows, S), dtype=torch.float64, device=dev),
+                count=torch.empty((n_windows, S), dtype=torch.int64, device=dev),
+                min=torch.empty((n_windows, S), dtype=torch.float64, device=dev),
+                max=torch.empty((n_windows, S), dtype=torch.float64, device=dev),
+                n_points=torch.empty(S, dtype=torch.int32, device=dev),
+                status=torch.empty(S, dtype=torch.int32, device=dev))
+        rc = capi.lib().m3tsz_decode_downsample_batch(
+            self.ctx.handle, C.byref(self.opts), _ptr(streams), streams.numel(), _ptr(offsets), S,
+            int(range_start_ns), int(window_ns), int(n_windows), _ptr(out.sum), _ptr(out.count),
+            _ptr(out.min), _ptr(out.max), _ptr(out.n_points), _ptr(out.status),
+            _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_decode_downsample_batch")
+        return out
+
+    # ------------------------------------------------------------------ encode
+    def encode_bound(self, n_points: int) -> int:
+        return int(capi.lib().m3tsz_encode_bound(int(n_points)))
+
+    def encode(self, ts: torch.Tensor, values: torch.Tensor, start: torch.Tensor,
+               unit=capi.UNIT_S, n_points: Optional[torch.Tensor] = None,
+               units: Optional[torch.Tensor] = None, annotations=None,
+               out_stride: Optional[int] = None, out: Optional[EncodeResult] = None) -> EncodeResult:
+        """ts int64 [S,P], values float64 [S,P], start int64 [S] (all on device).
+        annotations: optional (series_off int64 [S+1], entries uint8 [E,16], bytes uint8 [B])."""
+        assert ts.dtype == torch.int64 and values.dtype == torch.float64
+        assert ts.is_cuda and values.is_cuda and ts.is_contiguous() and values.is_contiguous()
+        assert start.dtype == torch.int64 and start.is_cuda
+        S, P = ts.shape
+        dev = self.device
+        if out_stride is None:
+            out_stride = self.encode_bound(P)
+        if out is None:
+            out = EncodeResult(
+                out=torch.empty((S, out_stride), dtype=torch.uint8, device=dev),
+                out_len=torch.empty(S, dtype=torch.int64, device=dev),
+                status=torch.empty(S, dtype=torch.int32, device=dev))
+        a_off = a_ent = a_bytes = None
+        if annotations is not None:
+            a_off, a_ent, a_bytes = annotations
+        rc = capi.lib().m3tsz_encode_batch(
+            self.ctx.handle, C.byref(self.opts), _ptr(ts), _ptr(values), S, P, _ptr(n_points),
+            _ptr(start), int(unit), _ptr(units), _ptr(a_off), _ptr(a_ent), _ptr(a_bytes),
+            _ptr(out.out), out.out.shape[1], _ptr(out.out_len), _ptr(out.status),
+            _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_encode_batch")
+        return out
+
+    def compact(self, enc: EncodeResult, align=16, capacity: Optional[int] = None):
+        """Packs slots into (packed uint8 [total], offsets int64 [S+1])."""
+        S, stride = enc.out.shape
+        dev = self.device
+        if capacity is None:
+            capacity = int(enc.out_len.sum().item()) + S * align + 16
+        packed = torch.empty(capacity, dtype=torch.uint8, device=dev)
+        offsets = torch.empty(S + 1, dtype=torch.int64, device=dev)
+        rc = capi.lib().m3tsz_compact_streams(
+            self.ctx.handle, _ptr(enc.out), stride, _ptr(enc.out_len), S, int(align), _ptr(packed),
+            capacity, _ptr(offsets), _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_compact_streams")
+        return packed, offsets
+
+    # ------------------------------------------------------------ host-buffer calls
+    def decode_host(self, h_streams, h_offsets, max_points, h_ts, h_values, h_n_points, h_status):
+        """All arguments are host tensors (pinned or pageable); copies are inside the call."""
+        S = h_offsets.numel() - 1
+        rc = capi.lib().m3tsz_decode_batch_host(
+            self.ctx.handle, C.byref(self.opts), _ptr(h_streams), h_streams.numel(), _ptr(h_offsets),
+            S, _ptr(h_ts), _ptr(h_values), max_points, _ptr(h_n_points), _ptr(h_status), None, None)
+        self.ctx.check(rc, "m3tsz_decode_batch_host")
+
+    def encode_host(self, h_ts, h_values, h_start, unit, h_out, h_out_len, h_status):
+        S, P = h_ts.shape
+        rc = capi.lib().m3tsz_encode_batch_host(
+            self.ctx.handle, C.byref(self.opts), _ptr(h_ts), _ptr(h_values), S, P, None,
+            _ptr(h_start), int(unit), None, None, None, None, 0, _ptr(h_out), h_out.shape[1],
+            _ptr(h_out_len), _ptr(h_status))
+        self.ctx.check(rc, "m3tsz_encode_batch_host")
+
+    def decode_downsample_host(self, h_streams, h_offsets, range_start_ns, window_ns, n_windows,
+                               h_sum, h_count, h_min, h_max, h_n_points, h_status):
+        S = h_offsets.numel() - 1
+        rc = capi.lib().m3tsz_decode_downsample_batch_host(
+            self.ctx.handle, C.byref(self.opts), _ptr(h_streams), h_streams.numel(), _ptr(h_offsets),
+            S, int(range_start_ns), int(window_ns), int(n_windows), _ptr(h_sum), _ptr(h_count),
+            _ptr(h_min), _ptr(h_max), _ptr(h_n_points), _ptr(h_status))
+        self.ctx.check(rc, "m3tsz_decode_downsample_batch_host")
+
+    def launch_count(self):
+        return self.ctx.launch_count()

@@ -1,0 +1,698 @@
+// m3tsz_encode.cu -- batch M3TSZ encode for sm_100a (+ stream compaction).
+//
+// Mapping: one LANE per series, 32 series per warp.  The
+// int-optimised value grammar is a sequential state machine per series
+// (maxMult / isFloat / IntSigBitsTracker, m3tsz/encoder.go:148-250), so each
+// lane runs its series' encoder while the WARP cooperates on memory:
+// (ts, value) inputs are staged through a transposed shared-memory tile from
+// coalesced 128-byte loads, each datapoint's code (<= 32-bit header + <= 64-bit
+// payload) is merged into a per-lane bit accumulator with funnel shifts, full
+// 32-bit words go to a transposed output tile, and the tile is written back
+// with coalesced 128-byte stores per series.
+//
+// Format: SURVEY.md Appendix A; reference encode path
+//   m3tsz/encoder.go:90-250, m3tsz/timestamp_encoder.go:72-259,
+//   m3tsz/float_encoder_iterator.go:69-103, m3tsz/int_sig_bits_tracker.go:35-91,
+//   m3tsz/m3tsz.go:78-119, ostream.go:133-221, scheme.go:198-220.
+#include <cub/device/device_scan.cuh>
+
+#include "m3tsz_common.cuh"
+#include "m3tsz_kernels.h"
+
+namespace m3tsz {
+
+constexpr int ENC_WARPS = 4;
+constexpr int ENC_STRIDE = 33;
+constexpr int ENC_IN_T = 16;    // datapoints staged per input tile
+constexpr int ENC_OUT_W = 64;   // output tile words per lane
+constexpr int ENC_GUARD = 10;   // words a single datapoint (no annotation) may add
+constexpr int ENC_IN_TILE_DWORDS = ENC_IN_T * ENC_STRIDE;
+constexpr int ENC_OUT_TILE_WORDS = ENC_OUT_W * ENC_STRIDE;
+constexpr size_t ENC_WARP_SMEM = 2 * (size_t)ENC_IN_TILE_DWORDS * 8 + (size_t)ENC_OUT_TILE_WORDS * 4;
+
+struct EncLane {
+  uint32_t carry, sh, k, words_out;
+  int64_t prev_time, prev_delta;
+  uint64_t prev_bits, prev_xor;
+  double int_val;
+  int unit;
+  int num_sig, hi_lower_sig, n_lower_sig, max_mult;
+  int err;
+  uint32_t n_enc;
+  bool is_float;
+};
+
+// ---- bit output -----------------------------------------------------------
+// appends the low n (1..32) bits of v
+__device__ __forceinline__ void put32(EncLane &s, uint32_t *tile, int lane, uint32_t v, int n) {
+  const uint32_t c0 = v << (32 - n);
+  const uint32_t m0 = s.carry | __funnelshift_rc(c0, 0u, s.sh);
+  const uint32_t m1 = __funnelshift_rc(0u, c0, s.sh);
+  const uint32_t tot = s.sh + (uint32_t)n;
+  if (tot >= 32) {
+    tile[s.k * ENC_STRIDE + lane] = m0;
+    s.k++;
+    s.carry = m1;
+    s.sh = tot - 32;
+  } else {
+    s.carry = m0;
+    s.sh = tot;
+  }
+}
+// appends the low n (0..64) bits of v
+__device__ __forceinline__ void put64(EncLane &s, uint32_t *tile, int lane, uint64_t v, int n) {
+  if (n > 32) {
+    put32(s, tile, lane, (uint32_t)(v >> 32), n - 32);
+    put32(s, tile, lane, (uint32_t)v, 32);
+  } else if (n > 0) {
+    put32(s, tile, lane, (uint32_t)v, n);
+  }
+}
+
+// appends header (low hb bits of hdr, hb 0..32) followed by payload (low plen
+// bits, plen 0..64): one merge of up to 96 bits into the accumulator.
+__device__ __forceinline__ void emit_code(EncLane &s, uint32_t *tile, int lane, uint32_t hdr, int hb,
+                                          uint64_t payload, int plen) {
+  const uint32_t H = hb ? (hdr << (32 - hb)) : 0u;
+  const uint64_t P = plen ? (payload << (64 - plen)) : 0ull;
+  const uint32_t Ph = (uint32_t)(P >> 32), Pl = (uint32_t)P;
+  const uint32_t c0 = H | __funnelshift_rc(Ph, 0u, (uint32_t)hb);
+  const uint32_t c1 = __funnelshift_rc(Pl, Ph, (uint32_t)hb);
+  const uint32_t c2 = __funnelshift_rc(0u, Pl, (uint32_t)hb);
+  const uint32_t m0 = s.carry | __funnelshift_rc(c0, 0u, s.sh);
+  const uint32_t m1 = __funnelshift_rc(c1, c0, s.sh);
+  const uint32_t m2 = __funnelshift_rc(c2, c1, s.sh);
+  const uint32_t m3 = __funnelshift_rc(0u, c2, s.sh);
+  const uint32_t tot = s.sh + (uint32_t)(hb + plen);
+  const uint32_t full = tot >> 5;
+  uint32_t *tp = tile + s.k * ENC_STRIDE + lane;
+  if (full > 0) tp[0] = m0;
+  if (full > 1) tp[ENC_STRIDE] = m1;
+  if (full > 2) tp[2 * ENC_STRIDE] = m2;
+  s.carry = full == 0 ? m0 : (full == 1 ? m1 : (full == 2 ? m2 : m3));
+  s.k += full;
+  s.sh = tot & 31u;
+}
+
+// ---- convertToIntFloat (m3tsz.go:78-119) ----------------------------------
+// Cheap NECESSARY condition for convertToIntFloat(v, cur) to return an int for
+// any cur in [0,6]: if some v*10^m lies within one ulp of an integer, then
+// fl(|v|*1e6) lies within 4 ulps of an integer (DESIGN.md §4.2 has the proof);
+// tested with margin 8.  Returns true ("maybe int") for everything it cannot
+// rule out, including NaN/Inf/huge/tiny values.
+__device__ __forceinline__ bool maybe_int(double v) {
+  const double a = fabs(v);
+  const double p = __dmul_rn(a, 1000000.0);
+  const uint64_t pb = (uint64_t)__double_as_longlong(p);
+  const int e = (int)(pb >> 52) & 0x7ff;
+  if (e >= 1023 + 48) return true;
+  if (e < 1023) return (e >= 1022) || (a < 1e-300);
+  const int f = 52 - (e - 1023);  // fractional mantissa bits, 5..52
+  const uint64_t mask = (1ull << f) - 1ull;
+  return ((pb + 8ull) & mask) <= 16ull;
+}
+
+// Go int64(float64) on amd64 (CVTTSD2SQ): out of range / NaN -> 0x8000000000000000
+__device__ __forceinline__ uint64_t go_f64_to_u64_via_i64(double a) {
+  if (!(a >= -9223372036854775808.0 && a < 9223372036854775808.0)) return 0x8000000000000000ull;
+  return (uint64_t)__double2ll_rz(a);
+}
+
+__device__ __noinline__ void convert_to_int_float(double v, int cur, double &val, int &mult,
+                                                  bool &is_float) {
+  if (cur == 0 && v < 9223372036854775807.0) {
+    const double i = trunc(v);
+    if (__dsub_rn(v, i) == 0.0) {
+      val = i;
+      mult = 0;
+      is_float = false;
+      return;
+    }
+  }
+  const double sign = (v < 0.0) ? -1.0 : 1.0;
+  for (int m = cur; m <= kMaxMult; m++) {
+    const double x = __dmul_rn(__dmul_rn(v, mult_pow10(m)), sign);
+    if (x >= 1e13) break;
+    const double i = trunc(x);
+    const double r = __dsub_rn(x, i);
+    if (r == 0.0) {
+      val = __dmul_rn(sign, i);
+      mult = m;
+      is_float = false;
+      return;
+    } else if (r < 0.1) {
+      const double below = __longlong_as_double(__double_as_longlong(x) - 1);  // Nextafter(x, 0)
+      if (below <= i) {
+        val = __dmul_rn(sign, i);
+        mult = m;
+        is_float = false;
+        return;
+      }
+    } else if (r > 0.9) {
+      const double next = __dadd_rn(i, 1.0);
+      const double above = __longlong_as_double(__double_as_longlong(x) + 1);  // Nextafter(x, next)
+      if (above >= next) {
+        val = __dmul_rn(sign, next);
+        mult = m;
+        is_float = false;
+        return;
+      }
+    }
+  }
+  val = v;
+  mult = 0;
+  is_float = true;
+}
+
+// IntSigBitsTracker.TrackNewSig, int_sig_bits_tracker.go:68-91
+__device__ __forceinline__ int track_new_sig(EncLane &s, int ns) {
+  int new_sig = s.num_sig;
+  if (ns > s.num_sig) {
+    new_sig = ns;
+  } else if (s.num_sig - ns >= 3) {
+    if (s.n_lower_sig == 0)
+      s.hi_lower_sig = ns;
+    else if (ns > s.hi_lower_sig)
+      s.hi_lower_sig = ns;
+    s.n_lower_sig++;
+    if (s.n_lower_sig >= 5) {
+      new_sig = s.hi_lower_sig;
+      s.n_lower_sig = 0;
+    }
+  } else {
+    s.n_lower_sig = 0;
+  }
+  return new_sig;
+}
+
+// writeIntSigMult (encoder.go:235-250) + WriteIntSig (int_sig_bits_tracker.go:48-62):
+// appends to the header accumulator
+__device__ __forceinline__ void sig_mult_hdr(EncLane &s, int sig, int mult, bool float_changed,
+                                             uint32_t &hdr, int &hb) {
+  if (s.num_sig != sig) {
+    if (sig == 0) {
+      hdr = (hdr << 2) | 2u;  // '1' '0'
+      hb += 2;
+    } else {
+      hdr = (hdr << 8) | (3u << 6) | (uint32_t)(sig - 1);  // '1' '1' + 6 bits
+      hb += 8;
+    }
+  } else {
+    hdr <<= 1;  // '0'
+    hb += 1;
+  }
+  s.num_sig = sig;
+  if (mult > s.max_mult) {
+    hdr = (hdr << 4) | 8u | (uint32_t)mult;
+    hb += 4;
+    s.max_mult = mult;
+  } else if (s.max_mult == mult && float_changed) {
+    hdr = (hdr << 4) | 8u | (uint32_t)s.max_mult;
+    hb += 4;
+  } else {
+    hdr <<= 1;
+    hb += 1;
+  }
+}
+
+// XOR code (float_encoder_iterator.go:75-103) appended after `hb` prefix bits
+__device__ __forceinline__ void xor_code(EncLane &s, uint64_t fb, uint32_t &hdr, int &hb,
+                                         uint64_t &payload, int &plen) {
+  const uint64_t x = s.prev_bits ^ fb;
+  if (x == 0) {
+    hdr <<= 1;
+    hb += 1;
+    plen = 0;
+  } else {
+    int pl, pt;
+    lz_tz(s.prev_xor, pl, pt);
+    const int cl = __clzll((long long)x);
+    const int ct = __ffsll((long long)x) - 1;
+    if (cl >= pl && ct >= pt) {
+      hdr = (hdr << 2) | 2u;
+      hb += 2;
+      payload = x >> pt;
+      plen = 64 - pl - pt;
+    } else {
+      const int nm = 64 - cl - ct;
+      hdr = (hdr << 14) | (3u << 12) | ((uint32_t)cl << 6) | (uint32_t)(nm - 1);
+      hb += 14;
+      payload = x >> ct;
+      plen = nm;
+    }
+  }
+  s.prev_xor = x;
+  s.prev_bits = fb;
+}
+
+// value grammar: encoder.go:112-231.  Produces header bits appended to
+// (hdr, hb) and the payload.
+template <bool INT_OPT>
+__device__ __forceinline__ void encode_value(EncLane &s, double v, uint32_t &hdr, int &hb,
+                                             uint64_t &payload, int &plen) {
+  const bool first = (s.n_enc == 0);
+  const uint64_t vbits = (uint64_t)__double_as_longlong(v);
+  payload = 0;
+  plen = 0;
+  if (!INT_OPT) {
+    if (first) {  // writeFullFloat
+      s.prev_bits = vbits;
+      s.prev_xor = vbits;
+      payload = vbits;
+      plen = 64;
+    } else {
+      xor_code(s, vbits, hdr, hb, payload, plen);
+    }
+    return;
+  }
+  double val = v;
+  int mult = 0;
+  bool isf = true;
+  if (maybe_int(v)) convert_to_int_float(v, first ? 0 : s.max_mult, val, mult, isf);
+  if (first) {  // writeFirstValue :112-146
+    if (isf) {
+      hdr = (hdr << 1) | 1u;
+      hb += 1;
+      s.prev_bits = vbits;
+      s.prev_xor = vbits;
+      payload = vbits;
+      plen = 64;
+      s.is_float = true;
+      s.max_mult = mult;
+    } else {
+      hdr <<= 1;  // opcodeIntMode
+      hb += 1;
+      s.int_val = val;
+      uint32_t neg_diff = 1;
+      double a = val;
+      if (val < 0.0) {
+        neg_diff = 0;
+        a = -val;
+      }
+      const uint64_t vb = go_f64_to_u64_via_i64(a);
+      const int ns = num_sig(vb);
+      sig_mult_hdr(s, ns, mult, false, hdr, hb);
+      hdr = (hdr << 1) | neg_diff;
+      hb += 1;
+      payload = vb;
+      plen = s.num_sig;
+    }
+    return;
+  }
+  // writeNextValue :148-172
+  double diff = 0.0;
+  if (!isf) diff = __dsub_rn(s.int_val, val);
+  if (isf || diff >= 9223372036854775807.0 || diff <= -9223372036854775808.0) {
+    const uint64_t fb = (uint64_t)__double_as_longlong(val);  // writeFloatVal :176-198
+    if (!s.is_float) {
+      hdr = (hdr << 3) | 1u;  // update, no-repeat, float-mode
+      hb += 3;
+      s.prev_bits = fb;
+      s.prev_xor = fb;
+      payload = fb;
+      plen = 64;
+      s.is_float = true;
+      s.max_mult = mult;
+    } else if (fb == s.prev_bits) {
+      hdr = (hdr << 2) | 1u;  // update, repeat
+      hb += 2;
+    } else {
+      hdr = (hdr << 1) | 1u;  // no-update
+      hb += 1;
+      xor_code(s, fb, hdr, hb, payload, plen);
+    }
+    return;
+  }
+  // writeIntVal :201-231
+  if (diff == 0.0 && !s.is_float && mult == s.max_mult) {
+    hdr = (hdr << 2) | 1u;
+    hb += 2;
+    return;
+  }
+  uint32_t neg = 0;
+  if (diff < 0.0) {
+    neg = 1;
+    diff = -diff;
+  }
+  const uint64_t db = go_f64_to_u64_via_i64(diff);
+  const int ns = num_sig(db);
+  const int new_sig = track_new_sig(s, ns);
+  const bool float_changed = s.is_float;
+  if (mult > s.max_mult || s.num_sig != new_sig || float_changed) {
+    hdr <<= 3;  // update, no-repeat, int-mode
+    hb += 3;
+    sig_mult_hdr(s, new_sig, mult, float_changed, hdr, hb);
+    hdr = (hdr << 1) | neg;
+    hb += 1;
+    payload = db;
+    plen = s.num_sig;
+    s.is_float = false;
+  } else {
+    hdr = (hdr << 2) | 2u | neg;  // no-update + sign
+    hb += 2;
+    payload = db;
+    plen = s.num_sig;
+  }
+  s.int_val = val;
+}
+
+// timestamp grammar: timestamp_encoder.go:104-246 (annotation handled by caller).
+// Small codes are returned in (hdr, hb); 32/64-bit fields are written directly.
+__device__ __forceinline__ void encode_time(EncLane &s, uint32_t *tile, int lane, int64_t t, int u,
+                                            uint32_t &hdr, int &hb) {
+  hdr = 0;
+  hb = 0;
+  const int64_t delta = (int64_t)((uint64_t)t - (uint64_t)s.prev_time);
+  const int64_t dd = (int64_t)((uint64_t)delta - (uint64_t)s.prev_delta);
+  s.prev_time = t;
+  if (u != s.unit && unit_is_valid(u)) {  // maybeWriteTimeUnitChange :141-162
+    put32(s, tile, lane, (kMarkerOpcode << 2) | (uint32_t)kMarkerTimeUnit, kMarkerBits);
+    put32(s, tile, lane, (uint32_t)u, 8);
+    s.unit = u;
+    put64(s, tile, lane, (uint64_t)dd, 64);  // writeDeltaOfDeltaTimeUnitChanged :197-203
+    s.prev_delta = 0;
+    return;
+  }
+  if (!unit_is_valid(u)) {
+    s.err = M3TSZ_ERR_UNRECOGNIZED_UNIT;
+    s.prev_delta = delta;
+    return;
+  }
+  s.prev_delta = delta;
+  const int kind = scheme_kind_for_unit(u);
+  if (dd == 0) {
+    hb = (kind == kSchemeZero) ? 0 : 1;
+    return;
+  }
+  const int64_t dod = dd / unit_nanos(u);  // ToNormalizedDuration, x/time/time.go:55-57
+  if (u <= 2 && dod != (int64_t)(int32_t)dod) {
+    s.err = M3TSZ_ERR_DOD_OVERFLOW;
+    return;
+  }
+  if (kind == kSchemeZero) return;
+  if (dod == 0) {
+    hb = 1;
+  } else if (dod >= -64 && dod <= 63) {
+    hdr = (2u << 7) | ((uint32_t)dod & 0x7fu);
+    hb = 9;
+  } else if (dod >= -256 && dod <= 255) {
+    hdr = (6u << 9) | ((uint32_t)dod & 0x1ffu);
+    hb = 12;
+  } else if (dod >= -2048 && dod <= 2047) {
+    hdr = (14u << 12) | ((uint32_t)dod & 0xfffu);
+    hb = 16;
+  } else {
+    put32(s, tile, lane, 0xfu, 4);
+    put64(s, tile, lane, (uint64_t)dod, kind == kScheme32 ? 32 : 64);
+  }
+}
+
+template <bool INT_OPT>
+__global__ void __launch_bounds__(ENC_WARPS * 32) encode_kernel(const EncodeParams p) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint8_t *wbase = reinterpret_cast<uint8_t *>(smem) + warp * ENC_WARP_SMEM;
+  uint64_t *ts_tile = reinterpret_cast<uint64_t *>(wbase);
+  uint64_t *val_tile = ts_tile + ENC_IN_TILE_DWORDS;
+  uint32_t *out_tile = reinterpret_cast<uint32_t *>(val_tile + ENC_IN_TILE_DWORDS);
+
+  const uint64_t warp_s0 = ((uint64_t)blockIdx.x * ENC_WARPS + warp) * 32ull;
+  if (warp_s0 >= p.n_series) return;
+  const uint64_t sidx = warp_s0 + lane;
+  const bool valid = sidx < p.n_series;
+
+  EncLane s;
+  s.carry = 0;
+  s.sh = 0;
+  s.k = 0;
+  s.words_out = 0;
+  s.prev_time = 0;
+  s.prev_delta = 0;
+  s.prev_bits = 0;
+  s.prev_xor = 0;
+  s.int_val = 0.0;
+  s.unit = 0;
+  s.num_sig = 0;
+  s.hi_lower_sig = 0;
+  s.n_lower_sig = 0;
+  s.max_mult = 0;
+  s.err = 0;
+  s.n_enc = 0;
+  s.is_float = false;
+
+  uint32_t n_pts = 0;
+  uint64_t ann_i = 0, ann_end = 0;
+  uint64_t last_ann_off = 0;
+  uint32_t last_ann_len = 0;  // 0 = no annotation written yet
+  const uint32_t slot_words = (uint32_t)(p.out_stride >> 2);
+  if (valid) {
+    n_pts = p.n_points ? p.n_points[sidx] : (uint32_t)p.points_stride;
+    if (n_pts > p.points_stride) {
+      s.err = M3TSZ_ERR_INVALID_ARG;
+      n_pts = 0;
+    }
+    const int64_t start = p.start[sidx];
+    s.prev_time = start;
+    s.unit = initial_time_unit(start, p.default_unit);  // encoder.reset :268-272
+    if (p.ann_series_off) {
+      ann_i = p.ann_series_off[sidx];
+      ann_end = p.ann_series_off[sidx + 1];
+    }
+    if (n_pts > 0 && s.err == 0) {
+      if (slot_words < (uint32_t)ENC_GUARD + 4u) {
+        s.err = M3TSZ_ERR_CAPACITY;
+      } else {
+        put64(s, out_tile, lane, (uint64_t)start, 64);  // WriteFirstTime :89-102
+      }
+    }
+  }
+
+  // writes every lane's staged words to its slot (coalesced per series)
+  auto flush_out = [&]() {
+    __syncwarp();
+    uint8_t *my_dst = p.out + sidx * p.out_stride + (uint64_t)s.words_out * 4ull;
+#pragma unroll 2
+    for (int j = 0; j < 32; j++) {
+      const uint32_t kj = __shfl_sync(FULL_MASK, s.k, j);
+      uint8_t *dst = reinterpret_cast<uint8_t *>(
+          __shfl_sync(FULL_MASK, (unsigned long long)my_dst, j));
+      for (uint32_t i = lane; i < kj; i += 32) {
+        const uint32_t w = out_tile[i * ENC_STRIDE + j];
+        reinterpret_cast<uint32_t *>(dst)[i] = __byte_perm(w, 0, 0x0123);
+      }
+    }
+    __syncwarp();
+    s.words_out += s.k;
+    s.k = 0;
+  };
+
+  uint32_t iter = 0;
+  uint32_t in_row0 = 0;
+  bool in_valid = false;
+  for (;;) {
+    const bool active = valid && s.err == 0 && iter < n_pts;
+    if (!__any_sync(FULL_MASK, active)) break;
+
+    // ---- stage inputs: ENC_IN_T datapoints of each of the 32 series ----
+    if (!in_valid || iter - in_row0 == (uint32_t)ENC_IN_T) {
+      in_row0 = iter;
+      in_valid = true;
+      const int r = lane & (ENC_IN_T - 1);
+      const bool isval = lane >= ENC_IN_T;
+      const uint64_t *src0 = (isval ? reinterpret_cast<const uint64_t *>(p.val)
+                                    : reinterpret_cast<const uint64_t *>(p.ts)) +
+                             warp_s0 * p.points_stride + in_row0 + r;
+      uint64_t *tile = isval ? val_tile : ts_tile;
+      const uint32_t my_n = active ? n_pts : 0u;
+      __syncwarp();
+#pragma unroll 4
+      for (int j = 0; j < 32; j++) {
+        const uint32_t nj = __shfl_sync(FULL_MASK, my_n, j);
+        if (in_row0 + (uint32_t)r < nj) tile[r * ENC_STRIDE + j] = __ldg(src0 + (uint64_t)j * p.points_stride);
+      }
+      __syncwarp();
+    }
+
+    // ---- make room in the output tile ----
+    const bool tight = active && (s.k > (uint32_t)(ENC_OUT_W - ENC_GUARD));
+    if (__any_sync(FULL_MASK, tight)) flush_out();
+
+    // ---- annotations (warp-cooperative; timestamp_encoder.go:166-195) ----
+    bool want_ann = false;
+    uint64_t a_off = 0;
+    uint32_t a_len = 0;
+    if (active && ann_i < ann_end) {
+      const m3tsz_annotation_entry e = p.ann_entries[ann_i];
+      if (e.dp_index == iter) {
+        ann_i++;
+        a_off = e.byte_offset;
+        a_len = e.length;
+        if (a_len > 0) {
+          // rewritten only when it differs from the last annotation written
+          // (xxhash64 inequality in the reference == byte inequality here)
+          bool same = (a_len == last_ann_len);
+          for (uint32_t i = 0; same && i < a_len; i++)
+            same = p.ann_bytes[a_off + i] == p.ann_bytes[last_ann_off + i];
+          want_ann = !same;
+        }
+      }
+    }
+    if (__any_sync(FULL_MASK, want_ann)) {
+      uint32_t rem = 0, done_bytes = 0;
+      if (want_ann) {
+        put32(s, out_tile, lane, (kMarkerOpcode << 2) | (uint32_t)kMarkerAnnotation, kMarkerBits);
+        uint64_t ux = ((uint64_t)(a_len - 1)) << 1;  // binary.PutVarint(len-1), len >= 1
+        while (ux >= 0x80) {
+          put32(s, out_tile, lane, (uint32_t)(ux & 0x7f) | 0x80u, 8);
+          ux >>= 7;
+        }
+        put32(s, out_tile, lane, (uint32_t)ux, 8);
+        rem = a_len;
+        last_ann_off = a_off;
+        last_ann_len = a_len;
+      }
+      for (;;) {
+        if (rem > 0) {
+          // capacity: stop this series rather than overrun its slot
+          const uint64_t need_words = (uint64_t)s.words_out + s.k + (rem + 3) / 4 + ENC_GUARD + 4;
+          if (need_words > slot_words) {
+            s.err = M3TSZ_ERR_CAPACITY;
+            rem = 0;
+          }
+        }
+        while (rem > 0 && s.k < (uint32_t)(ENC_OUT_W - ENC_GUARD)) {
+          put32(s, out_tile, lane, (uint32_t)p.ann_bytes[a_off + done_bytes], 8);
+          done_bytes++;
+          rem--;
+        }
+        if (!__any_sync(FULL_MASK, rem > 0)) break;
+        flush_out();
+      }
+    }
+
+    // ---- encode one datapoint ----
+    if (active && s.err == 0) {
+      if ((uint64_t)s.words_out + s.k + ENC_GUARD + 4 > slot_words) {
+        s.err = M3TSZ_ERR_CAPACITY;
+      } else {
+        const int row = (int)(iter - in_row0);
+        const int64_t t = (int64_t)ts_tile[row * ENC_STRIDE + lane];
+        const double v = __longlong_as_double((long long)val_tile[row * ENC_STRIDE + lane]);
+        const int u = p.units ? (int)p.units[sidx * p.points_stride + iter] : p.unit;
+        uint32_t hdr;
+        int hb;
+        encode_time(s, out_tile, lane, t, u, hdr, hb);
+        if (s.err == 0) {
+          uint64_t payload;
+          int plen;
+          encode_value<INT_OPT>(s, v, hdr, hb, payload, plen);
+          emit_code(s, out_tile, lane, hdr, hb, payload, plen);
+          s.n_enc++;
+        }
+      }
+    }
+    iter++;
+  }
+
+  // ---- tail: end-of-stream marker + zero padding (scheme.go:198-211) ----
+  uint64_t total_bits = 0;
+  if (valid && s.n_enc > 0) {
+    put32(s, out_tile, lane, (kMarkerOpcode << 2) | (uint32_t)kMarkerEOS, kMarkerBits);
+    total_bits = ((uint64_t)s.words_out + s.k) * 32ull + s.sh;
+    if (s.sh > 0) {  // flush the partial word (zero padded)
+      out_tile[s.k * ENC_STRIDE + lane] = s.carry;
+      s.k++;
+      s.carry = 0;
+      s.sh = 0;
+    }
+  } else if (valid) {
+    s.k = 0;  // nothing encoded: empty stream (encoder.go:285-289)
+    s.words_out = 0;
+  }
+  flush_out();
+  if (valid) {
+    if (p.out_len) p.out_len[sidx] = (total_bits + 7) >> 3;
+    if (p.status) p.status[sidx] = s.err;
+  }
+}
+
+cudaError_t launch_encode(const EncodeParams &p, bool int_optimized, cudaStream_t stream) {
+  constexpr size_t smem = ENC_WARP_SMEM * ENC_WARPS;
+  const uint64_t per_block = (uint64_t)ENC_WARPS * 32ull;
+  const uint64_t blocks = (p.n_series + per_block - 1) / per_block;
+  if (blocks == 0) return cudaSuccess;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (int_optimized) {
+    e = cudaFuncSetAttribute(encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    encode_kernel<true><<<(unsigned)blocks, ENC_WARPS * 32, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    encode_kernel<false><<<(unsigned)blocks, ENC_WARPS * 32, smem, stream>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// compaction: slots -> packed buffer with CSR offsets
+// ---------------------------------------------------------------------------
+__global__ void compact_lens_kernel(const uint64_t *len, uint64_t n, uint64_t mask, uint64_t *out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (len[i] + mask) & ~mask;
+  if (i == n) out[i] = 0;
+}
+
+__global__ void compact_gather_kernel(const uint8_t *slots, uint64_t slot_stride, const uint64_t *len,
+                                      uint64_t n, uint8_t *packed, uint64_t cap,
+                                      const uint64_t *offsets, int32_t *overflow) {
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const uint64_t o = offsets[w], l = len[w];
+  if (o + l > cap) {
+    if (lane == 0) atomicExch(overflow, 1);
+    return;
+  }
+  const uint8_t *src = slots + w * slot_stride;
+  uint8_t *dst = packed + o;
+  if ((((uintptr_t)dst | (uintptr_t)src) & 3u) == 0) {
+    const uint64_t nw = l >> 2;
+    for (uint64_t i = lane; i < nw; i += 32)
+      reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+    for (uint64_t i = (nw << 2) + lane; i < l; i += 32) dst[i] = src[i];
+  } else {
+    for (uint64_t i = lane; i < l; i += 32) dst[i] = src[i];
+  }
+}
+
+size_t compact_scan_tmp_bytes(uint64_t n_series) {
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, (uint64_t *)nullptr, (uint64_t *)nullptr,
+                                (int)(n_series + 1));
+  return tmp + (n_series + 1) * sizeof(uint64_t);
+}
+
+cudaError_t launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint64_t *len,
+                           uint64_t n_series, uint32_t align, uint8_t *packed,
+                           uint64_t packed_capacity, uint64_t *offsets, void *scan_tmp,
+                           size_t scan_tmp_bytes, int32_t *overflow_flag, cudaStream_t stream) {
+  if (n_series + 1 > 0x7fffffffull) return cudaErrorInvalidValue;
+  uint64_t *alen = reinterpret_cast<uint64_t *>(scan_tmp);
+  void *cub_tmp = reinterpret_cast<uint8_t *>(scan_tmp) + (n_series + 1) * sizeof(uint64_t);
+  size_t cub_bytes = scan_tmp_bytes - (n_series + 1) * sizeof(uint64_t);
+  const uint64_t mask = (uint64_t)align - 1;
+  const unsigned tb = 256;
+  compact_lens_kernel<<<(unsigned)((n_series + 1 + tb - 1) / tb), tb, 0, stream>>>(len, n_series, mask, alen);
+  cudaError_t e = cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, alen, offsets, (int)(n_series + 1), stream);
+  if (e != cudaSuccess) return e;
+  if (n_series == 0) return cudaGetLastError();
+  const uint64_t threads = n_series * 32ull;
+  compact_gather_kernel<<<(unsigned)((threads + tb - 1) / tb), tb, 0, stream>>>(
+      slots, slot_stride, len, n_series, packed, packed_capacity, offsets, overflow_flag);
+  return cudaGetLastError();
+}
+
+}  // namespace m3tsz

@@ -1,0 +1,67 @@
+// m3tsz_kernels.h -- internal launch interface between the C-ABI layer
+// (m3tsz_capi.cu) and the kernels (m3tsz_decode.cu, m3tsz_encode.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/m3tsz_b200.h"
+
+namespace m3tsz {
+
+struct DecodeParams {
+  const uint8_t *streams;
+  uint64_t streams_bytes;
+  const uint64_t *offsets;
+  uint64_t n_series;
+  int default_unit;
+  // plain decode outputs (series-major [n_series][cap])
+  int64_t *ts;
+  double *val;
+  uint64_t cap;
+  // fused downsample outputs (window-major [n_windows][n_series])
+  int64_t range_start, window;
+  uint32_t n_windows;
+  double *ds_sum;
+  int64_t *ds_count;
+  double *ds_min;
+  double *ds_max;
+  // per-series outputs
+  uint32_t *n_points;
+  int32_t *status;
+  uint8_t *unit_out;
+  m3tsz_annotation_ref *ann_out;
+};
+
+cudaError_t launch_decode(const DecodeParams &p, bool int_optimized, bool downsample,
+                          cudaStream_t stream);
+
+struct EncodeParams {
+  const int64_t *ts;
+  const double *val;
+  uint64_t n_series;
+  uint64_t points_stride;
+  const uint32_t *n_points;  // optional
+  const int64_t *start;
+  int unit;
+  const uint8_t *units;  // optional per-datapoint units
+  const uint64_t *ann_series_off;
+  const m3tsz_annotation_entry *ann_entries;
+  const uint8_t *ann_bytes;
+  int default_unit;
+  uint8_t *out;
+  uint64_t out_stride;
+  uint64_t *out_len;
+  int32_t *status;
+};
+
+cudaError_t launch_encode(const EncodeParams &p, bool int_optimized, cudaStream_t stream);
+
+// exclusive scan of aligned lengths + gather into a packed buffer
+cudaError_t launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint64_t *len,
+                           uint64_t n_series, uint32_t align, uint8_t *packed,
+                           uint64_t packed_capacity, uint64_t *offsets, void *scan_tmp,
+                           size_t scan_tmp_bytes, int32_t *overflow_flag, cudaStream_t stream);
+size_t compact_scan_tmp_bytes(uint64_t n_series);
+
+}  // namespace m3tsz

@@ -1,0 +1,467 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and
+the reference's golden vectors.  Bit-exact: bytes for encode, (int64, float64
+bit pattern) for decode."""
+import base64
+import json
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "m3tsz_goldens.json")))
+SEC = 1_000_000_000
+
+
+def hb(s):
+    return bytes.fromhex(s)
+
+
+@pytest.fixture(scope="module")
+def codecs():
+    from m3_b200.codec import BatchCodec
+    return {True: BatchCodec(0, True), False: BatchCodec(0, False)}
+
+
+def to_device_streams(streams):
+    """Packs streams back to back (CSR, unaligned starts) and uploads."""
+    blob = b"".join(streams)
+    off = np.zeros(len(streams) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(s) for s in streams])
+    buf = torch.zeros(len(blob) + 16, dtype=torch.uint8, device="cuda")
+    if blob:
+        buf[: len(blob)] = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
+    return buf[: len(blob)], torch.from_numpy(off).cuda(), len(blob)
+
+
+def gpu_decode(codec, streams, cap):
+    d, off, nbytes = to_device_streams(streams)
+    r = codec.decode(d, off, cap, want_annotations=True)
+    torch.cuda.synchronize()
+    return (r.ts.cpu().numpy(), r.values.cpu().numpy().view(np.uint64),
+            r.n_points.cpu().numpy().view(np.uint32), r.status.cpu().numpy(), r.unit.cpu().numpy(),
+            r.annotations.cpu().numpy())
+
+
+def oracle_decode(stream, int_opt):
+    dps, err = O.decode_all(stream, int_opt)
+    ts = np.array([d[0] for d in dps], dtype=np.int64)
+    vals = np.array([d[1] for d in dps], dtype=np.float64).view(np.uint64)
+    return ts, vals, err, dps
+
+
+def check_decode_against_oracle(codec, streams, int_opt, cap=2048):
+    ts, vals, n, st, unit, ann = gpu_decode(codec, streams, cap)
+    for i, s in enumerate(streams):
+        ots, ovals, oerr, dps = oracle_decode(s, int_opt)
+        assert n[i] == len(ots), (i, n[i], len(ots))
+        assert st[i] == oerr, (i, st[i], oerr)
+        assert (ts[i, : n[i]] == ots).all(), i
+        assert (vals[i, : n[i]] == ovals).all(), i
+        if dps:
+            assert unit[i] == dps[-1][2], i
+    return ts, vals, n, st, unit, ann
+
+
+# ------------------------------------------------------------------ goldens
+def test_decode_golden_streams(codecs):
+    streams = [hb(s["bytes"]) for s in G["streams"]]
+    ts, vals, n, st, unit, ann = check_decode_against_oracle(codecs[False], streams, False)
+    for i, s in enumerate(G["streams"]):
+        assert n[i] == len(s["datapoints"]) and st[i] == 0
+        for j, dp in enumerate(s["datapoints"]):
+            assert ts[i, j] == dp["ts"]
+            assert vals[i, j] == np.float64(dp["value"]).view(np.uint64)
+        # first annotation reference
+        bit_off, length, count = struct.unpack("<QII", ann[i].tobytes())
+        exp = [a for a in s["decoded_annotations"] if a]
+        assert count == len(exp)
+        if exp:
+            bits = int.from_bytes(streams[i], "big")
+            total = len(streams[i]) * 8
+            got = bytes(((bits >> (total - (bit_off + 8 * (k + 1)))) & 0xFF) for k in range(length))
+            assert got == hb(exp[0])
+
+
+def test_decode_fixtures_and_regression(codecs):
+    streams = [base64.b64decode(s) for s in G["fixtures_b64"]["streams"]]
+    streams.append(base64.b64decode(G["regression_b64"]["stream"]))
+    ts, vals, n, st, unit, _ = check_decode_against_oracle(codecs[True], streams, True)
+    assert list(n[:10]) == G["fixtures_b64"]["expected_points"]
+    assert n[10] == 150 and (st == 0).all()
+
+
+def test_encode_golden_streams_via_facade(codecs):
+    from m3_b200.encoding import Encoder, ReaderIterator
+    for s in G["streams"]:
+        e = Encoder(s["encoder_start"], s["int_optimized"])
+        assert e.stream() is None and e.len() == 0 and e.empty()
+        for dp in s["datapoints"]:
+            e.encode(dp["ts"], dp["value"], dp["unit"], hb(dp["annotation"]))
+        assert e.stream() == hb(s["bytes"]), s["name"]
+        assert e.len() == len(hb(s["bytes"]))
+        assert e.num_encoded() == len(s["datapoints"])
+        it = ReaderIterator(hb(s["bytes"]), s["int_optimized"])
+        got = []
+        while it.next():
+            got.append(it.current()[:2])
+        assert it.err() == 0
+        assert got == [(dp["ts"], float(dp["value"])) for dp in s["datapoints"]]
+        exp = [a for a in s["decoded_annotations"] if a]
+        assert it.first_annotation() == (hb(exp[0]) if exp else None)
+
+
+def test_reencode_fixtures_byte_identical(codecs):
+    """decode (GPU) -> re-encode (GPU) with the stream's own start/unit/annotations ==
+    the reference's fixture bytes (the byte-level pin for intOptimized=true)."""
+    from m3_b200.encoding import Encoder
+    streams = [base64.b64decode(s) for s in G["fixtures_b64"]["streams"]]
+    streams.append(base64.b64decode(G["regression_b64"]["stream"]))
+    for data in streams[:10]:
+        dps, err = O.decode_all(data, True)
+        start = struct.unpack(">q", data[:8])[0]
+        e = Encoder(start, True)
+        for t, v, u, a in dps:
+            e.encode(t, v, u, a)
+        assert e.stream() == data
+
+
+# ------------------------------------------------------------------ batch parity vs oracle
+def _mixed_series(rng, S, P):
+    """Series families that exercise every branch of the value grammar."""
+    start = 1599955200 * SEC
+    ts = np.zeros((S, P), dtype=np.int64)
+    vals = np.zeros((S, P), dtype=np.float64)
+    for s in range(S):
+        fam = s % 12
+        if fam in (0, 1):  # regular cadence
+            ts[s] = start + np.arange(P) * 60 * SEC
+        elif fam in (2, 3):  # jittered seconds
+            ts[s] = start + np.cumsum(rng.integers(1, 120, size=P)) * SEC
+        elif fam == 4:  # large gaps (default bucket)
+            ts[s] = start + np.cumsum(rng.integers(1, 100000, size=P)) * SEC
+        else:
+            ts[s] = start + np.arange(P) * 10 * SEC + rng.integers(0, 2, size=P) * SEC
+        walk = 100.0 + np.cumsum(rng.normal(size=P))
+        if fam in (0, 2, 4):
+            vals[s] = walk
+        elif fam == 1:
+            vals[s] = np.round(walk)  # ints
+        elif fam == 3:
+            vals[s] = np.round(walk, 2)  # 2 decimals
+        elif fam == 5:
+            vals[s] = np.round(walk * 1000) / 1000
+        elif fam == 6:
+            vals[s] = np.repeat(np.round(walk[: (P + 7) // 8], 1), 8)[:P]  # repeats
+        elif fam == 7:
+            v = np.round(walk)
+            v[rng.integers(0, P, size=max(1, P // 50))] += 0.123456789  # int<->float switches
+            vals[s] = v
+        elif fam == 8:
+            v = walk.copy()
+            v[rng.integers(0, P, size=5)] = np.nan
+            v[rng.integers(0, P, size=3)] = np.inf
+            v[rng.integers(0, P, size=3)] = -np.inf
+            v[rng.integers(0, P, size=3)] = -0.0
+            vals[s] = v
+        elif fam == 9:
+            vals[s] = np.round(rng.normal(size=P) * 1e6) * (10.0 ** rng.integers(0, 9))  # big ints
+        elif fam == 10:
+            v = np.round(walk)
+            idx = rng.integers(0, P, size=4)
+            v[idx] = [2.0 ** 63, -(2.0 ** 63), 1e300, -1e300][: len(idx)]
+            vals[s] = v
+        else:
+            vals[s] = -np.round(np.abs(walk) * 100) / 100  # negative decimals
+    return ts, vals, start
+
+
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_batch_encode_decode_mixed_vs_oracle(codecs, int_opt):
+    rng = np.random.default_rng(11)
+    S, P = 384, 333
+    ts, vals, start = _mixed_series(rng, S, P)
+    codec = codecs[int_opt]
+    o_out, o_len, o_st = O.encode_batch(ts, vals, start, O.UNIT_S, int_opt, n_threads=8)
+    assert (o_st == 0).all()
+    d_ts = torch.from_numpy(ts).cuda()
+    d_vals = torch.from_numpy(vals).cuda()
+    d_start = torch.full((S,), start, dtype=torch.int64, device="cuda")
+    enc = codec.encode(d_ts, d_vals, d_start, unit=O.UNIT_S)
+    torch.cuda.synchronize()
+    g_len = enc.out_len.cpu().numpy()
+    g_st = enc.status.cpu().numpy()
+    g_out = enc.out.cpu().numpy()
+    assert (g_st == 0).all(), g_st[g_st != 0]
+    for s in range(S):
+        assert g_len[s] == o_len[s], (s, s % 12, g_len[s], o_len[s])
+        assert (g_out[s, : g_len[s]] == o_out[s, : o_len[s]]).all(), (s, s % 12)
+    # compaction + decode of the GPU streams
+    packed, offsets = codec.compact(enc, align=1)
+    torch.cuda.synchronize()
+    total = int(offsets[-1].item())
+    assert total == int(g_len.sum())
+    dec = codec.decode(packed, offsets, P + 3)
+    torch.cuda.synchronize()
+    assert (dec.status.cpu().numpy() == 0).all()
+    assert (dec.n_points.cpu().numpy() == P).all()
+    assert (dec.ts[:, :P].cpu().numpy() == ts).all()
+    # decoded values must equal what the ORACLE decodes (int mode is lossy for -0.0 etc.)
+    gv = dec.values[:, :P].cpu().numpy().view(np.uint64)
+    for s in range(S):
+        _, ovals, oerr, _ = oracle_decode(o_out[s, : o_len[s]].tobytes(), int_opt)
+        assert oerr == 0
+        assert (gv[s] == ovals).all(), (s, s % 12)
+
+
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_gaussian_walk_batch_bitexact(codecs, int_opt):
+    from m3_b200 import synth
+    S, P = 4096, 1440
+    ts, vals, start = synth.gaussian_walk(S, P, "cuda", seed=5)
+    codec = codecs[int_opt]
+    enc = codec.encode(ts, vals, start, unit=O.UNIT_S)
+    torch.cuda.synchronize()
+    assert (enc.status == 0).all()
+    h_ts, h_vals = ts.cpu().numpy(), vals.cpu().numpy()
+    o_out, o_len, o_st = O.encode_batch(h_ts, h_vals, int(start[0].item()), O.UNIT_S, int_opt,
+                                        n_threads=8)
+    g_len = enc.out_len.cpu().numpy()
+    g_out = enc.out.cpu().numpy()
+    assert (g_len == o_len.astype(np.int64)).all()
+    for s in range(S):
+        assert (g_out[s, : g_len[s]] == o_out[s, : o_len[s]]).all(), s
+    packed, offsets = codec.compact(enc, align=16)
+    dec = codec.decode(packed, offsets, P)
+    torch.cuda.synchronize()
+    assert (dec.status == 0).all() and (dec.n_points == P).all()
+    assert torch.equal(dec.ts, ts)
+    assert torch.equal(dec.values.view(torch.int64), vals.view(torch.int64))
+
+
+def test_ragged_lengths_units_and_unaligned(codecs):
+    rng = np.random.default_rng(5)
+    for int_opt in (True, False):
+        streams = []
+        expect = []
+        for i in range(100):
+            n = int(rng.integers(0, 70))
+            unit = [O.UNIT_S, O.UNIT_MS, O.UNIT_US, O.UNIT_NS][i % 4]
+            un = {1: SEC, 2: 10 ** 6, 3: 10 ** 3, 4: 1}[unit]
+            start = 1599955200 * SEC + (int(rng.integers(0, 1000)) if i % 5 == 0 else 0)
+            e = O.Encoder(0, int_opt)
+            e.reset(start)
+            t = start
+            for j in range(n):
+                t += int(rng.integers(1, 5000)) * un
+                v = float(np.round(rng.normal() * 100, int(rng.integers(0, 4))))
+                if rng.random() < 0.1:
+                    v = float(rng.normal())
+                u = unit if rng.random() < 0.95 else O.UNIT_NS
+                assert e.encode(t, v, u, b"ann%d" % j if rng.random() < 0.05 else b"") == 0
+            s = e.stream() or b""
+            streams.append(s)
+        check_decode_against_oracle(codecs[int_opt], streams, int_opt, cap=128)
+
+
+def test_truncated_and_corrupt_streams(codecs):
+    # float mode: every byte-truncation of the golden streams behaves like the reference
+    streams = []
+    for s in G["streams"]:
+        b = hb(s["bytes"])
+        for cut in range(0, len(b)):
+            streams.append(b[:cut])
+    check_decode_against_oracle(codecs[False], streams, False, cap=64)
+    # raw encoder buffer without the end-of-stream tail: all points, then io.EOF
+    s0 = G["streams"][0]
+    ts, vals, n, st, _, _ = gpu_decode(codecs[False], [hb(s0["raw"])], 64)
+    assert n[0] == len(s0["datapoints"]) and st[0] == O.ERR_EOF
+    # reference error streams (iterator_test.go:265-269,387-394)
+    for c in G["iterator_error_streams"]["cases"]:
+        ts, vals, n, st, _, _ = gpu_decode(codecs[False], [hb(c["bytes"])], 64)
+        assert n[0] == 0 and st[0] != 0
+    # int mode: truncations must report an error (or a clean prefix) and never crash
+    f = base64.b64decode(G["fixtures_b64"]["streams"][0])
+    cuts = [f[:c] for c in range(1, len(f), 7)]
+    ts, vals, n, st, _, _ = gpu_decode(codecs[True], cuts, 1024)
+    assert (st != 0).all()
+    full, _, _, _ = oracle_decode(f, True)
+    for i in range(len(cuts)):
+        k = int(n[i])
+        assert k <= len(full) and (ts[i, :k] == full[:k]).all()
+
+
+def test_capacity_status(codecs):
+    s = hb(G["streams"][0]["bytes"])
+    ts, vals, n, st, _, _ = gpu_decode(codecs[False], [s, s], 3)
+    assert (n == 7).all() and (st == 100).all()
+    ots, _, _, _ = oracle_decode(s, False)
+    assert (ts[0, :3] == ots[:3]).all()
+
+
+def test_encode_errors_and_dod_overflow(codecs):
+    start = 1427162400 * SEC
+    P = 4
+    ts = np.array([[start, start + 1000 * 25 * 24 * 3600 * SEC, 0, 0],
+                   [start, start + 3600 * SEC, start + 7200 * SEC, start + 7201 * SEC]], dtype=np.int64)
+    vals = np.ones((2, P))
+    npts = torch.tensor([2, 4], dtype=torch.int32, device="cuda")
+    enc = codecs[False].encode(torch.from_numpy(ts).cuda(), torch.from_numpy(vals).cuda(),
+                               torch.full((2,), start, dtype=torch.int64, device="cuda"),
+                               unit=O.UNIT_S, n_points=npts)
+    torch.cuda.synchronize()
+    st = enc.status.cpu().numpy()
+    assert st[0] == O.ERR_DOD_OVERFLOW and st[1] == 0
+    # series 0 holds the datapoints before the failing one
+    ln = enc.out_len.cpu().numpy()
+    dps, err = O.decode_all(enc.out[0, : ln[0]].cpu().numpy().tobytes(), False)
+    assert err == 0 and [(d[0], d[1]) for d in dps] == [(start, 1.0)]
+    dps, err = O.decode_all(enc.out[1, : ln[1]].cpu().numpy().tobytes(), False)
+    assert err == 0 and [d[0] for d in dps] == list(ts[1])
+    # invalid unit -> errUnrecognizedTimeUnit
+    enc = codecs[False].encode(torch.from_numpy(ts).cuda(), torch.from_numpy(vals).cuda(),
+                               torch.full((2,), start, dtype=torch.int64, device="cuda"),
+                               unit=0, n_points=npts)
+    torch.cuda.synchronize()
+    assert (enc.status.cpu().numpy() == 6).all()
+    # too-small slot -> capacity status, no overrun
+    enc = codecs[False].encode(torch.from_numpy(ts).cuda(), torch.from_numpy(vals).cuda(),
+                               torch.full((2,), start, dtype=torch.int64, device="cuda"),
+                               unit=O.UNIT_S, n_points=npts, out_stride=32)
+    torch.cuda.synchronize()
+    assert (enc.status.cpu().numpy() == 100).all()
+
+
+def test_facade_roundtrip_and_errors(codecs):
+    from m3_b200 import capi
+    from m3_b200.encoding import Decoder, Encoder
+    # roundtrip_test.go:114-181 shape: unit changes + annotations, both modes
+    rng = np.random.default_rng(2)
+    for int_opt in (True, False):
+        t = 1427162462 * SEC
+        e = Encoder(1427162400 * SEC, int_opt)
+        o = O.Encoder(1427162400 * SEC, int_opt)
+        dps = []
+        for i in range(60):
+            t += int(rng.integers(1, 1200)) * SEC
+            v = float(np.round(rng.normal() * 50, 2))
+            unit = O.UNIT_MS if i == 0 else (O.UNIT_US if i == 10 else O.UNIT_S)
+            ann = b"foo" if i < 5 else (b"bar" if i < 7 else (b"long annotation " * 4 if i == 10 else b""))
+            e.encode(t, v, unit, ann)
+            assert o.encode(t, v, unit, ann) == 0
+            dps.append((t, v))
+        assert e.stream() == o.stream()
+        assert e.last_annotation_checksum() == o.last_annotation_checksum()[0]
+        it = Decoder(int_opt).decode(e.stream())
+        got = []
+        while it.next():
+            got.append(it.current()[:2])
+        assert it.err() == 0 and got == dps
+    e = Encoder(1427162400 * SEC, False)
+    e.encode(1427162400 * SEC, 1.0, O.UNIT_S)
+    with pytest.raises(capi.M3tszError) as ei:
+        e.encode(1427162400 * SEC + 1000 * 25 * 24 * 3600 * SEC, 2.0, O.UNIT_S)
+    assert "deltaOfDelta value 2160000000 s overflows 32 bits" in str(ei.value)
+    e.close()
+    with pytest.raises(capi.M3tszError):
+        e.encode(0, 1.0, O.UNIT_S)
+
+
+# ------------------------------------------------------------------ fused downsample
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_decode_downsample_vs_oracle(codecs, int_opt):
+    rng = np.random.default_rng(9)
+    S, P = 200, 300
+    ts, vals, start = _mixed_series(rng, S, P)
+    # out-of-order timestamps in a few series (legal inside one stream)
+    for s in range(0, S, 17):
+        i = rng.integers(10, P - 10)
+        ts[s, i], ts[s, i - 5] = ts[s, i - 5], ts[s, i]
+    o_out, o_len, o_st = O.encode_batch(ts, vals, start, O.UNIT_S, int_opt, n_threads=8)
+    streams = [o_out[s, : o_len[s]].tobytes() for s in range(S)]
+    d, off, nbytes = to_device_streams(streams)
+    window = 300 * SEC
+    n_win = 40
+    r = codecs[int_opt].decode_downsample(d, off, start, window, n_win)
+    torch.cuda.synchronize()
+    assert (r.status == 0).all() and (r.n_points == P).all()
+    gs, gc = r.sum.cpu().numpy(), r.count.cpu().numpy()
+    gmn, gmx = r.min.cpu().numpy(), r.max.cpu().numpy()
+    for s in range(S):
+        ots, ovals, _, _ = oracle_decode(streams[s], int_opt)
+        es, ec, emn, emx, _ = O.downsample_series(ots, ovals.view(np.float64), start, window, n_win)
+        assert (gc[:, s] == ec).all(), s
+        assert (gs[:, s].view(np.uint64) == es.view(np.uint64)).all(), s
+        assert (gmn[:, s].view(np.uint64) == emn.view(np.uint64)).all(), s
+        assert (gmx[:, s].view(np.uint64) == emx.view(np.uint64)).all(), s
+
+
+# ------------------------------------------------------------------ host-buffer entry points
+def test_host_entry_points(codecs):
+    from m3_b200 import synth
+    S, P = 1000, 200
+    ts, vals, start = synth.gaussian_walk(S, P, "cpu", seed=3)
+    codec = codecs[True]
+    stride = codec.encode_bound(P)
+    h_out = torch.empty((S, stride), dtype=torch.uint8).pin_memory()
+    h_len = torch.empty(S, dtype=torch.int64).pin_memory()
+    h_st = torch.empty(S, dtype=torch.int32).pin_memory()
+    codec.encode_host(ts.pin_memory(), vals.pin_memory(), start, O.UNIT_S, h_out, h_len, h_st)
+    assert (h_st == 0).all()
+    o_out, o_len, _ = O.encode_batch(ts.numpy(), vals.numpy(), int(start[0]), O.UNIT_S, True, n_threads=4)
+    assert (h_len.numpy() == o_len.astype(np.int64)).all()
+    streams = [h_out[s, : h_len[s]].numpy().tobytes() for s in range(S)]
+    assert all(streams[s] == o_out[s, : o_len[s]].tobytes() for s in range(S))
+    blob = b"".join(streams)
+    off = np.zeros(S + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(s) for s in streams])
+    h_streams = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    h_ts = torch.empty((S, P), dtype=torch.int64)
+    h_vals = torch.empty((S, P), dtype=torch.float64)
+    h_n = torch.empty(S, dtype=torch.int32)
+    codec.decode_host(h_streams, torch.from_numpy(off), P, h_ts, h_vals, h_n, h_st)
+    assert (h_st == 0).all() and (h_n == P).all()
+    assert torch.equal(h_ts, ts) and torch.equal(h_vals.view(torch.int64), vals.view(torch.int64))
+    W = 40
+    outs = [torch.empty((W, S), dtype=dt) for dt in (torch.float64, torch.int64, torch.float64, torch.float64)]
+    codec.decode_downsample_host(h_streams, torch.from_numpy(off), int(start[0]), 300 * SEC, W,
+                                 outs[0], outs[1], outs[2], outs[3], h_n, h_st)
+    assert (h_st == 0).all() and int(outs[1].sum()) == S * P
+    es, ec, emn, emx, _ = O.downsample_series(ts[7].numpy(), vals[7].numpy(), int(start[0]), 300 * SEC, W)
+    assert (outs[0][:, 7].numpy() == es).all() and (outs[1][:, 7].numpy() == ec).all()
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_roundtrip_properties(codecs):
+    """BASELINE config 2 size (100k x 1440): encode -> decode round trip is the
+    identity, stream lengths are self-consistent, and a sample of series is
+    byte-identical to the oracle."""
+    from m3_b200 import synth
+    S, P = 100_000, 1440
+    codec = codecs[True]
+    ts, vals, start = synth.gaussian_walk(S, P, "cuda", seed=77)
+    enc = codec.encode(ts, vals, start, unit=O.UNIT_S)
+    assert int((enc.status != 0).sum()) == 0
+    packed, offsets = codec.compact(enc, align=16)
+    total = int(offsets[-1].item())
+    bpd = float(enc.out_len.sum().item()) / (S * P)
+    assert 6.5 < bpd < 8.0, bpd  # ~7.3 B/dp for the Gaussian walk
+    dec = codec.decode(packed, offsets, P)
+    torch.cuda.synchronize()
+    assert int((dec.status != 0).sum()) == 0 and bool((dec.n_points == P).all())
+    assert torch.equal(dec.ts, ts)
+    assert torch.equal(dec.values.view(torch.int64), vals.view(torch.int64))
+    idx = np.random.default_rng(1).integers(0, S, size=64)
+    h_ts, h_vals = ts[idx].cpu().numpy(), vals[idx].cpu().numpy()
+    o_out, o_len, _ = O.encode_batch(h_ts, h_vals, int(start[0].item()), O.UNIT_S, True, n_threads=8)
+    g_len = enc.out_len[idx].cpu().numpy()
+    g_out = enc.out[idx].cpu().numpy()
+    for k in range(len(idx)):
+        assert g_len[k] == o_len[k] and (g_out[k, : g_len[k]] == o_out[k, : o_len[k]]).all()
+    assert total >= int(enc.out_len.sum().item())
