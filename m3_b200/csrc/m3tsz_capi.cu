@@ -152,7 +152,8 @@ int m3tsz_decode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t 
   if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
   if (n_series == 0) return M3TSZ_OK;
   if (!d_streams || !d_offsets || !d_ts || !d_val || max_points == 0 ||
-      max_points > 0xffffffffull || ((uintptr_t)d_streams & 15u))
+      max_points > 0xffffffffull || ((uintptr_t)d_streams & 15u) ||
+      streams_bytes >= (1ull << 34))  // 32-bit word indices inside the kernel; split larger batches
     return M3TSZ_ERR_INVALID_ARG;
   CK(cudaSetDevice(ctx->device));
   DecodeParams p;
@@ -183,7 +184,7 @@ int m3tsz_decode_downsample_batch(m3tsz_ctx *ctx, const m3tsz_options *opts,
   if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
   if (n_series == 0) return M3TSZ_OK;
   if (!d_streams || !d_offsets || !d_sum || !d_count || !d_min || !d_max || window_ns <= 0 ||
-      n_windows == 0 || ((uintptr_t)d_streams & 15u))
+      n_windows == 0 || ((uintptr_t)d_streams & 15u) || streams_bytes >= (1ull << 34))
     return M3TSZ_ERR_INVALID_ARG;
   // range_start + n_windows*window must not overflow int64
   if ((__int128)range_start_ns + (__int128)n_windows * (__int128)window_ns > (__int128)INT64_MAX)

@@ -3,11 +3,12 @@
 // Mapping: one LANE per series, 32 series per warp.  A stream is
 // a serial bit-dependency chain (every field width depends on decoded state),
 // so the per-series state machine runs on one lane while the WARP cooperates
-// on memory: each lane's compressed words are staged into shared memory with
-// coalesced 128-byte global loads (transposed [word][lane] tile, stride 33),
-// every datapoint is parsed from four shared-memory words with funnel shifts,
-// and decoded (ts, value) pairs go through a second transposed tile so global
-// stores are 128-byte coalesced per series.
+// on memory: each lane's compressed words are staged into a shared-memory ring
+// ([word][lane], stride 33) by asynchronous 128-byte-coalesced copies
+// (cp.async / LDGSTS) issued one refill ahead of consumption, every datapoint
+// is parsed branch-free from four ring words with funnel shifts, and decoded
+// (ts, value) pairs go through a second transposed tile so global stores are
+// coalesced per series.
 //
 // Format: SURVEY.md Appendix A; reference decode path
 //   m3tsz/iterator.go:81-219, m3tsz/timestamp_iterator.go:80-326,
@@ -17,14 +18,16 @@
 
 namespace m3tsz {
 
-constexpr int DEC_WARPS = 4;     // warps per block
-constexpr int DEC_IN_W = 64;     // staged words per lane
-constexpr int DEC_STRIDE = 33;   // tile row stride (words / dwords): conflict-free transposes
-constexpr int DEC_OUT_T = 16;    // output tile rows (datapoints per flush)
-constexpr int DEC_FAST_WORDS = 4;  // the fast path reads 4 consecutive words
+constexpr int DEC_WARPS = 4;      // warps per block
+constexpr int DEC_RING = 64;      // staged words per lane (ring buffer, power of two)
+constexpr int DEC_MIRROR = 3;     // rows 64..66 mirror rows 0..2 so 4-word reads never wrap
+constexpr int DEC_FILL = 32;      // words per lane per asynchronous refill
+constexpr int DEC_STRIDE = 33;    // tile row stride (words / dwords): conflict-free transposes
+constexpr int DEC_OUT_T = 8;      // output tile rows (datapoints per flush)
+constexpr int DEC_FAST_WORDS = 4; // the fast path reads 4 consecutive words
 
-constexpr int DEC_IN_TILE_WORDS = DEC_IN_W * DEC_STRIDE;                 // u32
-constexpr int DEC_OUT_TILE_DWORDS = DEC_OUT_T * DEC_STRIDE;              // u64
+constexpr int DEC_IN_TILE_WORDS = (DEC_RING + DEC_MIRROR + 1) * DEC_STRIDE;  // u32 (+1 row pad: 8B align)
+constexpr int DEC_OUT_TILE_DWORDS = DEC_OUT_T * DEC_STRIDE;                  // u64
 constexpr size_t DEC_WARP_SMEM_PLAIN =
     (size_t)DEC_IN_TILE_WORDS * 4 + 2 * (size_t)DEC_OUT_TILE_DWORDS * 8;
 constexpr size_t DEC_WARP_SMEM_DS = (size_t)DEC_IN_TILE_WORDS * 4;
@@ -41,6 +44,7 @@ struct DecState {
   double int_val;
   int64_t unit_ns;
   int sig, mult, unit, scheme;
+  int emit_unit;  // time unit in force at the last datapoint produced
   int err;
   uint32_t n;
   bool is_float, done;
@@ -320,6 +324,7 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const uint8_t *base, ui
     if (int_hdr) s.is_float = false;
   }
   out_t = s.prev_time;
+  s.emit_unit = s.unit;
   if (!INT_OPT || s.is_float) {
     out_v = s.prev_bits;
   } else {
@@ -340,6 +345,43 @@ __device__ __forceinline__ uint64_t extract64(uint32_t w0, uint32_t w1, uint32_t
   return ((uint64_t)hi << 32) | lo;
 }
 
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+// 4-byte asynchronous global->shared copy (LDGSTS); bytes past src_bytes are zero-filled
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Warp-cooperative asynchronous refill: for every lane j in `mask`, copies the
+// DEC_FILL words starting at global word my_gw (of lane j) into lane j's ring
+// column.  Ring slot of a word == its global word index & (DEC_RING-1) (every
+// stream's base is DEC_RING-word aligned), slots 0..2 are mirrored to 64..66.
+__device__ __forceinline__ void ring_fill(uint32_t *ring, const uint8_t *streams, uint64_t nbytes,
+                                          uint32_t mask, uint32_t my_gw, int lane) {
+  const uint32_t ring_sa = smem_addr(ring);
+  // lanes whose whole refill lies inside the buffer take the unchecked path
+  const uint32_t inb = __ballot_sync(FULL_MASK, ((uint64_t)my_gw + DEC_FILL) * 4ull <= nbytes);
+  while (mask) {
+    const int j = __ffs((int)mask) - 1;
+    mask &= mask - 1;
+    const uint32_t gw = __shfl_sync(FULL_MASK, my_gw, j) + (uint32_t)lane;
+    const uint32_t slot = gw & (DEC_RING - 1);
+    const uint32_t dst = ring_sa + (slot * DEC_STRIDE + (uint32_t)j) * 4u;
+    const uint64_t b = (uint64_t)gw * 4ull;
+    uint32_t nb = 4;
+    const uint8_t *src = streams + b;
+    if (!((inb >> j) & 1u)) {
+      nb = (b + 4 <= nbytes) ? 4u : (b < nbytes ? (uint32_t)(nbytes - b) : 0u);
+      if (nb == 0) src = streams;
+    }
+    cp_async4(dst, src, nb);
+    if (slot < (uint32_t)DEC_MIRROR) cp_async4(dst + DEC_RING * DEC_STRIDE * 4u, src, nb);
+  }
+}
+
 struct DsAcc {  // fused-downsample per-lane accumulator (aggregation.Gauge, gauge.go:31-106)
   int64_t cur_w, hi_w, w_start;
   double sum, mn, mx;
@@ -347,14 +389,14 @@ struct DsAcc {  // fused-downsample per-lane accumulator (aggregation.Gauge, gau
 };
 
 template <bool INT_OPT, int MODE>
-__global__ void __launch_bounds__(DEC_WARPS * 32)
+__global__ void __launch_bounds__(DEC_WARPS * 32, 4)
     decode_kernel(const DecodeParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   constexpr size_t warp_smem = (MODE == 0) ? DEC_WARP_SMEM_PLAIN : DEC_WARP_SMEM_DS;
-  uint32_t *in_tile = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem) + warp * warp_smem);
-  uint64_t *ts_tile = reinterpret_cast<uint64_t *>(in_tile + DEC_IN_TILE_WORDS);
+  uint32_t *ring = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem) + warp * warp_smem);
+  uint64_t *ts_tile = reinterpret_cast<uint64_t *>(ring + DEC_IN_TILE_WORDS);
   uint64_t *val_tile = ts_tile + DEC_OUT_TILE_DWORDS;
 
   const uint64_t warp_s0 = ((uint64_t)blockIdx.x * DEC_WARPS + warp) * 32ull;
@@ -376,6 +418,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
   s.mult = 0;
   s.unit = 0;
   s.scheme = kSchemeNone;
+  s.emit_unit = 0;
   s.err = 0;
   s.n = 0;
   s.is_float = false;
@@ -391,12 +434,17 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
     } else if (o1 - o0 >= (1ull << 28)) {
       s.err = M3TSZ_ERR_STREAM_TOO_LARGE;
     } else {
-      s.wbase = o0 >> 2;
-      s.pos = (uint32_t)(o0 & 3) * 8u;
+      // base = the stream's first word rounded down to a DEC_RING-word boundary
+      const uint64_t w = o0 >> 2;
+      s.wbase = w & ~(uint64_t)(DEC_RING - 1);
+      s.pos = (uint32_t)(w - s.wbase) * 32u + (uint32_t)(o0 & 3) * 8u;
       s.end = s.pos + (uint32_t)(o1 - o0) * 8u;
       pos0 = s.pos;
     }
   }
+  const uint32_t gbase = (uint32_t)s.wbase;  // streams_bytes < 16 GiB (checked by the host)
+  // previous XOR's leading / trailing zero counts, kept eagerly (float path)
+  int plz = 64, ptz = 0;
 
   DsAcc acc;
   acc.cur_w = -1;
@@ -409,145 +457,136 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
   const int64_t range_end = p.range_start + (int64_t)p.n_windows * p.window;
   (void)range_end;
 
-  uint32_t tile_w0 = 0;
-  bool tile_valid = false;
-  uint32_t iter = 0;       // warp-uniform datapoint index
-  uint32_t tile_row0 = 0;  // datapoint index of output tile row 0
+  uint32_t filled = s.pos >> 5;  // words [.., filled) have been requested (relative to wbase)
+  uint32_t safe = filled;        // words [.., safe) have landed in the ring
+  uint32_t iter = 0;             // warp-uniform datapoint index
+  uint32_t tile_row0 = 0;        // datapoint index of output tile row 0
 
   for (;;) {
     const bool active = !s.done && s.err == 0;
     if (!__any_sync(FULL_MASK, active)) break;
 
-    // ---- (re)stage the compressed words of all 32 series ----
-    uint32_t k = (s.pos >> 5) - tile_w0;
-    const bool need = active && (!tile_valid || k > (uint32_t)(DEC_IN_W - DEC_FAST_WORDS));
-    if (__any_sync(FULL_MASK, need)) {
-      const uint32_t amask = __ballot_sync(FULL_MASK, active);
-      tile_w0 = s.pos >> 5;
-      const uint64_t my_src = s.wbase + tile_w0;
-      __syncwarp();
-#pragma unroll 4
-      for (int j = 0; j < 32; j++) {
-        const uint64_t src = __shfl_sync(FULL_MASK, my_src, j);
-        if ((amask >> j) & 1u) {
-#pragma unroll
-          for (int hh = 0; hh < DEC_IN_W / 32; hh++) {
-            const int wi = lane + 32 * hh;
-            in_tile[wi * DEC_STRIDE + j] = load_be32(p.streams, p.streams_bytes, src + wi);
-          }
+    // ---- ring maintenance: wait for the refill in flight, request the next ----
+    uint32_t cw = s.pos >> 5;
+    {
+      int avail = (int)(filled - cw);
+      if (__any_sync(FULL_MASK, active && (avail <= DEC_RING - DEC_FILL || cw + DEC_FAST_WORDS > safe))) {
+        cp_async_wait_all();
+        __syncwarp();
+        if (avail < 0) {  // the slow path skipped past the ring (annotation): restart at cw
+          filled = cw;
+          avail = 0;
+        }
+        safe = filled;
+        const uint32_t fmask = __ballot_sync(FULL_MASK, active && avail <= DEC_RING - DEC_FILL);
+        if (fmask) {
+          ring_fill(ring, p.streams, p.streams_bytes, fmask, gbase + filled, lane);
+          if ((fmask >> lane) & 1u) filled += DEC_FILL;
+        }
+        if (__any_sync(FULL_MASK, active && cw + DEC_FAST_WORDS > safe && filled > safe)) {
+          cp_async_wait_all();  // start-up / restart only: nothing staged yet
+          __syncwarp();
+          safe = filled;
         }
       }
-      __syncwarp();
-      tile_valid = true;
-      k = 0;
     }
 
     int64_t t = 0;
     uint64_t v = 0;
     bool emitted = false;
-    if (active) {
-      // ---------------- fast path: parse from 4 staged words ----------------
-      const uint32_t *tp = in_tile + k * DEC_STRIDE + lane;
-      const uint32_t w0 = tp[0], w1 = tp[DEC_STRIDE], w2 = tp[2 * DEC_STRIDE],
-                     w3 = tp[3 * DEC_STRIDE];
-      const uint32_t sh = s.pos & 31u;
-      const uint32_t h = __funnelshift_l(w1, w0, sh);
-      bool ok = (s.prev_time != 0) && (s.scheme == kScheme32 || s.scheme == kScheme64) &&
-                (s.unit >= 1 && s.unit <= 4);
-      uint32_t c = 1;  // bits consumed
-      int64_t dod = 0;
-      if (h >> 31) {  // non-zero delta-of-delta bucket, marker, or default bucket
-        if ((h >> 23) == kMarkerOpcode) {
-          ok = false;
-        } else if ((h >> 30) == 2u) {
-          c = 9;
-          dod = (int64_t)(((int32_t)(h << 2)) >> 25);
-        } else if ((h >> 29) == 6u) {
-          c = 12;
-          dod = (int64_t)(((int32_t)(h << 3)) >> 23);
-        } else if ((h >> 28) == 14u) {
-          c = 16;
-          dod = (int64_t)(((int32_t)(h << 4)) >> 20);
-        } else {
-          ok = false;
-        }
-        dod = (int64_t)((uint64_t)dod * (uint64_t)s.unit_ns);
-      }
-      uint32_t x = h << c;
-      // value grammar (iterator.go:128-176)
-      int kind = 0;  // 0 float-next, 1 int-diff, 2 repeat
-      if (INT_OPT) {
-        if (x >> 31) {
-          x <<= 1;
-          c += 1;
-          kind = s.is_float ? 0 : 1;
-          if (kind == 1 && s.sig == 64) ok = false;
-        } else if ((x >> 30) == 1u) {
-          c += 2;
-          kind = 2;
-        } else {
-          ok = false;
-        }
-      }
-      if (ok) {
-        int n = 0, tz = 0;
-        bool zero_xor = false;
-        if (kind == 0) {
-          if (!(x >> 31)) {
-            zero_xor = true;
-            c += 1;
-          } else if (!(x & 0x40000000u)) {
-            int pl, pt;
-            lz_tz(s.prev_xor, pl, pt);
-            n = 64 - pl - pt;
-            tz = pt;
-            c += 2;
-          } else {
-            const int lz = (int)((x >> 24) & 63u);
-            n = (int)((x >> 18) & 63u) + 1;
-            tz = 64 - lz - n;
-            c += 14;
-          }
-        } else if (kind == 1) {
-          n = s.sig + 1;
-        }
-        uint64_t payload = 0;
-        if (n > 0) payload = extract64(w0, w1, w2, w3, sh + c) >> (64 - n);
-        c += (uint32_t)n;
-        if (s.pos + c > s.end) {
-          s.err = M3TSZ_ERR_EOF;  // truncated stream: datapoint is not produced
-        } else {
-          s.pos += c;
-          s.prev_delta = (int64_t)((uint64_t)s.prev_delta + (uint64_t)dod);
-          s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
-          if (kind == 0) {
-            const uint64_t xr = zero_xor ? 0ull : ((tz < 0) ? 0ull : (payload << tz));
-            s.prev_xor = xr;
-            s.prev_bits ^= xr;
-          } else if (kind == 1) {
-            const uint64_t neg = payload >> s.sig;
-            const uint64_t mag = payload & ((1ull << s.sig) - 1ull);
-            const double m = __ull2double_rn(mag);
-            s.int_val = neg ? __dadd_rn(s.int_val, m) : __dsub_rn(s.int_val, m);
-          }
-          t = s.prev_time;
-          if (!INT_OPT || s.is_float) {
-            v = s.prev_bits;
-          } else {
-            const double dv = s.mult ? __ddiv_rn(s.int_val, mult_pow10(s.mult)) : s.int_val;
-            v = (uint64_t)__double_as_longlong(dv);
-          }
-          emitted = true;
-        }
+    // ---------------- fast path: branch-free parse of 4 ring words ----------------
+    const uint32_t *tp = ring + (cw & (DEC_RING - 1)) * DEC_STRIDE + lane;
+    const uint32_t w0 = __byte_perm(tp[0], 0, 0x0123), w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123),
+                   w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123),
+                   w3 = __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123);
+    const uint32_t sh = s.pos & 31u;
+    const uint32_t h = __funnelshift_l(w1, w0, sh);
+    bool ok = active && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0) &&
+              (s.scheme == kScheme32 || s.scheme == kScheme64) && (s.unit >= 1 && s.unit <= 4);
+    uint32_t c = 1;  // bits consumed before the payload
+    int64_t dod = 0;
+    if (__any_sync(FULL_MASK, ok && (h >> 31))) {  // some lane has a non-zero delta-of-delta
+      const bool nz = (h >> 31) != 0;
+      const bool m9 = (h >> 30) == 2u, m12 = (h >> 29) == 6u, m16 = (h >> 28) == 14u;
+      const bool marker = (h >> 23) == kMarkerOpcode;
+      const int32_t f = m9 ? (((int32_t)(h << 2)) >> 25)
+                           : (m12 ? (((int32_t)(h << 3)) >> 23) : (((int32_t)(h << 4)) >> 20));
+      c = nz ? (m9 ? 9u : (m12 ? 12u : 16u)) : 1u;
+      ok = ok && (!nz || ((m9 || m12 || m16) && !marker));
+      dod = nz ? (int64_t)((uint64_t)(int64_t)f * (uint64_t)s.unit_ns) : 0;
+    }
+    uint32_t x = h << c;
+    // value grammar (iterator.go:128-176); kinds: float-next / int-diff / repeat
+    bool k_float = true, k_int = false;
+    if (INT_OPT) {
+      const bool b0 = (x >> 31) != 0;
+      const bool rep = !b0 && ((x >> 30) & 1u);
+      ok = ok && (b0 || rep);
+      k_float = b0 && s.is_float;
+      k_int = b0 && !s.is_float;
+      ok = ok && !(k_int && s.sig == 64);
+      c += b0 ? 1u : 2u;
+      x <<= 1;
+    }
+    const bool zero = !(x >> 31);
+    const bool cont = (x >> 30) == 2u;
+    const int lz = (int)((x >> 24) & 63u);
+    const int nunc = (int)((x >> 18) & 63u) + 1;
+    int n = cont ? (64 - plz - ptz) : nunc;
+    int tz = cont ? ptz : (64 - lz - nunc);
+    uint32_t hb = cont ? 2u : 14u;
+    if (zero) {
+      n = 0;
+      hb = 1;
+    }
+    if (!k_float) {
+      hb = 0;
+      n = k_int ? s.sig + 1 : 0;
+    }
+    c += hb;
+    const uint64_t field = extract64(w0, w1, w2, w3, sh + c);
+    const uint64_t payload = n ? (field >> (64 - n)) : 0ull;
+    c += (uint32_t)n;
+    if (ok) {
+      if (s.pos + c > s.end) {
+        s.err = M3TSZ_ERR_EOF;  // truncated stream: the datapoint is not produced
       } else {
-        // copy-in / copy-out keeps the lane state in registers on the fast path
-        DecState tmp = s;
+        s.pos += c;
+        s.prev_delta = (int64_t)((uint64_t)s.prev_delta + (uint64_t)dod);
+        s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
+        if (k_float) {
+          const uint64_t xr = (tz < 0) ? 0ull : (payload << tz);
+          s.prev_xor = xr;
+          s.prev_bits ^= xr;
+          lz_tz(xr, plz, ptz);
+        }
+        t = s.prev_time;
+        v = s.prev_bits;
+        emitted = true;
+      }
+    }
+    if (INT_OPT && __any_sync(FULL_MASK, emitted && !s.is_float)) {  // int-mode lanes
+      if (emitted && !s.is_float) {
+        if (k_int) {
+          const uint64_t neg = payload >> s.sig;
+          const uint64_t mag = payload & ((1ull << s.sig) - 1ull);
+          const double m = __ull2double_rn(mag);
+          s.int_val = neg ? __dadd_rn(s.int_val, m) : __dsub_rn(s.int_val, m);
+        }
+        const double dv = s.mult ? __ddiv_rn(s.int_val, mult_pow10(s.mult)) : s.int_val;
+        v = (uint64_t)__double_as_longlong(dv);
+      }
+    }
+    if (__any_sync(FULL_MASK, active && !ok)) {  // complete grammar, from global memory
+      if (active && !ok) {
+        DecState tmp = s;  // copy-in / copy-out keeps the lane state in registers
         int64_t st = 0;
         uint64_t sv = 0;
         emitted = decode_dp_slow<INT_OPT>(tmp, p.streams, p.streams_bytes, p.default_unit, st, sv);
         s = tmp;
         t = st;
         v = sv;
+        lz_tz(s.prev_xor, plz, ptz);
       }
     }
 
@@ -617,20 +656,33 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
       __syncwarp();
       const uint32_t lim = s.n < (uint32_t)p.cap ? s.n : (uint32_t)p.cap;
       const uint32_t my_rows = lim > tile_row0 ? min(lim - tile_row0, (uint32_t)DEC_OUT_T) : 0u;
+      // lanes 0-7: ts rows of series 2i, 8-15: value rows of 2i, 16-23 / 24-31: same for 2i+1
       const int r = lane & (DEC_OUT_T - 1);
-      const bool isval = lane >= DEC_OUT_T;
-      const uint64_t *tile = isval ? val_tile : ts_tile;
-      uint64_t *dst0 = (isval ? reinterpret_cast<uint64_t *>(p.val) : reinterpret_cast<uint64_t *>(p.ts)) +
-                       warp_s0 * p.cap + tile_row0 + r;
+      const bool isval = (lane >> 3) & 1;
+      const int jo = lane >> 4;
+      const uint64_t *tile = (isval ? val_tile : ts_tile) + r * DEC_STRIDE + jo;
+      uint64_t *dst = (isval ? reinterpret_cast<uint64_t *>(p.val) : reinterpret_cast<uint64_t *>(p.ts)) +
+                      (warp_s0 + jo) * p.cap + tile_row0 + r;
+      const uint64_t step = 2ull * p.cap;
+      if (__all_sync(FULL_MASK, my_rows == (uint32_t)DEC_OUT_T)) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          *dst = tile[2 * i];
+          dst += step;
+        }
+      } else {
 #pragma unroll 4
-      for (int j = 0; j < 32; j++) {
-        const uint32_t rows = __shfl_sync(FULL_MASK, my_rows, j);
-        if ((uint32_t)r < rows) dst0[(uint64_t)j * p.cap] = tile[r * DEC_STRIDE + j];
+        for (int i = 0; i < 16; i++) {
+          const uint32_t rows = __shfl_sync(FULL_MASK, my_rows, 2 * i + jo);
+          if ((uint32_t)r < rows) *dst = tile[2 * i];
+          dst += step;
+        }
       }
       __syncwarp();
       tile_row0 = iter;
     }
   }
+  cp_async_wait_all();
 
   // ---------------- epilogue ----------------
   if (MODE == 0) {
@@ -639,13 +691,16 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
       const uint32_t lim = s.n < (uint32_t)p.cap ? s.n : (uint32_t)p.cap;
       const uint32_t my_rows = lim > tile_row0 ? min(lim - tile_row0, (uint32_t)DEC_OUT_T) : 0u;
       const int r = lane & (DEC_OUT_T - 1);
-      const bool isval = lane >= DEC_OUT_T;
-      const uint64_t *tile = isval ? val_tile : ts_tile;
-      uint64_t *dst0 = (isval ? reinterpret_cast<uint64_t *>(p.val) : reinterpret_cast<uint64_t *>(p.ts)) +
-                       warp_s0 * p.cap + tile_row0 + r;
-      for (int j = 0; j < 32; j++) {
-        const uint32_t rows = __shfl_sync(FULL_MASK, my_rows, j);
-        if ((uint32_t)r < rows) dst0[(uint64_t)j * p.cap] = tile[r * DEC_STRIDE + j];
+      const bool isval = (lane >> 3) & 1;
+      const int jo = lane >> 4;
+      const uint64_t *tile = (isval ? val_tile : ts_tile) + r * DEC_STRIDE + jo;
+      uint64_t *dst = (isval ? reinterpret_cast<uint64_t *>(p.val) : reinterpret_cast<uint64_t *>(p.ts)) +
+                      (warp_s0 + jo) * p.cap + tile_row0 + r;
+      const uint64_t step = 2ull * p.cap;
+      for (int i = 0; i < 16; i++) {
+        const uint32_t rows = __shfl_sync(FULL_MASK, my_rows, 2 * i + jo);
+        if ((uint32_t)r < rows) *dst = tile[2 * i];
+        dst += step;
       }
     }
   } else if (valid) {
@@ -669,7 +724,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
     int st = s.err;
     if (MODE == 0 && st == 0 && s.n > p.cap) st = M3TSZ_ERR_CAPACITY;
     if (p.status) p.status[sidx] = st;
-    if (p.unit_out) p.unit_out[sidx] = (uint8_t)s.unit;
+    if (p.unit_out) p.unit_out[sidx] = (uint8_t)(s.n ? s.emit_unit : s.unit);
     if (p.ann_out) {
       m3tsz_annotation_ref a;
       a.bit_offset = s.ann_count ? (uint64_t)(s.ann_bit - pos0) : 0ull;
@@ -684,13 +739,9 @@ template <bool INT_OPT, int MODE>
 static cudaError_t launch_one(const DecodeParams &p, cudaStream_t stream) {
   constexpr size_t warp_smem = (MODE == 0) ? DEC_WARP_SMEM_PLAIN : DEC_WARP_SMEM_DS;
   constexpr size_t smem = warp_smem * DEC_WARPS;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(decode_kernel<INT_OPT, MODE>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(decode_kernel<INT_OPT, MODE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   const uint64_t per_block = (uint64_t)DEC_WARPS * 32ull;
   const uint64_t blocks = (p.n_series + per_block - 1) / per_block;
   if (blocks == 0) return cudaSuccess;

@@ -278,10 +278,10 @@ def test_truncated_and_corrupt_streams(codecs):
         for cut in range(0, len(b)):
             streams.append(b[:cut])
     check_decode_against_oracle(codecs[False], streams, False, cap=64)
-    # raw encoder buffer without the end-of-stream tail: all points, then io.EOF
-    s0 = G["streams"][0]
-    ts, vals, n, st, _, _ = gpu_decode(codecs[False], [hb(s0["raw"])], 64)
-    assert n[0] == len(s0["datapoints"]) and st[0] == O.ERR_EOF
+    # raw encoder buffers without the end-of-stream tail: ends in io.EOF like the reference
+    raws = [hb(s["raw"]) for s in G["streams"] if "raw" in s]
+    ts, vals, n, st, _, _ = check_decode_against_oracle(codecs[False], raws, False, cap=64)
+    assert (st == O.ERR_EOF).all()
     # reference error streams (iterator_test.go:265-269,387-394)
     for c in G["iterator_error_streams"]["cases"]:
         ts, vals, n, st, _, _ = gpu_decode(codecs[False], [hb(c["bytes"])], 64)
@@ -438,30 +438,45 @@ def test_host_entry_points(codecs):
 
 
 # ------------------------------------------------------------------ full-size properties
-def test_full_size_roundtrip_properties(codecs):
-    """BASELINE config 2 size (100k x 1440): encode -> decode round trip is the
-    identity, stream lengths are self-consistent, and a sample of series is
-    byte-identical to the oracle."""
+@pytest.mark.parametrize("int_opt", [False, True])
+def test_full_size_roundtrip_properties(codecs, int_opt):
+    """BASELINE config 2 size (100k x 1440).  Size-independent properties:
+    encode -> decode round trip is the identity (float mode; in int-optimised mode
+    the reference itself rounds values within one ulp of a short decimal,
+    m3tsz.go:72-77, so there the identity holds up to that documented loss),
+    stream lengths are self-consistent, and a random sample of series is
+    byte-identical to the oracle encoder / bit-identical to the oracle decoder."""
     from m3_b200 import synth
     S, P = 100_000, 1440
-    codec = codecs[True]
+    codec = codecs[int_opt]
     ts, vals, start = synth.gaussian_walk(S, P, "cuda", seed=77)
     enc = codec.encode(ts, vals, start, unit=O.UNIT_S)
     assert int((enc.status != 0).sum()) == 0
     packed, offsets = codec.compact(enc, align=16)
     total = int(offsets[-1].item())
     bpd = float(enc.out_len.sum().item()) / (S * P)
-    assert 6.5 < bpd < 8.0, bpd  # SURVEY.md §8: ~7.3 B/dp for the Gaussian walk
+    assert 6.5 < bpd < 8.0, bpd  # SURVEY.md §8: ~7.2-7.3 B/dp for the Gaussian walk
     dec = codec.decode(packed, offsets, P)
     torch.cuda.synchronize()
     assert int((dec.status != 0).sum()) == 0 and bool((dec.n_points == P).all())
     assert torch.equal(dec.ts, ts)
-    assert torch.equal(dec.values.view(torch.int64), vals.view(torch.int64))
+    same = dec.values.view(torch.int64) == vals.view(torch.int64)
+    n_diff = int((~same).sum().item())
+    if not int_opt:
+        assert n_diff == 0
+    else:
+        assert n_diff < S * P * 1e-6, n_diff  # ~3e-8 expected (SURVEY.md §7)
+        if n_diff:
+            a, b = dec.values[~same], vals[~same]
+            assert bool(((a - b).abs() <= 4e-16 * b.abs()).all())
     idx = np.random.default_rng(1).integers(0, S, size=64)
     h_ts, h_vals = ts[idx].cpu().numpy(), vals[idx].cpu().numpy()
-    o_out, o_len, _ = O.encode_batch(h_ts, h_vals, int(start[0].item()), O.UNIT_S, True, n_threads=8)
+    o_out, o_len, _ = O.encode_batch(h_ts, h_vals, int(start[0].item()), O.UNIT_S, int_opt, n_threads=8)
     g_len = enc.out_len[idx].cpu().numpy()
     g_out = enc.out[idx].cpu().numpy()
+    g_dec = dec.values[idx].cpu().numpy().view(np.uint64)
     for k in range(len(idx)):
         assert g_len[k] == o_len[k] and (g_out[k, : g_len[k]] == o_out[k, : o_len[k]]).all()
+        _, ovals, oerr, _ = oracle_decode(o_out[k, : o_len[k]].tobytes(), int_opt)
+        assert oerr == 0 and (g_dec[k] == ovals).all()
     assert total >= int(enc.out_len.sum().item())
