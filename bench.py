@@ -1,0 +1,453 @@
+#!/usr/bin/env python3
+"""bench.py -- M3TSZ datapoints/sec (encode + decode) on N B200s of one node.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
+prints ONE JSON line on rank 0.  One "step" = one pass of the hot path over one
+batch: batch ENCODE of S series x P points (lane-per-series sm_100a kernel),
+stream compaction, and batch DECODE of the resulting bitstreams.  The batch is
+BASELINE.json configs[1] ("batch decode 100k series x 1440 points, Gaussian-walk
+values") per GPU; with N GPUs every rank holds its own 100k-series shard (weak
+scaling, no data-path collective: series are independent).
+
+  value   = S*P*N / step time, inputs and outputs resident in HBM (CUDA events)
+  e2e     = the same step through the C ABI's *_host entry points with pinned
+            HOST buffers (H2D of inputs and D2H of results inside the timed region)
+  roofline= the decode kernel: algorithmic bytes (compressed bytes + CSR offsets
+            in, 16 B/dp out) / its average duration inside the timed region
+  cpu_baseline = the CPU oracle (plain-C restatement of the reference's Go codec;
+            no Go toolchain in this image) on all host cores, bounded sample
+
+`--impl reference` times that CPU oracle as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "M3TSZ datapoints/sec encode+decode"
+UNIT = "datapoints/s"
+SEC = 1_000_000_000
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--series", type=int, default=100_000, help="series per GPU")
+    ap.add_argument("--points", type=int, default=1440)
+    ap.add_argument("--int-optimized", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(workload):
+    """dram bytes per decode launch from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(workload)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU oracle arm
+def cpu_oracle_throughput(n_series, n_points, int_opt, budget_s, steps=1, warmup=0):
+    """Times the CPU oracle (encode + decode of a Gaussian-walk sample) on all host
+    cores.  Returns (dp/s over the timed steps, dict describing the run)."""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from m3_b200 import synth
+
+    cores = os.cpu_count() or 1
+    probe_s = max(cores * 4, 64)
+    ts, vals, start = synth.gaussian_walk(probe_s, n_points, "cpu", seed=99)
+    ts_np, vals_np, st = ts.numpy(), vals.numpy(), int(start[0])
+
+    def run(ts_np, vals_np):
+        S = ts_np.shape[0]
+        t0 = time.perf_counter()
+        out, ln, status = O.encode_batch(ts_np, vals_np, st, 1, int_opt, n_threads=cores)
+        t1 = time.perf_counter()
+        off = np.zeros(S + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(ln)
+        blob = np.concatenate([out[i, : ln[i]] for i in range(S)])
+        t2 = time.perf_counter()
+        O.decode_batch(blob, off, n_points, int_opt, n_threads=cores)
+        t3 = time.perf_counter()
+        return (t1 - t0), (t3 - t2)
+
+    run(ts_np, vals_np)  # warm the library / page in
+    te, td = run(ts_np, vals_np)
+    per_series = (te + td) / probe_s
+    total_steps = max(1, steps + warmup)
+    S = int(max(probe_s, min(n_series, budget_s / total_steps / max(per_series, 1e-9))))
+    S = max(cores, (S // cores) * cores)
+    ts, vals, start = synth.gaussian_walk(S, n_points, "cpu", seed=100)
+    ts_np, vals_np = ts.numpy(), vals.numpy()
+    for _ in range(warmup):
+        run(ts_np, vals_np)
+    tot_e = tot_d = 0.0
+    for _ in range(steps):
+        te, td = run(ts_np, vals_np)
+        tot_e += te
+        tot_d += td
+    dp = S * n_points * steps
+    info = {
+        "cores": cores, "sample": "%d series x %d points per step (Gaussian walk, intOptimized=%s), "
+        "encode then decode, %d threads" % (S, n_points, bool(int_opt), cores),
+        "encode_dps": dp / tot_e, "decode_dps": dp / tot_d, "ms_per_step": (tot_e + tot_d) * 1e3 / steps,
+        "kind": "port",
+        "note": "C restatement of the reference algorithm (Go toolchain unavailable); published Go "
+                "anchor: BenchmarkM3TSZDecode 69272 ns/op ~ 10.4 M dp/s per core",
+    }
+    return dp / (tot_e + tot_d), info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, info = cpu_oracle_throughput(args.series, args.points, args.int_optimized,
+                                        budget_s=60.0, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/f64",
+        "data": "synthetic",
+        "config": {"workload": "CPU oracle encode+decode, bounded sample of %d-series x %d-point "
+                               "Gaussian-walk batch" % (args.series, args.points),
+                   "int_optimized": bool(args.int_optimized)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                         "sample": info["sample"], "encode_dps": info["encode_dps"],
+                         "decode_dps": info["decode_dps"], "note": info["note"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from m3_b200 import synth
+    from m3_b200.codec import BatchCodec, DecodeResult, EncodeResult
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the codec has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    S, P = args.series, args.points
+    int_opt = bool(args.int_optimized)
+    codec = BatchCodec(local_rank, int_optimized=int_opt)
+    ts, vals, start = synth.gaussian_walk(S, P, dev, seed=1000 + rank)
+    stride = codec.encode_bound(P)
+    enc = EncodeResult(out=torch.empty((S, stride), dtype=torch.uint8, device=dev),
+                       out_len=torch.empty(S, dtype=torch.int64, device=dev),
+                       status=torch.empty(S, dtype=torch.int32, device=dev))
+    codec.encode(ts, vals, start, unit=1, out=enc)
+    total = int(enc.out_len.sum().item())
+    cap_bytes = total + 16 * S + 64
+    packed = torch.empty(cap_bytes, dtype=torch.uint8, device=dev)
+    offsets = torch.empty(S + 1, dtype=torch.int64, device=dev)
+    dec = DecodeResult(ts=torch.empty((S, P), dtype=torch.int64, device=dev),
+                       values=torch.empty((S, P), dtype=torch.float64, device=dev),
+                       n_points=torch.empty(S, dtype=torch.int32, device=dev),
+                       status=torch.empty(S, dtype=torch.int32, device=dev),
+                       unit=torch.empty(S, dtype=torch.uint8, device=dev), annotations=None)
+    import ctypes as C
+    from m3_b200 import capi
+
+    def compact():
+        rc = capi.lib().m3tsz_compact_streams(
+            codec.ctx.handle, C.c_void_p(enc.out.data_ptr()), stride, C.c_void_p(enc.out_len.data_ptr()),
+            S, 16, C.c_void_p(packed.data_ptr()), cap_bytes, C.c_void_p(offsets.data_ptr()),
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        codec.ctx.check(rc, "compact")
+
+    dec_events = []
+
+    def step(record=False):
+        codec.encode(ts, vals, start, unit=1, out=enc)
+        compact()
+        if record:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            codec.decode(packed, offsets, P, out=dec)
+            e1.record()
+            dec_events.append((e0, e1))
+        else:
+            codec.decode(packed, offsets, P, out=dec)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    # sanity: the timed path round-trips (float mode exactly; int mode up to the
+    # reference's own near-integer rounding)
+    assert int((enc.status != 0).sum()) == 0 and int((dec.status != 0).sum()) == 0
+    assert torch.equal(dec.ts, ts)
+    mism = int((dec.values.view(torch.int64) != vals.view(torch.int64)).sum())
+    assert mism <= S * P * 1e-6, mism
+    compressed_bytes = int(enc.out_len.sum().item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = codec.launch_count()
+    barrier()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    ev1.record()
+    barrier()
+    launches = codec.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms_total = ev0.elapsed_time(ev1)
+    dec_ms = sum(a.elapsed_time(b) for a, b in dec_events) / len(dec_events)
+    t = torch.tensor([ms_total, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, dec_ms_max = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    value = S * P * world / (ms_per_step * 1e-3)
+
+    # separate per-kernel timings (same buffers, outside the headline region)
+    def time_fn(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    enc_ms = time_fn(lambda: codec.encode(ts, vals, start, unit=1, out=enc))
+    ds = codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC, (P * 60 + 299) // 300)
+    ds_ms = time_fn(lambda: codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC,
+                                                    (P * 60 + 299) // 300, out=ds))
+    n_win = ds.sum.shape[0]
+
+    # ---- fetch-side all-gather (only when a query spans shards) ----
+    allgather = None
+    if world > 1:
+        from m3_b200.sharded import all_gather_blocks
+        sub = min(S, max(1, (8 << 30) // (world * P * 16)))  # bound the gathered block to ~8 GiB
+        blk_t, blk_v = dec.ts[:sub].contiguous(), dec.values[:sub].contiguous()
+        all_gather_blocks(blk_t, sub * world)
+        barrier()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        g_t = all_gather_blocks(blk_t, sub * world)
+        g_v = all_gather_blocks(blk_v, sub * world)
+        b.record()
+        barrier()
+        ag = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
+        recv = (world - 1) * sub * P * 16
+        allgather = {"series_per_rank": sub, "ms": float(ag[0]), "bytes_received_per_gpu": recv,
+                     "gbs_per_gpu": recv / (float(ag[0]) * 1e-3) / 1e9,
+                     "nvlink_peer_peak_gbs": 770.0, "frac": recv / (float(ag[0]) * 1e-3) / 1e9 / 770.0}
+        del g_t, g_v
+
+    # ---- e2e: the same step through the *_host C ABI with pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        h_ts = ts.cpu().pin_memory()
+        h_vals = vals.cpu().pin_memory()
+        h_start = start.cpu().pin_memory()
+        h_packed = torch.empty(cap_bytes, dtype=torch.uint8).pin_memory()
+        h_off = torch.empty(S + 1, dtype=torch.int64).pin_memory()
+        h_len = torch.empty(S, dtype=torch.int64).pin_memory()
+        h_st = torch.empty(S, dtype=torch.int32).pin_memory()
+        h_dts = torch.empty((S, P), dtype=torch.int64).pin_memory()
+        h_dvals = torch.empty((S, P), dtype=torch.float64).pin_memory()
+        h_n = torch.empty(S, dtype=torch.int32).pin_memory()
+
+        def host_step():
+            codec.encode_host(h_ts, h_vals, h_start, 1, h_packed, h_off, h_len, h_st, align=16)
+            nbytes = int(h_off[-1])
+            codec.decode_host(h_packed[:nbytes], h_off, P, h_dts, h_dvals, h_n, h_st)
+            return nbytes
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            nb = host_step()
+        assert torch.equal(h_dts, h_ts)
+        barrier()
+        l0 = codec.launch_count()
+        t0 = time.perf_counter()
+        e_steps = max(1, min(args.steps, 5))
+        for _ in range(e_steps):
+            nb = host_step()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        e_launch = codec.launch_count() - l0
+        tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e_s = float(tt[0]) / e_steps
+        h2d = S * P * 16 + S * 8 + nb + (S + 1) * 8
+        d2h = nb + (S + 1) * 8 + S * 12 + S * P * 16 + S * 8
+        e2e = {"value": S * P * world / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": e_s * 1e3, "steps": e_steps,
+               "launches_per_step": e_launch / e_steps,
+               "api": "m3tsz_encode_batch_host + m3tsz_decode_batch_host (pinned host buffers)"}
+        del h_ts, h_vals, h_dts, h_dvals, h_packed
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the decode kernel ----
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = compressed_bytes + (S + 1) * 8 + S * P * 16 + S * 9  # in: streams + offsets; out: ts, val, n/status/unit
+    achieved = alg_bytes / (dec_ms_max * 1e-3) / 1e9
+    workload = "%dx%d" % (S, P)
+    roofline = {"bound": "hbm", "kernel": "m3tsz::decode_kernel<%s,0>" % ("true" if int_opt else "false"),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(workload), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms_max,
+                "bytes_per_dp": alg_bytes / (S * P)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cv, info = cpu_oracle_throughput(S, P, int_opt, budget_s=args.cpu_seconds)
+        cpu = {"value": cv, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+               "sample": info["sample"], "encode_dps": info["encode_dps"], "decode_dps": info["decode_dps"],
+               "note": info["note"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64/f64 (integer bit manipulation; float64 values)",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: batch of %d series x %d points per GPU, Gaussian random walk "
+                               "(x0=100, N(0,1) steps), 60 s cadence, unit=Second; step = encode + "
+                               "compact + decode" % (S, P),
+                   "series_per_gpu": S, "points": P, "int_optimized": int_opt,
+                   "compressed_bytes_per_dp": compressed_bytes / (S * P),
+                   "l2": "inputs %.2f GB and outputs %.2f GB per step >> 126 MB L2, no flush needed"
+                         % (S * P * 16 / 1e9, (compressed_bytes + S * P * 16) / 1e9),
+                   "parallelism": "series sharded per GPU, no data-path collective"},
+        "encode_dps": S * P / (enc_ms * 1e-3), "decode_dps": S * P / (dec_ms_max * 1e-3),
+        "decode_downsample_dps": S * P / (ds_ms * 1e-3),
+        "decode_downsample": {"windows": n_win, "ms": ds_ms,
+                              "algorithmic_gbs": (compressed_bytes + n_win * S * 32) / (ds_ms * 1e-3) / 1e9},
+        "encode_ms": enc_ms, "decode_ms": dec_ms_max,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "clocks": clocks, "fetch_allgather": allgather,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

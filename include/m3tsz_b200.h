@@ -181,13 +181,19 @@ int m3tsz_compact_streams(m3tsz_ctx *ctx, const uint8_t *d_slots, uint64_t slot_
                           uint8_t *d_packed, uint64_t packed_capacity, uint64_t *d_offsets,
                           void *stream);
 
+/* Host-buffer encode: copies the inputs to the device, encodes, packs the
+ * streams on the device (m3tsz_compact_streams, `align`-byte aligned starts)
+ * and copies back ONE contiguous buffer + CSR offsets -- the fileset data-file
+ * layout -- so that only compressed bytes cross PCIe.  h_offsets has
+ * n_series+1 entries; stream s is h_packed[h_offsets[s] .. +h_out_len[s]). */
 int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *h_ts,
                             const double *h_val, uint64_t n_series, uint64_t points_stride,
                             const uint32_t *h_n_points, const int64_t *h_start, int32_t unit,
                             const uint8_t *h_units, const uint64_t *h_ann_series_off,
                             const m3tsz_annotation_entry *h_ann_entries,
-                            const uint8_t *h_ann_bytes, uint64_t ann_bytes_len, uint8_t *h_out,
-                            uint64_t out_stride, uint64_t *h_out_len, int32_t *h_status);
+                            const uint8_t *h_ann_bytes, uint64_t ann_bytes_len, uint32_t align,
+                            uint8_t *h_packed, uint64_t packed_capacity, uint64_t *h_offsets,
+                            uint64_t *h_out_len, int32_t *h_status);
 
 /* ------------------------------------------------------------------------
  * Fused decode + downsample (BASELINE config 4).  Decodes every stream and

@@ -90,7 +90,7 @@ def lib():
                                      vp, vp, vp]
     L.m3tsz_encode_batch_host.restype = C.c_int
     L.m3tsz_encode_batch_host.argtypes = [vp, po, vp, vp, u64, u64, vp, vp, i32, vp, vp, vp, vp, u64,
-                                          vp, u64, vp, vp]
+                                          u32, vp, u64, vp, vp, vp]
     L.m3tsz_compact_streams.restype = C.c_int
     L.m3tsz_compact_streams.argtypes = [vp, vp, u64, vp, u64, u32, vp, u64, vp, vp]
     L.m3tsz_decode_downsample_batch.restype = C.c_int

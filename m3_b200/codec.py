@@ -163,12 +163,14 @@ class BatchCodec:
             S, _ptr(h_ts), _ptr(h_values), max_points, _ptr(h_n_points), _ptr(h_status), None, None)
         self.ctx.check(rc, "m3tsz_decode_batch_host")
 
-    def encode_host(self, h_ts, h_values, h_start, unit, h_out, h_out_len, h_status):
+    def encode_host(self, h_ts, h_values, h_start, unit, h_packed, h_offsets, h_out_len, h_status,
+                    align=16):
+        """Host tensors in, ONE packed stream buffer + CSR offsets (int64 [S+1]) out."""
         S, P = h_ts.shape
         rc = capi.lib().m3tsz_encode_batch_host(
             self.ctx.handle, C.byref(self.opts), _ptr(h_ts), _ptr(h_values), S, P, None,
-            _ptr(h_start), int(unit), None, None, None, None, 0, _ptr(h_out), h_out.shape[1],
-            _ptr(h_out_len), _ptr(h_status))
+            _ptr(h_start), int(unit), None, None, None, None, 0, int(align), _ptr(h_packed),
+            h_packed.numel(), _ptr(h_offsets), _ptr(h_out_len), _ptr(h_status))
         self.ctx.check(rc, "m3tsz_encode_batch_host")
 
     def decode_downsample_host(self, h_streams, h_offsets, range_start_ns, window_ns, n_windows,

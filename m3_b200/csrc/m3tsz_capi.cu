@@ -357,23 +357,29 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
                             const uint32_t *h_n_points, const int64_t *h_start, int32_t unit,
                             const uint8_t *h_units, const uint64_t *h_ann_series_off,
                             const m3tsz_annotation_entry *h_ann_entries,
-                            const uint8_t *h_ann_bytes, uint64_t ann_bytes_len, uint8_t *h_out,
-                            uint64_t out_stride, uint64_t *h_out_len, int32_t *h_status) {
+                            const uint8_t *h_ann_bytes, uint64_t ann_bytes_len, uint32_t align,
+                            uint8_t *h_packed, uint64_t packed_capacity, uint64_t *h_offsets,
+                            uint64_t *h_out_len, int32_t *h_status) {
   if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
   if (n_series == 0) return M3TSZ_OK;
-  if (!h_ts || !h_val || !h_start || !h_out || !h_out_len) return M3TSZ_ERR_INVALID_ARG;
+  if (!h_ts || !h_val || !h_start || !h_packed || !h_offsets) return M3TSZ_ERR_INVALID_ARG;
+  if (!(align == 1 || align == 4 || align == 8 || align == 16)) return M3TSZ_ERR_INVALID_ARG;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const size_t nb = (size_t)n_series * points_stride * 8;
+  uint64_t ann_total = h_ann_series_off ? ann_bytes_len + 16 * h_ann_series_off[n_series] : 0;
+  const uint64_t out_stride = m3tsz_encode_bound(points_stride) + ((ann_total + 15) & ~15ull);
   void *d_ts, *d_val, *d_np = nullptr, *d_start, *d_units = nullptr, *d_aoff = nullptr,
-                      *d_aent = nullptr, *d_abytes = nullptr, *d_out, *d_len, *d_st;
+                      *d_aent = nullptr, *d_abytes = nullptr, *d_out, *d_len, *d_st, *d_packed, *d_off;
   int rc;
   if ((rc = ensure(ctx, 2, nb, &d_ts))) return rc;
   if ((rc = ensure(ctx, 3, nb, &d_val))) return rc;
-  if ((rc = ensure(ctx, 1, n_series * 8, &d_start))) return rc;
-  if ((rc = ensure(ctx, 0, n_series * out_stride, &d_out))) return rc;
+  if ((rc = ensure(ctx, 1, (n_series + 1) * 8, &d_start))) return rc;
+  if ((rc = ensure(ctx, 8, n_series * out_stride, &d_out))) return rc;
   if ((rc = ensure(ctx, 12, n_series * 8, &d_len))) return rc;
   if ((rc = ensure(ctx, 5, n_series * 4, &d_st))) return rc;
+  if ((rc = ensure(ctx, 0, packed_capacity + 16, &d_packed))) return rc;
+  if ((rc = ensure(ctx, 9, (n_series + 1) * 8, &d_off))) return rc;
   CK(cudaMemcpyAsync(d_ts, h_ts, nb, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_val, h_val, nb, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_start, h_start, n_series * 8, cudaMemcpyHostToDevice, st));
@@ -403,9 +409,17 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
                           (const m3tsz_annotation_entry *)d_aent, (const uint8_t *)d_abytes,
                           (uint8_t *)d_out, out_stride, (uint64_t *)d_len, (int32_t *)d_st, st);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h_out, d_out, n_series * out_stride, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(h_out_len, d_len, n_series * 8, cudaMemcpyDeviceToHost, st));
+  rc = m3tsz_compact_streams(ctx, (const uint8_t *)d_out, out_stride, (const uint64_t *)d_len,
+                             n_series, align, (uint8_t *)d_packed, packed_capacity,
+                             (uint64_t *)d_off, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_offsets, d_off, (n_series + 1) * 8, cudaMemcpyDeviceToHost, st));
+  if (h_out_len) CK(cudaMemcpyAsync(h_out_len, d_len, n_series * 8, cudaMemcpyDeviceToHost, st));
   if (h_status) CK(cudaMemcpyAsync(h_status, d_st, n_series * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const uint64_t total = h_offsets[n_series];
+  if (total > packed_capacity) return M3TSZ_ERR_CAPACITY;
+  CK(cudaMemcpyAsync(h_packed, d_packed, total, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return M3TSZ_OK;
 }

@@ -21,7 +21,9 @@ namespace m3tsz {
 constexpr int DEC_WARPS = 4;      // warps per block
 constexpr int DEC_RING = 64;      // staged words per lane (ring buffer, power of two)
 constexpr int DEC_MIRROR = 3;     // rows 64..66 mirror rows 0..2 so 4-word reads never wrap
-constexpr int DEC_FILL = 32;      // words per lane per asynchronous refill
+constexpr int DEC_FILL = 16;      // words per lane per asynchronous refill chunk
+constexpr int DEC_TRIGGER = 32;   // a lane with <= this many staged words ahead triggers a refill event
+constexpr int DEC_ACCEPT = DEC_RING - DEC_FILL;  // lanes with <= this many words ahead take a chunk
 constexpr int DEC_STRIDE = 33;    // tile row stride (words / dwords): conflict-free transposes
 constexpr int DEC_OUT_T = 8;      // output tile rows (datapoints per flush)
 constexpr int DEC_FAST_WORDS = 4; // the fast path reads 4 consecutive words
@@ -354,31 +356,58 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_
                : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+// waits until at most `d` of the most recently committed groups are still in flight
+__device__ __forceinline__ void cp_async_wait_pending(uint32_t d) {
+  switch (d) {
+    case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;  // stricter than needed
+  }
+}
 
 // Warp-cooperative asynchronous refill: for every lane j in `mask`, copies the
-// DEC_FILL words starting at global word my_gw (of lane j) into lane j's ring
-// column.  Ring slot of a word == its global word index & (DEC_RING-1) (every
-// stream's base is DEC_RING-word aligned), slots 0..2 are mirrored to 64..66.
+// DEC_FILL (=16) words starting at global word index my_gw (of lane j, always a
+// multiple of 16) into lane j's ring column; one instruction serves two series
+// (lanes 0-15 -> series 2i, lanes 16-31 -> series 2i+1).  Ring slot of a word ==
+// its global word index & (DEC_RING-1) (every stream's base is DEC_RING-word
+// aligned); slots 0..2 are mirrored to 64..66 so 4-word reads never wrap.
 __device__ __forceinline__ void ring_fill(uint32_t *ring, const uint8_t *streams, uint64_t nbytes,
                                           uint32_t mask, uint32_t my_gw, int lane) {
-  const uint32_t ring_sa = smem_addr(ring);
-  // lanes whose whole refill lies inside the buffer take the unchecked path
-  const uint32_t inb = __ballot_sync(FULL_MASK, ((uint64_t)my_gw + DEC_FILL) * 4ull <= nbytes);
-  while (mask) {
-    const int j = __ffs((int)mask) - 1;
-    mask &= mask - 1;
-    const uint32_t gw = __shfl_sync(FULL_MASK, my_gw, j) + (uint32_t)lane;
-    const uint32_t slot = gw & (DEC_RING - 1);
-    const uint32_t dst = ring_sa + (slot * DEC_STRIDE + (uint32_t)j) * 4u;
-    const uint64_t b = (uint64_t)gw * 4ull;
-    uint32_t nb = 4;
-    const uint8_t *src = streams + b;
-    if (!((inb >> j) & 1u)) {
-      nb = (b + 4 <= nbytes) ? 4u : (b < nbytes ? (uint32_t)(nbytes - b) : 0u);
-      if (nb == 0) src = streams;
+  const int sub = lane & 15, half = lane >> 4;
+  const uint32_t lane_dst = smem_addr(ring) + (uint32_t)sub * (DEC_STRIDE * 4u) + (uint32_t)half * 4u;
+  const uint8_t *lane_src = streams + (uint32_t)sub * 4u;
+  const uint32_t safe_words = (uint32_t)(nbytes >> 2);  // complete words in the buffer
+  const bool all_inb = __all_sync(FULL_MASK, my_gw + DEC_FILL <= safe_words);
+  if (mask == FULL_MASK && all_inb) {
+#pragma unroll 8
+    for (int i = 0; i < 16; i++) {
+      const uint32_t gw = __shfl_sync(FULL_MASK, my_gw, 2 * i + half);
+      const uint32_t slot0 = gw & (DEC_RING - 1);
+      const uint32_t dst = lane_dst + slot0 * (DEC_STRIDE * 4u) + (uint32_t)i * 8u;
+      const uint8_t *src = lane_src + (uint64_t)gw * 4ull;
+      cp_async4(dst, src, 4u);
+      if (sub < DEC_MIRROR && slot0 == 0) cp_async4(dst + DEC_RING * DEC_STRIDE * 4u, src, 4u);
     }
-    cp_async4(dst, src, nb);
-    if (slot < (uint32_t)DEC_MIRROR) cp_async4(dst + DEC_RING * DEC_STRIDE * 4u, src, nb);
+    return;
+  }
+  for (int i = 0; i < 16; i++) {
+    if (!((mask >> (2 * i)) & 3u)) continue;  // warp-uniform
+    const int j = 2 * i + half;
+    const uint32_t gw = __shfl_sync(FULL_MASK, my_gw, j);
+    if ((mask >> j) & 1u) {
+      const uint32_t slot0 = gw & (DEC_RING - 1);
+      const uint32_t dst = lane_dst + slot0 * (DEC_STRIDE * 4u) + (uint32_t)i * 8u;
+      const uint64_t b = ((uint64_t)gw + (uint32_t)sub) * 4ull;
+      const uint32_t nb = (b + 4 <= nbytes) ? 4u : (b < nbytes ? (uint32_t)(nbytes - b) : 0u);
+      const uint8_t *src = nb ? (streams + b) : streams;
+      cp_async4(dst, src, nb);
+      if (sub < DEC_MIRROR && slot0 == 0) cp_async4(dst + DEC_RING * DEC_STRIDE * 4u, src, nb);
+    }
   }
 }
 
@@ -457,34 +486,47 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)
   const int64_t range_end = p.range_start + (int64_t)p.n_windows * p.window;
   (void)range_end;
 
-  uint32_t filled = s.pos >> 5;  // words [.., filled) have been requested (relative to wbase)
-  uint32_t safe = filled;        // words [.., safe) have landed in the ring
-  uint32_t iter = 0;             // warp-uniform datapoint index
-  uint32_t tile_row0 = 0;        // datapoint index of output tile row 0
+  // refills are DEC_FILL-word aligned: start at the stream's first word rounded down
+  uint32_t filled = (s.pos >> 5) & ~(uint32_t)(DEC_FILL - 1);  // words [.., filled) requested
+  uint32_t safe = filled;                                       // words [.., safe) have landed
+  uint32_t iter = 0;       // warp-uniform datapoint index
+  uint32_t tile_row0 = 0;  // datapoint index of output tile row 0
+  // scheme/unit admit the fast path (they only change on the slow path)
+  bool su_ok = false;
 
   for (;;) {
     const bool active = !s.done && s.err == 0;
     if (!__any_sync(FULL_MASK, active)) break;
 
-    // ---- ring maintenance: wait for the refill in flight, request the next ----
-    uint32_t cw = s.pos >> 5;
+    // ---- ring maintenance ----
+    // A refill EVENT is warp-wide: it first waits for the previous event's copies
+    // (issued >= 4 datapoints ago, so normally already landed), then every lane
+    // with room takes another 16-word chunk.  The lane that is furthest ahead
+    // triggers the event while it still has ~28 landed words in hand, and after
+    // an event every lane has >= 49 words requested, so events cannot cluster.
+    const uint32_t cw = s.pos >> 5;
     {
       int avail = (int)(filled - cw);
-      if (__any_sync(FULL_MASK, active && (avail <= DEC_RING - DEC_FILL || cw + DEC_FAST_WORDS > safe))) {
+      if (__any_sync(FULL_MASK, active && avail <= DEC_TRIGGER)) {
         cp_async_wait_all();
         __syncwarp();
         if (avail < 0) {  // the slow path skipped past the ring (annotation): restart at cw
-          filled = cw;
-          avail = 0;
+          filled = cw & ~(uint32_t)(DEC_FILL - 1);
+          avail = (int)(filled - cw);
         }
         safe = filled;
-        const uint32_t fmask = __ballot_sync(FULL_MASK, active && avail <= DEC_RING - DEC_FILL);
-        if (fmask) {
+#pragma unroll 1
+        for (int rep = 0; rep < 3; rep++) {
+          const uint32_t fmask = __ballot_sync(FULL_MASK, active && avail <= DEC_ACCEPT);
+          if (!fmask) break;
           ring_fill(ring, p.streams, p.streams_bytes, fmask, gbase + filled, lane);
-          if ((fmask >> lane) & 1u) filled += DEC_FILL;
+          if ((fmask >> lane) & 1u) {
+            filled += DEC_FILL;
+            avail += DEC_FILL;
+          }
         }
         if (__any_sync(FULL_MASK, active && cw + DEC_FAST_WORDS > safe && filled > safe)) {
-          cp_async_wait_all();  // start-up / restart only: nothing staged yet
+          cp_async_wait_all();  // start-up / restart only: nothing landed yet
           __syncwarp();
           safe = filled;
         }
@@ -501,8 +543,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)
                    w3 = __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123);
     const uint32_t sh = s.pos & 31u;
     const uint32_t h = __funnelshift_l(w1, w0, sh);
-    bool ok = active && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0) &&
-              (s.scheme == kScheme32 || s.scheme == kScheme64) && (s.unit >= 1 && s.unit <= 4);
+    bool ok = active && su_ok && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
     uint32_t c = 1;  // bits consumed before the payload
     int64_t dod = 0;
     if (__any_sync(FULL_MASK, ok && (h >> 31))) {  // some lane has a non-zero delta-of-delta
@@ -539,7 +580,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)
       n = 0;
       hb = 1;
     }
-    if (!k_float) {
+    if (INT_OPT && !k_float) {
       hb = 0;
       n = k_int ? s.sig + 1 : 0;
     }
@@ -547,26 +588,63 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)
     const uint64_t field = extract64(w0, w1, w2, w3, sh + c);
     const uint64_t payload = n ? (field >> (64 - n)) : 0ull;
     c += (uint32_t)n;
-    if (ok) {
-      if (s.pos + c > s.end) {
-        s.err = M3TSZ_ERR_EOF;  // truncated stream: the datapoint is not produced
+    const bool ok2 = ok && (s.pos + c <= s.end);
+    if (__all_sync(FULL_MASK, ok2 || !active)) {
+      // hot: every live lane takes the fast path -> unconditional state update
+      // (finished lanes compute garbage they never read again)
+      s.pos += c;
+      s.prev_delta = (int64_t)((uint64_t)s.prev_delta + (uint64_t)dod);
+      s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
+      if (!INT_OPT) {
+        const uint64_t xr = (tz < 0) ? 0ull : (payload << tz);
+        s.prev_xor = xr;
+        s.prev_bits ^= xr;
+        lz_tz(xr, plz, ptz);
       } else {
-        s.pos += c;
-        s.prev_delta = (int64_t)((uint64_t)s.prev_delta + (uint64_t)dod);
-        s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
-        if (k_float) {
-          const uint64_t xr = (tz < 0) ? 0ull : (payload << tz);
-          s.prev_xor = xr;
-          s.prev_bits ^= xr;
-          lz_tz(xr, plz, ptz);
+        const uint64_t xr = (k_float && tz >= 0) ? (payload << tz) : 0ull;
+        s.prev_bits ^= xr;
+        int nlz, ntz;
+        lz_tz(xr, nlz, ntz);
+        s.prev_xor = k_float ? xr : s.prev_xor;
+        plz = k_float ? nlz : plz;
+        ptz = k_float ? ntz : ptz;
+      }
+      t = s.prev_time;
+      v = s.prev_bits;
+      emitted = active;
+    } else {
+      if (ok) {
+        if (!ok2) {
+          s.err = M3TSZ_ERR_EOF;  // truncated stream: the datapoint is not produced
+        } else {
+          s.pos += c;
+          s.prev_delta = (int64_t)((uint64_t)s.prev_delta + (uint64_t)dod);
+          s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
+          if (k_float) {
+            const uint64_t xr = (tz < 0) ? 0ull : (payload << tz);
+            s.prev_xor = xr;
+            s.prev_bits ^= xr;
+            lz_tz(xr, plz, ptz);
+          }
+          t = s.prev_time;
+          v = s.prev_bits;
+          emitted = true;
         }
-        t = s.prev_time;
-        v = s.prev_bits;
-        emitted = true;
+      } else if (active) {  // complete grammar, from global memory
+        DecState tmp = s;   // copy-in / copy-out keeps the lane state in registers
+        int64_t st = 0;
+        uint64_t sv = 0;
+        const bool em = decode_dp_slow<INT_OPT>(tmp, p.streams, p.streams_bytes, p.default_unit, st, sv);
+        s = tmp;
+        t = st;
+        v = sv;
+        emitted = em;
+        lz_tz(s.prev_xor, plz, ptz);
+        su_ok = (s.scheme == kScheme32 || s.scheme == kScheme64) && (s.unit >= 1 && s.unit <= 4);
       }
     }
-    if (INT_OPT && __any_sync(FULL_MASK, emitted && !s.is_float)) {  // int-mode lanes
-      if (emitted && !s.is_float) {
+    if (INT_OPT && __any_sync(FULL_MASK, emitted && ok && !s.is_float)) {  // int-mode lanes (fast path)
+      if (emitted && ok && !s.is_float) {
         if (k_int) {
           const uint64_t neg = payload >> s.sig;
           const uint64_t mag = payload & ((1ull << s.sig) - 1ull);
@@ -575,18 +653,6 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)
         }
         const double dv = s.mult ? __ddiv_rn(s.int_val, mult_pow10(s.mult)) : s.int_val;
         v = (uint64_t)__double_as_longlong(dv);
-      }
-    }
-    if (__any_sync(FULL_MASK, active && !ok)) {  // complete grammar, from global memory
-      if (active && !ok) {
-        DecState tmp = s;  // copy-in / copy-out keeps the lane state in registers
-        int64_t st = 0;
-        uint64_t sv = 0;
-        emitted = decode_dp_slow<INT_OPT>(tmp, p.streams, p.streams_bytes, p.default_unit, st, sv);
-        s = tmp;
-        t = st;
-        v = sv;
-        lz_tz(s.prev_xor, plz, ptz);
       }
     }
 

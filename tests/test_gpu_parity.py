@@ -408,20 +408,20 @@ def test_host_entry_points(codecs):
     S, P = 1000, 200
     ts, vals, start = synth.gaussian_walk(S, P, "cpu", seed=3)
     codec = codecs[True]
-    stride = codec.encode_bound(P)
-    h_out = torch.empty((S, stride), dtype=torch.uint8).pin_memory()
+    h_packed = torch.empty(S * (P * 9 + 64), dtype=torch.uint8).pin_memory()
+    h_off = torch.empty(S + 1, dtype=torch.int64).pin_memory()
     h_len = torch.empty(S, dtype=torch.int64).pin_memory()
     h_st = torch.empty(S, dtype=torch.int32).pin_memory()
-    codec.encode_host(ts.pin_memory(), vals.pin_memory(), start, O.UNIT_S, h_out, h_len, h_st)
+    codec.encode_host(ts.pin_memory(), vals.pin_memory(), start, O.UNIT_S, h_packed, h_off, h_len,
+                      h_st, align=1)
     assert (h_st == 0).all()
     o_out, o_len, _ = O.encode_batch(ts.numpy(), vals.numpy(), int(start[0]), O.UNIT_S, True, n_threads=4)
     assert (h_len.numpy() == o_len.astype(np.int64)).all()
-    streams = [h_out[s, : h_len[s]].numpy().tobytes() for s in range(S)]
+    off = h_off.numpy().copy()
+    assert off[0] == 0 and (np.diff(off) == h_len.numpy()).all()
+    streams = [h_packed[off[s]: off[s + 1]].numpy().tobytes() for s in range(S)]
     assert all(streams[s] == o_out[s, : o_len[s]].tobytes() for s in range(S))
-    blob = b"".join(streams)
-    off = np.zeros(S + 1, dtype=np.int64)
-    off[1:] = np.cumsum([len(s) for s in streams])
-    h_streams = torch.frombuffer(bytearray(blob), dtype=torch.uint8)
+    h_streams = h_packed[: off[-1]].clone()
     h_ts = torch.empty((S, P), dtype=torch.int64)
     h_vals = torch.empty((S, P), dtype=torch.float64)
     h_n = torch.empty(S, dtype=torch.int32)
