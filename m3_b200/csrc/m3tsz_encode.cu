@@ -23,12 +23,12 @@ namespace m3tsz {
 
 constexpr int ENC_WARPS = 4;
 constexpr int ENC_STRIDE = 33;
-constexpr int ENC_IN_T = 16;    // datapoints staged per input tile
-constexpr int ENC_OUT_W = 64;   // output tile words per lane
+constexpr int ENC_IN_T = 8;     // datapoints per input tile (double buffered, cp.async)
+constexpr int ENC_OUT_W = 40;   // output tile words per lane
 constexpr int ENC_GUARD = 10;   // words a single datapoint (no annotation) may add
-constexpr int ENC_IN_TILE_DWORDS = ENC_IN_T * ENC_STRIDE;
+constexpr int ENC_IN_TILE_DWORDS = ENC_IN_T * ENC_STRIDE;   // one array (ts or val), one buffer
 constexpr int ENC_OUT_TILE_WORDS = ENC_OUT_W * ENC_STRIDE;
-constexpr size_t ENC_WARP_SMEM = 2 * (size_t)ENC_IN_TILE_DWORDS * 8 + (size_t)ENC_OUT_TILE_WORDS * 4;
+constexpr size_t ENC_WARP_SMEM = 4 * (size_t)ENC_IN_TILE_DWORDS * 8 + (size_t)ENC_OUT_TILE_WORDS * 4;
 
 struct EncLane {
   uint32_t carry, sh, k, words_out;
@@ -407,15 +407,22 @@ __device__ __forceinline__ void encode_time(EncLane &s, uint32_t *tile, int lane
   }
 }
 
+__device__ __forceinline__ uint32_t enc_smem_addr(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void enc_cp_async8(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
+}
+
 template <bool INT_OPT>
-__global__ void __launch_bounds__(ENC_WARPS * 32) encode_kernel(const EncodeParams p) {
+__global__ void __launch_bounds__(ENC_WARPS * 32, 4) encode_kernel(const EncodeParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   uint8_t *wbase = reinterpret_cast<uint8_t *>(smem) + warp * ENC_WARP_SMEM;
-  uint64_t *ts_tile = reinterpret_cast<uint64_t *>(wbase);
-  uint64_t *val_tile = ts_tile + ENC_IN_TILE_DWORDS;
-  uint32_t *out_tile = reinterpret_cast<uint32_t *>(val_tile + ENC_IN_TILE_DWORDS);
+  // in_tiles: [buffer][array (0 ts, 1 val)][row][lane]
+  uint64_t *in_tiles = reinterpret_cast<uint64_t *>(wbase);
+  uint32_t *out_tile = reinterpret_cast<uint32_t *>(in_tiles + 4 * ENC_IN_TILE_DWORDS);
 
   const uint64_t warp_s0 = ((uint64_t)blockIdx.x * ENC_WARPS + warp) * 32ull;
   if (warp_s0 >= p.n_series) return;
@@ -467,52 +474,92 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_kernel(const EncodePara
       }
     }
   }
+  const uint32_t max_pts = __reduce_max_sync(FULL_MASK, n_pts);
 
-  // writes every lane's staged words to its slot (coalesced per series)
+  // Lane-local flush: every lane streams the complete 16-byte groups of ITS OWN
+  // column to its slot (big-endian byte order) and keeps the <= 3 leftover words.
+  uint8_t *my_out = p.out + sidx * p.out_stride;
   auto flush_out = [&]() {
     __syncwarp();
-    uint8_t *my_dst = p.out + sidx * p.out_stride + (uint64_t)s.words_out * 4ull;
-#pragma unroll 2
-    for (int j = 0; j < 32; j++) {
-      const uint32_t kj = __shfl_sync(FULL_MASK, s.k, j);
-      uint8_t *dst = reinterpret_cast<uint8_t *>(
-          __shfl_sync(FULL_MASK, (unsigned long long)my_dst, j));
-      for (uint32_t i = lane; i < kj; i += 32) {
-        const uint32_t w = out_tile[i * ENC_STRIDE + j];
-        reinterpret_cast<uint32_t *>(dst)[i] = __byte_perm(w, 0, 0x0123);
+    const uint32_t kmax = __reduce_max_sync(FULL_MASK, s.k);
+    const uint32_t full = s.k >> 2;
+    uint4 *dst = reinterpret_cast<uint4 *>(my_out + (uint64_t)s.words_out * 4ull);
+    for (uint32_t q = 0; q < (kmax >> 2); q++) {
+      if (q < full) {
+        const uint32_t *tp = out_tile + (4 * q) * ENC_STRIDE + lane;
+        uint4 v;
+        v.x = __byte_perm(tp[0], 0, 0x0123);
+        v.y = __byte_perm(tp[ENC_STRIDE], 0, 0x0123);
+        v.z = __byte_perm(tp[2 * ENC_STRIDE], 0, 0x0123);
+        v.w = __byte_perm(tp[3 * ENC_STRIDE], 0, 0x0123);
+        dst[q] = v;
       }
     }
+    const uint32_t rem = s.k & 3u;
+    uint32_t r0 = 0, r1 = 0, r2 = 0;
+    {
+      const uint32_t *tp = out_tile + (4 * full) * ENC_STRIDE + lane;
+      if (rem > 0) r0 = tp[0];
+      if (rem > 1) r1 = tp[ENC_STRIDE];
+      if (rem > 2) r2 = tp[2 * ENC_STRIDE];
+    }
     __syncwarp();
-    s.words_out += s.k;
-    s.k = 0;
+    if (rem > 0) out_tile[lane] = r0;
+    if (rem > 1) out_tile[ENC_STRIDE + lane] = r1;
+    if (rem > 2) out_tile[2 * ENC_STRIDE + lane] = r2;
+    s.words_out += 4 * full;
+    s.k = rem;
+    __syncwarp();
   };
 
+  // asynchronous staging of input tile `tile` (rows tile*ENC_IN_T ..) into buffer tile&1:
+  // lanes 0-7 / 8-15: ts / value rows of series 2i, lanes 16-23 / 24-31: of series 2i+1
+  const int st_r = lane & (ENC_IN_T - 1);
+  const int st_arr = (lane >> 3) & 1;
+  const int st_jo = lane >> 4;
+  const bool uniform_n = __all_sync(FULL_MASK, !valid || n_pts == max_pts) && __all_sync(FULL_MASK, valid);
+  auto stage = [&](uint32_t tile) {
+    const uint32_t row0 = tile * ENC_IN_T;
+    if (row0 >= max_pts) return;
+    const uint64_t *src = (st_arr ? reinterpret_cast<const uint64_t *>(p.val)
+                                  : reinterpret_cast<const uint64_t *>(p.ts)) +
+                          (warp_s0 + st_jo) * p.points_stride + row0 + st_r;
+    const uint32_t dst0 = enc_smem_addr(in_tiles + ((tile & 1u) * 2u + (uint32_t)st_arr) * ENC_IN_TILE_DWORDS +
+                                        st_r * ENC_STRIDE + st_jo);
+    const uint64_t step = 2ull * p.points_stride;
+    if (uniform_n && row0 + ENC_IN_T <= max_pts) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        enc_cp_async8(dst0 + (uint32_t)i * 16u, src);
+        src += step;
+      }
+    } else {
+      for (int i = 0; i < 16; i++) {
+        const uint32_t nj = __shfl_sync(FULL_MASK, (valid && s.err == 0) ? n_pts : 0u, 2 * i + st_jo);
+        if (row0 + (uint32_t)st_r < nj) enc_cp_async8(dst0 + (uint32_t)i * 16u, src);
+        src += step;
+      }
+    }
+  };
+
+  stage(0);
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+
   uint32_t iter = 0;
-  uint32_t in_row0 = 0;
-  bool in_valid = false;
   for (;;) {
     const bool active = valid && s.err == 0 && iter < n_pts;
     if (!__any_sync(FULL_MASK, active)) break;
 
-    // ---- stage inputs: ENC_IN_T datapoints of each of the 32 series ----
-    if (!in_valid || iter - in_row0 == (uint32_t)ENC_IN_T) {
-      in_row0 = iter;
-      in_valid = true;
-      const int r = lane & (ENC_IN_T - 1);
-      const bool isval = lane >= ENC_IN_T;
-      const uint64_t *src0 = (isval ? reinterpret_cast<const uint64_t *>(p.val)
-                                    : reinterpret_cast<const uint64_t *>(p.ts)) +
-                             warp_s0 * p.points_stride + in_row0 + r;
-      uint64_t *tile = isval ? val_tile : ts_tile;
-      const uint32_t my_n = active ? n_pts : 0u;
-      __syncwarp();
-#pragma unroll 4
-      for (int j = 0; j < 32; j++) {
-        const uint32_t nj = __shfl_sync(FULL_MASK, my_n, j);
-        if (in_row0 + (uint32_t)r < nj) tile[r * ENC_STRIDE + j] = __ldg(src0 + (uint64_t)j * p.points_stride);
-      }
+    // ---- input pipeline: request tile t+1, wait for tile t ----
+    if ((iter & (ENC_IN_T - 1)) == 0) {
+      __syncwarp();  // everyone is done reading the buffer about to be overwritten
+      stage(iter / ENC_IN_T + 1);
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
       __syncwarp();
     }
+    const uint64_t *ts_tile = in_tiles + (((iter / ENC_IN_T) & 1u) * 2u) * ENC_IN_TILE_DWORDS;
+    const uint64_t *val_tile = ts_tile + ENC_IN_TILE_DWORDS;
 
     // ---- make room in the output tile ----
     const bool tight = active && (s.k > (uint32_t)(ENC_OUT_W - ENC_GUARD));
@@ -522,52 +569,54 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_kernel(const EncodePara
     bool want_ann = false;
     uint64_t a_off = 0;
     uint32_t a_len = 0;
-    if (active && ann_i < ann_end) {
-      const m3tsz_annotation_entry e = p.ann_entries[ann_i];
-      if (e.dp_index == iter) {
-        ann_i++;
-        a_off = e.byte_offset;
-        a_len = e.length;
-        if (a_len > 0) {
-          // rewritten only when it differs from the last annotation written
-          // (xxhash64 inequality in the reference == byte inequality here)
-          bool same = (a_len == last_ann_len);
-          for (uint32_t i = 0; same && i < a_len; i++)
-            same = p.ann_bytes[a_off + i] == p.ann_bytes[last_ann_off + i];
-          want_ann = !same;
-        }
-      }
-    }
-    if (__any_sync(FULL_MASK, want_ann)) {
-      uint32_t rem = 0, done_bytes = 0;
-      if (want_ann) {
-        put32(s, out_tile, lane, (kMarkerOpcode << 2) | (uint32_t)kMarkerAnnotation, kMarkerBits);
-        uint64_t ux = ((uint64_t)(a_len - 1)) << 1;  // binary.PutVarint(len-1), len >= 1
-        while (ux >= 0x80) {
-          put32(s, out_tile, lane, (uint32_t)(ux & 0x7f) | 0x80u, 8);
-          ux >>= 7;
-        }
-        put32(s, out_tile, lane, (uint32_t)ux, 8);
-        rem = a_len;
-        last_ann_off = a_off;
-        last_ann_len = a_len;
-      }
-      for (;;) {
-        if (rem > 0) {
-          // capacity: stop this series rather than overrun its slot
-          const uint64_t need_words = (uint64_t)s.words_out + s.k + (rem + 3) / 4 + ENC_GUARD + 4;
-          if (need_words > slot_words) {
-            s.err = M3TSZ_ERR_CAPACITY;
-            rem = 0;
+    if (p.ann_series_off) {
+      if (active && ann_i < ann_end) {
+        const m3tsz_annotation_entry e = p.ann_entries[ann_i];
+        if (e.dp_index == iter) {
+          ann_i++;
+          a_off = e.byte_offset;
+          a_len = e.length;
+          if (a_len > 0) {
+            // rewritten only when it differs from the last annotation written
+            // (xxhash64 inequality in the reference == byte inequality here)
+            bool same = (a_len == last_ann_len);
+            for (uint32_t i = 0; same && i < a_len; i++)
+              same = p.ann_bytes[a_off + i] == p.ann_bytes[last_ann_off + i];
+            want_ann = !same;
           }
         }
-        while (rem > 0 && s.k < (uint32_t)(ENC_OUT_W - ENC_GUARD)) {
-          put32(s, out_tile, lane, (uint32_t)p.ann_bytes[a_off + done_bytes], 8);
-          done_bytes++;
-          rem--;
+      }
+      if (__any_sync(FULL_MASK, want_ann)) {
+        uint32_t rem = 0, done_bytes = 0;
+        if (want_ann) {
+          put32(s, out_tile, lane, (kMarkerOpcode << 2) | (uint32_t)kMarkerAnnotation, kMarkerBits);
+          uint64_t ux = ((uint64_t)(a_len - 1)) << 1;  // binary.PutVarint(len-1), len >= 1
+          while (ux >= 0x80) {
+            put32(s, out_tile, lane, (uint32_t)(ux & 0x7f) | 0x80u, 8);
+            ux >>= 7;
+          }
+          put32(s, out_tile, lane, (uint32_t)ux, 8);
+          rem = a_len;
+          last_ann_off = a_off;
+          last_ann_len = a_len;
         }
-        if (!__any_sync(FULL_MASK, rem > 0)) break;
-        flush_out();
+        for (;;) {
+          if (rem > 0) {
+            // capacity: stop this series rather than overrun its slot
+            const uint64_t need_words = (uint64_t)s.words_out + s.k + (rem + 3) / 4 + ENC_GUARD + 4;
+            if (need_words > slot_words) {
+              s.err = M3TSZ_ERR_CAPACITY;
+              rem = 0;
+            }
+          }
+          while (rem > 0 && s.k < (uint32_t)(ENC_OUT_W - ENC_GUARD)) {
+            put32(s, out_tile, lane, (uint32_t)p.ann_bytes[a_off + done_bytes], 8);
+            done_bytes++;
+            rem--;
+          }
+          if (!__any_sync(FULL_MASK, rem > 0)) break;
+          flush_out();
+        }
       }
     }
 
@@ -576,7 +625,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_kernel(const EncodePara
       if ((uint64_t)s.words_out + s.k + ENC_GUARD + 4 > slot_words) {
         s.err = M3TSZ_ERR_CAPACITY;
       } else {
-        const int row = (int)(iter - in_row0);
+        const int row = (int)(iter & (ENC_IN_T - 1));
         const int64_t t = (int64_t)ts_tile[row * ENC_STRIDE + lane];
         const double v = __longlong_as_double((long long)val_tile[row * ENC_STRIDE + lane]);
         const int u = p.units ? (int)p.units[sidx * p.points_stride + iter] : p.unit;
@@ -594,6 +643,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_kernel(const EncodePara
     }
     iter++;
   }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
 
   // ---- tail: end-of-stream marker + zero padding (scheme.go:198-211) ----
   uint64_t total_bits = 0;
@@ -606,9 +656,16 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_kernel(const EncodePara
       s.carry = 0;
       s.sh = 0;
     }
+    // pad to a whole 16-byte group (zeros; bytes past out_len are unspecified)
+    while (s.k & 3u) {
+      out_tile[s.k * ENC_STRIDE + lane] = 0u;
+      s.k++;
+    }
   } else if (valid) {
     s.k = 0;  // nothing encoded: empty stream (encoder.go:285-289)
     s.words_out = 0;
+  } else {
+    s.k = 0;
   }
   flush_out();
   if (valid) {
