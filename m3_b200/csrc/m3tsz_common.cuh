@@ -70,8 +70,10 @@ __device__ __forceinline__ int64_t sign_extend(uint64_t v, int n) {
 
 // encoding.LeadingAndTrailingZeros (encoding.go:33-43): (64, 0) for v == 0
 __device__ __forceinline__ void lz_tz(uint64_t v, int &lz, int &tz) {
-  lz = __clzll((long long)v);
-  tz = v ? (__ffsll((long long)v) - 1) : 0;
+  const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  lz = hi ? __clz((int)hi) : 32 + __clz((int)lo);  // 64 for v == 0
+  const int tlo = __clz((int)__brev(lo)), thi = 32 + __clz((int)__brev(hi));
+  tz = lo ? tlo : (hi ? thi : 0);
 }
 
 __device__ __forceinline__ int num_sig(uint64_t v) { return 64 - __clzll((long long)v); }  // encoding.go:29-31

@@ -517,7 +517,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)
         safe = filled;
 #pragma unroll 1
         for (int rep = 0; rep < 3; rep++) {
-          const uint32_t fmask = __ballot_sync(FULL_MASK, active && avail <= DEC_ACCEPT);
+          // first pass: everyone with room tops up; later passes only serve lanes that
+          // are still short (start-up / after a restart)
+          const uint32_t fmask =
+              __ballot_sync(FULL_MASK, active && avail <= (rep == 0 ? DEC_ACCEPT : DEC_TRIGGER));
           if (!fmask) break;
           ring_fill(ring, p.streams, p.streams_bytes, fmask, gbase + filled, lane);
           if ((fmask >> lane) & 1u) {
