@@ -2,7 +2,7 @@
 points, 60 s cadence from a day-aligned block start, unit = Second, values a
 Gaussian random walk x0 = 100, x_i = x_{i-1} + N(0,1).  Generated with torch on
 whichever device is asked for; the same tensors feed the GPU codec and (copied
-to the host) the CPU oracle, so both sides see bit-identical inputs."""
+to the host) any CPU-side checker, so both sides see bit-identical inputs."""
 import torch
 
 BLOCK_START_S = 1_599_955_200  # day-aligned => initial time unit = Second

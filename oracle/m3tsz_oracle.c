@@ -1574,27 +1574,47 @@ typedef struct {
 
 static void *batch_worker(void *arg) {
   batch_task *t = (batch_task *)arg;
+  /* one pooled encoder / iterator per worker, Reset between series (the reference
+   * pools them too: encoder_pool.go / iterator_pool.go) */
+  m3o_encoder *enc = NULL;
+  m3o_iter *it = NULL;
+  if (t->kind == 1) enc = m3o_encoder_new(0, t->int_optimized, t->default_unit);
+  if (t->kind == 0) it = m3o_iter_new(NULL, 0, t->int_optimized, t->default_unit);
   for (size_t s = t->lo; s < t->hi; s++) {
     if (t->kind == 0) {
-      int err = 0;
-      int64_t n = m3o_decode_series(t->streams + t->off[s], (size_t)(t->off[s + 1] - t->off[s]),
-                                    t->int_optimized, t->default_unit, t->ts_out + s * t->cap,
-                                    t->val_out + s * t->cap, t->cap, &err);
-      if (t->n_points) t->n_points[s] = (uint32_t)n;
-      if (t->status) t->status[s] = err;
-    } else {
-      int64_t n = m3o_encode_series(t->ts + s * t->n_per, t->vals + s * t->n_per, t->n_per,
-                                    t->start_ns[s], t->unit, t->int_optimized, t->default_unit,
-                                    t->out + s * t->out_stride, t->out_stride);
-      if (n < 0) {
-        if (t->out_len) t->out_len[s] = 0;
-        if (t->status) t->status[s] = (int32_t)(-n);
-      } else {
-        if (t->out_len) t->out_len[s] = (uint64_t)n;
-        if (t->status) t->status[s] = 0;
+      m3o_iter_reset(it, t->streams + t->off[s], (size_t)(t->off[s + 1] - t->off[s]));
+      int64_t *ts_out = t->ts_out + s * t->cap;
+      double *val_out = t->val_out + s * t->cap;
+      size_t n = 0;
+      while (m3o_iter_next(it)) {
+        if (n < t->cap) {
+          ts_out[n] = it->cur_ts;
+          val_out[n] = it->cur_val;
+        }
+        n++;
       }
+      if (t->n_points) t->n_points[s] = (uint32_t)n;
+      if (t->status) t->status[s] = it->err;
+    } else {
+      m3o_encoder_reset(enc, t->start_ns[s]);
+      const int64_t *ts = t->ts + s * t->n_per;
+      const double *vals = t->vals + s * t->n_per;
+      int err = 0;
+      for (size_t i = 0; i < t->n_per; i++) {
+        err = m3o_encoder_encode(enc, ts[i], vals[i], t->unit, NULL, 0);
+        if (err) break;
+      }
+      size_t len = err ? 0 : m3o_encoder_stream(enc, t->out + s * t->out_stride, t->out_stride);
+      if (!err && len > t->out_stride) {
+        err = 1000;
+        len = 0;
+      }
+      if (t->out_len) t->out_len[s] = (uint64_t)len;
+      if (t->status) t->status[s] = err;
     }
   }
+  m3o_encoder_free(enc);
+  m3o_iter_free(it);
   return NULL;
 }
 

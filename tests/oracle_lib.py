@@ -292,32 +292,40 @@ def decode_series(data, int_optimized=True, default_unit=UNIT_S, cap=4096):
 
 
 def encode_batch(ts, vals, start_ns, unit=UNIT_S, int_optimized=True, default_unit=UNIT_S,
-                 out_stride=None, n_threads=1):
-    """ts, vals: [S, P] arrays.  Returns (out[S, stride] uint8, out_len[S] uint64, status[S])."""
+                 out_stride=None, n_threads=1, bufs=None):
+    """ts, vals: [S, P] arrays.  Returns (out[S, stride] uint8, out_len[S] uint64, status[S]).
+    `bufs` = (out, out_len, status) reuses preallocated outputs (timing runs)."""
     ts = np.ascontiguousarray(ts, dtype=np.int64)
     vals = np.ascontiguousarray(vals, dtype=np.float64)
     S, P = ts.shape
     start = np.ascontiguousarray(np.broadcast_to(np.asarray(start_ns, dtype=np.int64), (S,)))
-    if out_stride is None:
-        out_stride = 64 + 20 * P
-    out = np.zeros((S, out_stride), dtype=np.uint8)
-    out_len = np.zeros(S, dtype=np.uint64)
-    status = np.zeros(S, dtype=np.int32)
+    if bufs is not None:
+        out, out_len, status = bufs
+        out_stride = out.shape[1]
+    else:
+        if out_stride is None:
+            out_stride = 64 + 20 * P
+        out = np.zeros((S, out_stride), dtype=np.uint8)
+        out_len = np.zeros(S, dtype=np.uint64)
+        status = np.zeros(S, dtype=np.int32)
     lib().m3o_encode_batch(_ptr(ts), _ptr(vals), S, P, _ptr(start), unit, int(int_optimized),
                            default_unit, _ptr(out), out_stride, _ptr(out_len), _ptr(status),
                            n_threads)
     return out, out_len, status
 
 
-def decode_batch(streams, off, cap, int_optimized=True, default_unit=UNIT_S, n_threads=1):
+def decode_batch(streams, off, cap, int_optimized=True, default_unit=UNIT_S, n_threads=1, bufs=None):
     """streams: uint8 [total]; off: uint64 [S+1].  Returns ts[S,cap], vals[S,cap], n[S], status[S]."""
     streams = np.ascontiguousarray(streams, dtype=np.uint8)
     off = np.ascontiguousarray(off, dtype=np.uint64)
     S = len(off) - 1
-    ts = np.zeros((S, cap), dtype=np.int64)
-    vals = np.zeros((S, cap), dtype=np.float64)
-    n = np.zeros(S, dtype=np.uint32)
-    status = np.zeros(S, dtype=np.int32)
+    if bufs is not None:
+        ts, vals, n, status = bufs
+    else:
+        ts = np.zeros((S, cap), dtype=np.int64)
+        vals = np.zeros((S, cap), dtype=np.float64)
+        n = np.zeros(S, dtype=np.uint32)
+        status = np.zeros(S, dtype=np.int32)
     lib().m3o_decode_batch(_ptr(streams), _ptr(off), S, int(int_optimized), default_unit, _ptr(ts),
                            _ptr(vals), cap, _ptr(n), _ptr(status), n_threads)
     return ts, vals, n, status
