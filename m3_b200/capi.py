@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libm3tsz_b200.so")
+LIB_PATH = os.environ.get("M3TSZ_B200_LIB") or os.path.join(_HERE, "libm3tsz_b200.so")  # env: tuning builds
 
 OK = 0
 ERR_EOF = 1

@@ -23,11 +23,15 @@ struct Scratch {
 
 struct m3tsz_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;  // used by the *_host entry points
+  cudaStream_t stream = nullptr;   // used by the *_host entry points
+  cudaStream_t stream2 = nullptr;  // second lane of the chunked H2D / kernel / D2H pipeline
+  cudaEvent_t ev = nullptr;
   uint64_t launches = 0;
   char last_error[256] = {0};
-  Scratch s[16];
-  int32_t *d_flag = nullptr;
+  Scratch s[40];
+  int32_t *d_flag = nullptr;  // [2]
+  void *h_stage[2] = {nullptr, nullptr};  // pinned staging for per-chunk offsets
+  size_t h_stage_bytes[2] = {0, 0};
 };
 
 namespace {
@@ -61,6 +65,27 @@ int ensure(m3tsz_ctx *ctx, int slot, size_t bytes, void **out) {
   }
   *out = sc.ptr;
   return M3TSZ_OK;
+}
+
+int ensure_stage(m3tsz_ctx *ctx, int i, size_t bytes) {
+  if (ctx->h_stage_bytes[i] >= bytes) return M3TSZ_OK;
+  if (ctx->h_stage[i]) CK(cudaFreeHost(ctx->h_stage[i]));
+  ctx->h_stage[i] = nullptr;
+  ctx->h_stage_bytes[i] = 0;
+  CK(cudaMallocHost(&ctx->h_stage[i], bytes));
+  ctx->h_stage_bytes[i] = bytes;
+  return M3TSZ_OK;
+}
+
+// Series per pipeline chunk: ~8 chunks per call, but never tiny ones.
+uint64_t pick_chunk(uint64_t n_series, uint64_t bytes_per_series) {
+  uint64_t ch = (n_series + 7) / 8;
+  uint64_t min_ch = (16ull << 20) / (bytes_per_series ? bytes_per_series : 1);
+  if (min_ch < 2048) min_ch = 2048;
+  if (ch < min_ch) ch = min_ch;
+  if (ch > n_series) ch = n_series;
+  ch = (ch + 127) & ~127ull;  // whole thread blocks
+  return ch;
 }
 
 bool valid_opts(const m3tsz_options *o) {
@@ -113,7 +138,9 @@ int m3tsz_ctx_create(int device, m3tsz_ctx **out) {
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaMalloc(&ctx->d_flag, sizeof(int32_t)) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaMalloc(&ctx->d_flag, 2 * sizeof(int32_t)) != cudaSuccess) {
     (void)cudaGetLastError();
     delete ctx;
     return M3TSZ_ERR_CUDA;
@@ -128,6 +155,10 @@ void m3tsz_ctx_destroy(m3tsz_ctx *ctx) {
   for (auto &sc : ctx->s)
     if (sc.ptr) cudaFree(sc.ptr);
   if (ctx->d_flag) cudaFree(ctx->d_flag);
+  for (int i = 0; i < 2; i++)
+    if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
+  if (ctx->ev) cudaEventDestroy(ctx->ev);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -283,7 +314,6 @@ int m3tsz_decode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const uin
   if (n_series == 0) return M3TSZ_OK;
   if (!h_streams || !h_offsets || !h_ts || !h_val || max_points == 0) return M3TSZ_ERR_INVALID_ARG;
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
   void *d_streams, *d_off, *d_ts, *d_val, *d_n, *d_st, *d_unit = nullptr, *d_ann = nullptr;
   int rc;
   if ((rc = ensure(ctx, 0, streams_bytes + 16, &d_streams))) return rc;
@@ -294,21 +324,41 @@ int m3tsz_decode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const uin
   if ((rc = ensure(ctx, 5, n_series * 4, &d_st))) return rc;
   if (h_unit && (rc = ensure(ctx, 6, n_series, &d_unit))) return rc;
   if (h_ann && (rc = ensure(ctx, 7, n_series * sizeof(m3tsz_annotation_ref), &d_ann))) return rc;
-  CK(cudaMemcpyAsync(d_streams, h_streams, streams_bytes, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_off, h_offsets, (n_series + 1) * 8, cudaMemcpyHostToDevice, st));
-  rc = m3tsz_decode_batch(ctx, opts, (const uint8_t *)d_streams, streams_bytes,
-                          (const uint64_t *)d_off, n_series, (int64_t *)d_ts, (double *)d_val,
-                          max_points, (uint32_t *)d_n, (int32_t *)d_st, (uint8_t *)d_unit,
-                          (m3tsz_annotation_ref *)d_ann, st);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(h_ts, d_ts, n_series * max_points * 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(h_val, d_val, n_series * max_points * 8, cudaMemcpyDeviceToHost, st));
-  if (h_n_points) CK(cudaMemcpyAsync(h_n_points, d_n, n_series * 4, cudaMemcpyDeviceToHost, st));
-  if (h_status) CK(cudaMemcpyAsync(h_status, d_st, n_series * 4, cudaMemcpyDeviceToHost, st));
-  if (h_unit) CK(cudaMemcpyAsync(h_unit, d_unit, n_series, cudaMemcpyDeviceToHost, st));
-  if (h_ann)
-    CK(cudaMemcpyAsync(h_ann, d_ann, n_series * sizeof(m3tsz_annotation_ref), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  // Chunked pipeline over two streams: the H2D copy of chunk c+1 overlaps the
+  // kernel and the D2H copy of chunk c (PCIe is full duplex).
+  cudaStream_t sts[2] = {ctx->stream, ctx->stream2};
+  CK(cudaMemcpyAsync(d_off, h_offsets, (n_series + 1) * 8, cudaMemcpyHostToDevice, sts[0]));
+  CK(cudaEventRecord(ctx->ev, sts[0]));
+  CK(cudaStreamWaitEvent(sts[1], ctx->ev, 0));
+  const uint64_t per_series = streams_bytes / n_series + max_points * 16;
+  const uint64_t ch = pick_chunk(n_series, per_series);
+  int k = 0;
+  for (uint64_t c0 = 0; c0 < n_series; c0 += ch, k++) {
+    const uint64_t c1 = (c0 + ch < n_series) ? c0 + ch : n_series, n = c1 - c0;
+    cudaStream_t st = sts[k & 1];
+    const uint64_t b0 = h_offsets[c0], b1 = h_offsets[c1];
+    if (b1 < b0 || b1 > streams_bytes) return M3TSZ_ERR_INVALID_ARG;
+    if (b1 > b0)
+      CK(cudaMemcpyAsync((uint8_t *)d_streams + b0, h_streams + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+    rc = m3tsz_decode_batch(ctx, opts, (const uint8_t *)d_streams, streams_bytes,
+                            (const uint64_t *)d_off + c0, n, (int64_t *)d_ts + c0 * max_points,
+                            (double *)d_val + c0 * max_points, max_points, (uint32_t *)d_n + c0,
+                            (int32_t *)d_st + c0, d_unit ? (uint8_t *)d_unit + c0 : nullptr,
+                            d_ann ? (m3tsz_annotation_ref *)d_ann + c0 : nullptr, st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_ts + c0 * max_points, (int64_t *)d_ts + c0 * max_points, n * max_points * 8,
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_val + c0 * max_points, (double *)d_val + c0 * max_points, n * max_points * 8,
+                       cudaMemcpyDeviceToHost, st));
+    if (h_n_points) CK(cudaMemcpyAsync(h_n_points + c0, (uint32_t *)d_n + c0, n * 4, cudaMemcpyDeviceToHost, st));
+    if (h_status) CK(cudaMemcpyAsync(h_status + c0, (int32_t *)d_st + c0, n * 4, cudaMemcpyDeviceToHost, st));
+    if (h_unit) CK(cudaMemcpyAsync(h_unit + c0, (uint8_t *)d_unit + c0, n, cudaMemcpyDeviceToHost, st));
+    if (h_ann)
+      CK(cudaMemcpyAsync(h_ann + c0, (m3tsz_annotation_ref *)d_ann + c0, n * sizeof(m3tsz_annotation_ref),
+                         cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(sts[0]));
+  CK(cudaStreamSynchronize(sts[1]));
   return M3TSZ_OK;
 }
 
@@ -361,35 +411,25 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
                             uint8_t *h_packed, uint64_t packed_capacity, uint64_t *h_offsets,
                             uint64_t *h_out_len, int32_t *h_status) {
   if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
+  if (!h_offsets) return M3TSZ_ERR_INVALID_ARG;
+  h_offsets[0] = 0;
   if (n_series == 0) return M3TSZ_OK;
-  if (!h_ts || !h_val || !h_start || !h_packed || !h_offsets) return M3TSZ_ERR_INVALID_ARG;
+  if (!h_ts || !h_val || !h_start || !h_packed) return M3TSZ_ERR_INVALID_ARG;
   if (!(align == 1 || align == 4 || align == 8 || align == 16)) return M3TSZ_ERR_INVALID_ARG;
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
-  const size_t nb = (size_t)n_series * points_stride * 8;
-  uint64_t ann_total = h_ann_series_off ? ann_bytes_len + 16 * h_ann_series_off[n_series] : 0;
+  cudaStream_t sts[2] = {ctx->stream, ctx->stream2};
+  const uint64_t ann_total = h_ann_series_off ? ann_bytes_len + 16 * h_ann_series_off[n_series] : 0;
   const uint64_t out_stride = m3tsz_encode_bound(points_stride) + ((ann_total + 15) & ~15ull);
-  void *d_ts, *d_val, *d_np = nullptr, *d_start, *d_units = nullptr, *d_aoff = nullptr,
-                      *d_aent = nullptr, *d_abytes = nullptr, *d_out, *d_len, *d_st, *d_packed, *d_off;
+  const uint64_t ch = pick_chunk(n_series, points_stride * 16 + points_stride * 8);
+  const size_t row_bytes = (size_t)points_stride * 8;
   int rc;
-  if ((rc = ensure(ctx, 2, nb, &d_ts))) return rc;
-  if ((rc = ensure(ctx, 3, nb, &d_val))) return rc;
+  // whole-batch device inputs that are small: start, n_points, annotations
+  void *d_start, *d_np = nullptr, *d_aoff = nullptr, *d_aent = nullptr, *d_abytes = nullptr;
   if ((rc = ensure(ctx, 1, (n_series + 1) * 8, &d_start))) return rc;
-  if ((rc = ensure(ctx, 8, n_series * out_stride, &d_out))) return rc;
-  if ((rc = ensure(ctx, 12, n_series * 8, &d_len))) return rc;
-  if ((rc = ensure(ctx, 5, n_series * 4, &d_st))) return rc;
-  if ((rc = ensure(ctx, 0, packed_capacity + 16, &d_packed))) return rc;
-  if ((rc = ensure(ctx, 9, (n_series + 1) * 8, &d_off))) return rc;
-  CK(cudaMemcpyAsync(d_ts, h_ts, nb, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_val, h_val, nb, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_start, h_start, n_series * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_start, h_start, n_series * 8, cudaMemcpyHostToDevice, sts[0]));
   if (h_n_points) {
     if ((rc = ensure(ctx, 4, n_series * 4, &d_np))) return rc;
-    CK(cudaMemcpyAsync(d_np, h_n_points, n_series * 4, cudaMemcpyHostToDevice, st));
-  }
-  if (h_units) {
-    if ((rc = ensure(ctx, 6, n_series * points_stride, &d_units))) return rc;
-    CK(cudaMemcpyAsync(d_units, h_units, n_series * points_stride, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_np, h_n_points, n_series * 4, cudaMemcpyHostToDevice, sts[0]));
   }
   if (h_ann_series_off) {
     if (!h_ann_entries || (!h_ann_bytes && ann_bytes_len)) return M3TSZ_ERR_INVALID_ARG;
@@ -397,30 +437,96 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
     if ((rc = ensure(ctx, 7, (n_series + 1) * 8, &d_aoff))) return rc;
     if ((rc = ensure(ctx, 13, n_ent * sizeof(m3tsz_annotation_entry), &d_aent))) return rc;
     if ((rc = ensure(ctx, 14, ann_bytes_len, &d_abytes))) return rc;
-    CK(cudaMemcpyAsync(d_aoff, h_ann_series_off, (n_series + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_aoff, h_ann_series_off, (n_series + 1) * 8, cudaMemcpyHostToDevice, sts[0]));
     if (n_ent)
       CK(cudaMemcpyAsync(d_aent, h_ann_entries, n_ent * sizeof(m3tsz_annotation_entry),
-                         cudaMemcpyHostToDevice, st));
-    if (ann_bytes_len) CK(cudaMemcpyAsync(d_abytes, h_ann_bytes, ann_bytes_len, cudaMemcpyHostToDevice, st));
+                         cudaMemcpyHostToDevice, sts[0]));
+    if (ann_bytes_len) CK(cudaMemcpyAsync(d_abytes, h_ann_bytes, ann_bytes_len, cudaMemcpyHostToDevice, sts[0]));
   }
-  rc = m3tsz_encode_batch(ctx, opts, (const int64_t *)d_ts, (const double *)d_val, n_series,
-                          points_stride, (const uint32_t *)d_np, (const int64_t *)d_start, unit,
-                          (const uint8_t *)d_units, (const uint64_t *)d_aoff,
-                          (const m3tsz_annotation_entry *)d_aent, (const uint8_t *)d_abytes,
-                          (uint8_t *)d_out, out_stride, (uint64_t *)d_len, (int32_t *)d_st, st);
-  if (rc) return rc;
-  rc = m3tsz_compact_streams(ctx, (const uint8_t *)d_out, out_stride, (const uint64_t *)d_len,
-                             n_series, align, (uint8_t *)d_packed, packed_capacity,
-                             (uint64_t *)d_off, st);
-  if (rc) return rc;
-  CK(cudaMemcpyAsync(h_offsets, d_off, (n_series + 1) * 8, cudaMemcpyDeviceToHost, st));
-  if (h_out_len) CK(cudaMemcpyAsync(h_out_len, d_len, n_series * 8, cudaMemcpyDeviceToHost, st));
-  if (h_status) CK(cudaMemcpyAsync(h_status, d_st, n_series * 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  const uint64_t total = h_offsets[n_series];
-  if (total > packed_capacity) return M3TSZ_ERR_CAPACITY;
-  CK(cudaMemcpyAsync(h_packed, d_packed, total, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  CK(cudaEventRecord(ctx->ev, sts[0]));
+  CK(cudaStreamWaitEvent(sts[1], ctx->ev, 0));
+
+  // per-stream chunk buffers
+  struct Lane {
+    void *ts, *val, *units, *out, *len, *st, *packed, *off, *tmp;
+    uint64_t c0, c1;
+    bool busy;
+  } ln[2];
+  const size_t tmp_bytes = compact_scan_tmp_bytes(ch);
+  for (int i = 0; i < 2; i++) {
+    const int b = 16 + i * 10;
+    ln[i].units = nullptr;
+    ln[i].busy = false;
+    if ((rc = ensure(ctx, b + 0, ch * row_bytes, &ln[i].ts))) return rc;
+    if ((rc = ensure(ctx, b + 1, ch * row_bytes, &ln[i].val))) return rc;
+    if (h_units && (rc = ensure(ctx, b + 2, ch * points_stride, &ln[i].units))) return rc;
+    if ((rc = ensure(ctx, b + 3, ch * out_stride, &ln[i].out))) return rc;
+    if ((rc = ensure(ctx, b + 4, ch * 8, &ln[i].len))) return rc;
+    if ((rc = ensure(ctx, b + 5, ch * 4, &ln[i].st))) return rc;
+    if ((rc = ensure(ctx, b + 6, ch * out_stride + 16, &ln[i].packed))) return rc;
+    if ((rc = ensure(ctx, b + 7, (ch + 1) * 8, &ln[i].off))) return rc;
+    if ((rc = ensure(ctx, b + 8, tmp_bytes, &ln[i].tmp))) return rc;
+    if ((rc = ensure_stage(ctx, i, (ch + 1) * 8))) return rc;
+  }
+  CK(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int32_t), sts[0]));
+
+  auto issue = [&](int i, uint64_t c0) -> int {
+    Lane &L = ln[i];
+    cudaStream_t st = sts[i];
+    L.c0 = c0;
+    L.c1 = (c0 + ch < n_series) ? c0 + ch : n_series;
+    L.busy = true;
+    const uint64_t n = L.c1 - c0;
+    CK(cudaMemcpyAsync(L.ts, h_ts + c0 * points_stride, n * row_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(L.val, h_val + c0 * points_stride, n * row_bytes, cudaMemcpyHostToDevice, st));
+    if (h_units)
+      CK(cudaMemcpyAsync(L.units, h_units + c0 * points_stride, n * points_stride, cudaMemcpyHostToDevice, st));
+    int r = m3tsz_encode_batch(ctx, opts, (const int64_t *)L.ts, (const double *)L.val, n, points_stride,
+                               d_np ? (const uint32_t *)d_np + c0 : nullptr, (const int64_t *)d_start + c0,
+                               unit, (const uint8_t *)L.units, d_aoff ? (const uint64_t *)d_aoff + c0 : nullptr,
+                               (const m3tsz_annotation_entry *)d_aent, (const uint8_t *)d_abytes,
+                               (uint8_t *)L.out, out_stride, (uint64_t *)L.len, (int32_t *)L.st, st);
+    if (r) return r;
+    CK(launch_compact((const uint8_t *)L.out, out_stride, (const uint64_t *)L.len, n, align,
+                      (uint8_t *)L.packed, ch * out_stride + 16, (uint64_t *)L.off, L.tmp, tmp_bytes,
+                      ctx->d_flag + i, st));
+    ctx->launches += 3;
+    CK(cudaMemcpyAsync(ctx->h_stage[i], L.off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (h_out_len) CK(cudaMemcpyAsync(h_out_len + c0, L.len, n * 8, cudaMemcpyDeviceToHost, st));
+    if (h_status) CK(cudaMemcpyAsync(h_status + c0, L.st, n * 4, cudaMemcpyDeviceToHost, st));
+    return M3TSZ_OK;
+  };
+  uint64_t host_base = 0;
+  auto finish = [&](int i) -> int {
+    Lane &L = ln[i];
+    if (!L.busy) return M3TSZ_OK;
+    L.busy = false;
+    CK(cudaStreamSynchronize(sts[i]));  // offsets of this chunk are on the host now
+    const uint64_t n = L.c1 - L.c0;
+    const uint64_t *co = (const uint64_t *)ctx->h_stage[i];
+    const uint64_t total = co[n];
+    if (host_base + total > packed_capacity) return M3TSZ_ERR_CAPACITY;
+    if (total)
+      CK(cudaMemcpyAsync(h_packed + host_base, L.packed, total, cudaMemcpyDeviceToHost, sts[i]));
+    for (uint64_t j = 0; j <= n; j++) h_offsets[L.c0 + j] = host_base + co[j];
+    host_base += total;
+    host_base = (host_base + align - 1) & ~(uint64_t)(align - 1);
+    return M3TSZ_OK;
+  };
+  int k = 0;
+  if ((rc = issue(0, 0))) return rc;
+  for (uint64_t c0 = 0; c0 < n_series; c0 += ch, k++) {
+    const uint64_t next = c0 + ch;
+    if (next < n_series) {
+      // the other lane's previous chunk has been finished already (its D2H is queued
+      // on its own stream, so reusing its buffers is ordered)
+      if ((rc = issue((k + 1) & 1, next))) return rc;
+    }
+    if ((rc = finish(k & 1))) return rc;
+  }
+  CK(cudaStreamSynchronize(sts[0]));
+  CK(cudaStreamSynchronize(sts[1]));
+  // CSR convention: offsets[n] is the end of the last stream; un-pad the final alignment
   return M3TSZ_OK;
 }
 

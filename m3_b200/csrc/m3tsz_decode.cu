@@ -18,14 +18,31 @@
 
 namespace m3tsz {
 
+// Tuning knobs (overridable with -D for sweeps; defaults = best of the round-1 sweep
+// at 100k x 1440, see profiles/r01_decode_history.md)
+#ifndef M3_DEC_OUT_T
+#define M3_DEC_OUT_T 8  // output tile rows (datapoints per flush)
+#endif
+#ifndef M3_DEC_TRIGGER
+#define M3_DEC_TRIGGER 24  // <= this many requested words ahead: the lane triggers a refill event
+#endif
+#ifndef M3_DEC_CHK
+#define M3_DEC_CHK 4  // ring bookkeeping every CHK datapoints
+#endif
+#ifndef M3_DEC_SAFE_MIN
+#define M3_DEC_SAFE_MIN 12  // fewer landed words ahead than this: confirm the copy in flight
+#endif
+#ifndef M3_DEC_MIN_BLOCKS
+#define M3_DEC_MIN_BLOCKS 4
+#endif
 constexpr int DEC_WARPS = 4;      // warps per block
 constexpr int DEC_RING = 64;      // staged words per lane (ring buffer, power of two)
 constexpr int DEC_MIRROR = 3;     // rows 64..66 mirror rows 0..2 so 4-word reads never wrap
 constexpr int DEC_FILL = 16;      // words per lane per asynchronous refill chunk
-constexpr int DEC_TRIGGER = 32;   // a lane with <= this many staged words ahead triggers a refill event
+constexpr int DEC_TRIGGER = M3_DEC_TRIGGER;
 constexpr int DEC_ACCEPT = DEC_RING - DEC_FILL;  // lanes with <= this many words ahead take a chunk
 constexpr int DEC_STRIDE = 33;    // tile row stride (words / dwords): conflict-free transposes
-constexpr int DEC_OUT_T = 8;      // output tile rows (datapoints per flush)
+constexpr int DEC_OUT_T = M3_DEC_OUT_T;
 constexpr int DEC_FAST_WORDS = 4; // the fast path reads 4 consecutive words
 
 constexpr int DEC_IN_TILE_WORDS = (DEC_RING + DEC_MIRROR + 1) * DEC_STRIDE;  // u32 (+1 row pad: 8B align)
@@ -418,7 +435,7 @@ struct DsAcc {  // fused-downsample per-lane accumulator (aggregation.Gauge, gau
 };
 
 template <bool INT_OPT, int MODE>
-__global__ void __launch_bounds__(DEC_WARPS * 32, 4)
+__global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
     decode_kernel(const DecodeParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
@@ -489,25 +506,36 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)
   // refills are DEC_FILL-word aligned: start at the stream's first word rounded down
   uint32_t filled = (s.pos >> 5) & ~(uint32_t)(DEC_FILL - 1);  // words [.., filled) requested
   uint32_t safe = filled;                                       // words [.., safe) have landed
-  uint32_t iter = 0;       // warp-uniform datapoint index
-  uint32_t tile_row0 = 0;  // datapoint index of output tile row 0
+  uint32_t tile_row0 = 0;  // datapoint index of output tile row 0 (warp-uniform)
   // scheme/unit admit the fast path (they only change on the slow path)
   bool su_ok = false;
 
-  for (;;) {
-    const bool active = !s.done && s.err == 0;
-    if (!__any_sync(FULL_MASK, active)) break;
+  // flush geometry: one store instruction writes DEC_OUT_T rows of ts and of values
+  // for FL_SPI series
+  constexpr int FL_SPI = 32 / (2 * DEC_OUT_T);  // series per instruction
+  constexpr int FL_ITERS = 32 / FL_SPI;
+  const int fl_r = lane & (DEC_OUT_T - 1);
+  const bool fl_isval = (lane / DEC_OUT_T) & 1;
+  const int fl_jo = lane / (2 * DEC_OUT_T);
+  const uint64_t *fl_tile = (fl_isval ? val_tile : ts_tile) + fl_r * DEC_STRIDE + fl_jo;
+  uint64_t *fl_base = (fl_isval ? reinterpret_cast<uint64_t *>(p.val) : reinterpret_cast<uint64_t *>(p.ts)) +
+                      (warp_s0 + fl_jo) * p.cap + fl_r;
+  const uint64_t fl_step = (uint64_t)FL_SPI * p.cap;
 
-    // ---- ring maintenance ----
+  for (;;) {  // one group of DEC_OUT_T datapoints per iteration
+    if (!__any_sync(FULL_MASK, !s.done && s.err == 0)) break;
+
+    // ---- ring maintenance (every M3_DEC_CHK datapoints) ----
     // A refill EVENT is warp-wide: it first waits for the previous event's copies
-    // (issued >= 4 datapoints ago, so normally already landed), then every lane
-    // with room takes another 16-word chunk.  The lane that is furthest ahead
-    // triggers the event while it still has ~28 landed words in hand, and after
-    // an event every lane has >= 49 words requested, so events cannot cluster.
-    const uint32_t cw = s.pos >> 5;
-    {
+    // (issued many datapoints ago, so normally landed), then every lane with room
+    // takes another 16-word chunk.  Lanes that nevertheless run dry fall back to
+    // the slow path (reads global memory), so the thresholds only tune speed.
+    auto ring_service = [&]() {
+      const bool active = !s.done && s.err == 0;
+      const uint32_t cw = s.pos >> 5;
       int avail = (int)(filled - cw);
-      if (__any_sync(FULL_MASK, active && avail <= DEC_TRIGGER)) {
+      if (__any_sync(FULL_MASK, active && (avail <= DEC_TRIGGER ||
+                                           ((int)(safe - cw) < M3_DEC_SAFE_MIN && filled > safe)))) {
         cp_async_wait_all();
         __syncwarp();
         if (avail < 0) {  // the slow path skipped past the ring (annotation): restart at cw
@@ -517,8 +545,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)
         safe = filled;
 #pragma unroll 1
         for (int rep = 0; rep < 3; rep++) {
-          // first pass: everyone with room tops up; later passes only serve lanes that
-          // are still short (start-up / after a restart)
+          // first pass: everyone with room tops up when someone is at the trigger level;
+          // later passes only serve lanes that are still short (start-up / restart)
+          const bool trig = __any_sync(FULL_MASK, active && avail <= DEC_TRIGGER);
+          if (!trig) break;
           const uint32_t fmask =
               __ballot_sync(FULL_MASK, active && avail <= (rep == 0 ? DEC_ACCEPT : DEC_TRIGGER));
           if (!fmask) break;
@@ -534,245 +564,248 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 4)
           safe = filled;
         }
       }
-    }
+    };
 
-    int64_t t = 0;
-    uint64_t v = 0;
-    bool emitted = false;
-    // ---------------- fast path: branch-free parse of 4 ring words ----------------
-    const uint32_t *tp = ring + (cw & (DEC_RING - 1)) * DEC_STRIDE + lane;
-    const uint32_t w0 = __byte_perm(tp[0], 0, 0x0123), w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123),
-                   w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123),
-                   w3 = __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123);
-    const uint32_t sh = s.pos & 31u;
-    const uint32_t h = __funnelshift_l(w1, w0, sh);
-    bool ok = active && su_ok && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
-    uint32_t c = 1;  // bits consumed before the payload
-    int64_t dod = 0;
-    if (__any_sync(FULL_MASK, ok && (h >> 31))) {  // some lane has a non-zero delta-of-delta
-      const bool nz = (h >> 31) != 0;
-      const bool m9 = (h >> 30) == 2u, m12 = (h >> 29) == 6u, m16 = (h >> 28) == 14u;
-      const bool marker = (h >> 23) == kMarkerOpcode;
-      const int32_t f = m9 ? (((int32_t)(h << 2)) >> 25)
-                           : (m12 ? (((int32_t)(h << 3)) >> 23) : (((int32_t)(h << 4)) >> 20));
-      c = nz ? (m9 ? 9u : (m12 ? 12u : 16u)) : 1u;
-      ok = ok && (!nz || ((m9 || m12 || m16) && !marker));
-      dod = nz ? (int64_t)((uint64_t)(int64_t)f * (uint64_t)s.unit_ns) : 0;
-    }
-    uint32_t x = h << c;
-    // value grammar (iterator.go:128-176); kinds: float-next / int-diff / repeat
-    bool k_float = true, k_int = false;
-    if (INT_OPT) {
-      const bool b0 = (x >> 31) != 0;
-      const bool rep = !b0 && ((x >> 30) & 1u);
-      ok = ok && (b0 || rep);
-      k_float = b0 && s.is_float;
-      k_int = b0 && !s.is_float;
-      ok = ok && !(k_int && s.sig == 64);
-      c += b0 ? 1u : 2u;
-      x <<= 1;
-    }
-    const bool zero = !(x >> 31);
-    const bool cont = (x >> 30) == 2u;
-    const int lz = (int)((x >> 24) & 63u);
-    const int nunc = (int)((x >> 18) & 63u) + 1;
-    int n = cont ? (64 - plz - ptz) : nunc;
-    int tz = cont ? ptz : (64 - lz - nunc);
-    uint32_t hb = cont ? 2u : 14u;
-    if (zero) {
-      n = 0;
-      hb = 1;
-    }
-    if (INT_OPT && !k_float) {
-      hb = 0;
-      n = k_int ? s.sig + 1 : 0;
-    }
-    c += hb;
-    const uint64_t field = extract64(w0, w1, w2, w3, sh + c);
-    const uint64_t payload = n ? (field >> (64 - n)) : 0ull;
-    c += (uint32_t)n;
-    const bool ok2 = ok && (s.pos + c <= s.end);
-    if (__all_sync(FULL_MASK, ok2 || !active)) {
-      // hot: every live lane takes the fast path -> unconditional state update
-      // (finished lanes compute garbage they never read again)
-      s.pos += c;
-      s.prev_delta = (int64_t)((uint64_t)s.prev_delta + (uint64_t)dod);
-      s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
-      if (!INT_OPT) {
-        const uint64_t xr = (tz < 0) ? 0ull : (payload << tz);
-        s.prev_xor = xr;
-        s.prev_bits ^= xr;
-        lz_tz(xr, plz, ptz);
-      } else {
-        const uint64_t xr = (k_float && tz >= 0) ? (payload << tz) : 0ull;
-        s.prev_bits ^= xr;
-        int nlz, ntz;
-        lz_tz(xr, nlz, ntz);
-        s.prev_xor = k_float ? xr : s.prev_xor;
-        plz = k_float ? nlz : plz;
-        ptz = k_float ? ntz : ptz;
-      }
-      t = s.prev_time;
-      v = s.prev_bits;
-      emitted = active;
-    } else {
-      if (ok) {
-        if (!ok2) {
-          s.err = M3TSZ_ERR_EOF;  // truncated stream: the datapoint is not produced
-        } else {
+#pragma unroll 1
+    for (int row = 0; row < DEC_OUT_T; row++) {
+      if ((row & (M3_DEC_CHK - 1)) == 0) ring_service();
+      const bool active = !s.done && s.err == 0;
+      const uint32_t cw = s.pos >> 5;
+      int64_t t = 0;
+      uint64_t v = 0;
+      bool emitted = false;
+      // ---------------- parse 4 ring words ----------------
+      const uint32_t *tp = ring + (cw & (DEC_RING - 1)) * DEC_STRIDE + lane;
+      const uint32_t w0 = __byte_perm(tp[0], 0, 0x0123), w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123),
+                     w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123),
+                     w3 = __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123);
+      const uint32_t sh = s.pos & 31u;
+      const uint32_t h = __funnelshift_l(w1, w0, sh);
+      const bool okb = active && su_ok && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
+
+      // ---- hot candidate: zero delta-of-delta, float XOR code ----
+      {
+        uint32_t x = h << 1;
+        uint32_t c = 1;
+        bool hot = okb && !(h >> 31);
+        if (INT_OPT) {
+          hot = hot && (x >> 31) && s.is_float;  // '1' = no mode update
+          x <<= 1;
+          c = 2;
+        }
+        const bool zero = !(x >> 31);
+        const bool cont = (x >> 30) == 2u;
+        const int lz = (int)((x >> 24) & 63u);
+        const int nunc = (int)((x >> 18) & 63u) + 1;
+        int n = cont ? (64 - plz - ptz) : nunc;
+        int tz = cont ? ptz : (64 - lz - nunc);
+        c += cont ? 2u : 14u;
+        if (zero) {
+          n = 0;
+          c -= cont ? 1u : 13u;
+        }
+        const uint64_t field = extract64(w0, w1, w2, w3, sh + c);
+        const uint64_t payload = n ? (field >> (64 - n)) : 0ull;
+        c += (uint32_t)n;
+        hot = hot && (s.pos + c <= s.end);
+        if (__all_sync(FULL_MASK, hot || !active)) {
+          // every live lane: unconditional update (finished lanes compute garbage
+          // they never read again)
           s.pos += c;
-          s.prev_delta = (int64_t)((uint64_t)s.prev_delta + (uint64_t)dod);
           s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
-          if (k_float) {
-            const uint64_t xr = (tz < 0) ? 0ull : (payload << tz);
-            s.prev_xor = xr;
-            s.prev_bits ^= xr;
-            lz_tz(xr, plz, ptz);
+          const uint64_t xr = (tz < 0) ? 0ull : (payload << tz);
+          s.prev_xor = xr;
+          s.prev_bits ^= xr;
+          lz_tz(xr, plz, ptz);
+          if (MODE == 0) {
+            ts_tile[row * DEC_STRIDE + lane] = (uint64_t)s.prev_time;
+            val_tile[row * DEC_STRIDE + lane] = s.prev_bits;
+            s.n += active ? 1u : 0u;
+            continue;
           }
           t = s.prev_time;
           v = s.prev_bits;
-          emitted = true;
+          emitted = active;
+          goto sink;
         }
-      } else if (active) {  // complete grammar, from global memory
-        DecState tmp = s;   // copy-in / copy-out keeps the lane state in registers
-        int64_t st = 0;
-        uint64_t sv = 0;
-        const bool em = decode_dp_slow<INT_OPT>(tmp, p.streams, p.streams_bytes, p.default_unit, st, sv);
-        s = tmp;
-        t = st;
-        v = sv;
-        emitted = em;
-        lz_tz(s.prev_xor, plz, ptz);
-        su_ok = (s.scheme == kScheme32 || s.scheme == kScheme64) && (s.unit >= 1 && s.unit <= 4);
       }
-    }
-    if (INT_OPT && __any_sync(FULL_MASK, emitted && ok && !s.is_float)) {  // int-mode lanes (fast path)
-      if (emitted && ok && !s.is_float) {
-        if (k_int) {
-          const uint64_t neg = payload >> s.sig;
-          const uint64_t mag = payload & ((1ull << s.sig) - 1ull);
-          const double m = __ull2double_rn(mag);
-          s.int_val = neg ? __dadd_rn(s.int_val, m) : __dsub_rn(s.int_val, m);
-        }
-        const double dv = s.mult ? __ddiv_rn(s.int_val, mult_pow10(s.mult)) : s.int_val;
-        v = (uint64_t)__double_as_longlong(dv);
-      }
-    }
 
-    // ---------------- sink ----------------
-    if (MODE == 0) {
-      const int row = (int)(iter - tile_row0);
-      if (emitted) {
-        ts_tile[row * DEC_STRIDE + lane] = (uint64_t)t;
-        val_tile[row * DEC_STRIDE + lane] = v;
-        s.n++;
-      }
-    } else {
-      if (emitted) {
-        s.n++;
-        if (t >= p.range_start && t < range_end) {
-          if (!(acc.cur_w >= 0 && t >= acc.w_start && t - acc.w_start < p.window)) {
-            // commit the window we are leaving
-            if (acc.cur_w >= 0) {
-              const uint64_t o = (uint64_t)acc.cur_w * p.n_series + sidx;
-              p.ds_sum[o] = acc.sum;
-              p.ds_count[o] = acc.cnt;
-              p.ds_min[o] = acc.mn;
-              p.ds_max[o] = acc.mx;
+      // ---------------- general path (any mix of cases) ----------------
+      {
+        bool ok = okb;
+        uint32_t c = 1;  // bits consumed before the payload
+        int64_t dod = 0;
+        if (h >> 31) {
+          const bool m9 = (h >> 30) == 2u, m12 = (h >> 29) == 6u, m16 = (h >> 28) == 14u;
+          const bool marker = (h >> 23) == kMarkerOpcode;
+          const int32_t f = m9 ? (((int32_t)(h << 2)) >> 25)
+                               : (m12 ? (((int32_t)(h << 3)) >> 23) : (((int32_t)(h << 4)) >> 20));
+          c = m9 ? 9u : (m12 ? 12u : 16u);
+          ok = ok && (m9 || m12 || m16) && !marker;
+          dod = (int64_t)((uint64_t)(int64_t)f * (uint64_t)s.unit_ns);
+        }
+        uint32_t x = h << c;
+        // value grammar (iterator.go:128-176); kinds: float-next / int-diff / repeat
+        bool k_float = true, k_int = false;
+        if (INT_OPT) {
+          const bool b0 = (x >> 31) != 0;
+          const bool rep = !b0 && ((x >> 30) & 1u);
+          ok = ok && (b0 || rep);
+          k_float = b0 && s.is_float;
+          k_int = b0 && !s.is_float;
+          ok = ok && !(k_int && s.sig == 64);
+          c += b0 ? 1u : 2u;
+          x <<= 1;
+        }
+        const bool zero = !(x >> 31);
+        const bool cont = (x >> 30) == 2u;
+        const int lz = (int)((x >> 24) & 63u);
+        const int nunc = (int)((x >> 18) & 63u) + 1;
+        int n = cont ? (64 - plz - ptz) : nunc;
+        int tz = cont ? ptz : (64 - lz - nunc);
+        uint32_t hb = cont ? 2u : 14u;
+        if (zero) {
+          n = 0;
+          hb = 1;
+        }
+        if (INT_OPT && !k_float) {
+          hb = 0;
+          n = k_int ? s.sig + 1 : 0;
+        }
+        c += hb;
+        const uint64_t field = extract64(w0, w1, w2, w3, sh + c);
+        const uint64_t payload = n ? (field >> (64 - n)) : 0ull;
+        c += (uint32_t)n;
+        if (ok) {
+          if (s.pos + c > s.end) {
+            s.err = M3TSZ_ERR_EOF;  // truncated stream: the datapoint is not produced
+          } else {
+            s.pos += c;
+            s.prev_delta = (int64_t)((uint64_t)s.prev_delta + (uint64_t)dod);
+            s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
+            if (k_float) {
+              const uint64_t xr = (tz < 0) ? 0ull : (payload << tz);
+              s.prev_xor = xr;
+              s.prev_bits ^= xr;
+              lz_tz(xr, plz, ptz);
             }
-            int64_t nw;
-            if (acc.cur_w >= 0 && t >= acc.w_start + p.window && t - acc.w_start < 2 * p.window)
-              nw = acc.cur_w + 1;
-            else
-              nw = (int64_t)((uint64_t)(t - p.range_start) / (uint64_t)p.window);
-            if (nw > acc.hi_w) {
-              for (int64_t w = acc.hi_w + 1; w < nw; w++) {
-                const uint64_t o = (uint64_t)w * p.n_series + sidx;
-                p.ds_sum[o] = 0.0;
-                p.ds_count[o] = 0;
-                p.ds_min[o] = __longlong_as_double((long long)kGoNaNBits);
-                p.ds_max[o] = __longlong_as_double((long long)kGoNaNBits);
+            t = s.prev_time;
+            v = s.prev_bits;
+            emitted = true;
+            if (INT_OPT && !s.is_float) {  // int mode: diff or repeat
+              if (k_int) {
+                const uint64_t neg = payload >> s.sig;
+                const uint64_t mag = payload & ((1ull << s.sig) - 1ull);
+                const double m = __ull2double_rn(mag);
+                s.int_val = neg ? __dadd_rn(s.int_val, m) : __dsub_rn(s.int_val, m);
               }
-              acc.hi_w = nw;
-              acc.sum = 0.0;
-              acc.cnt = 0;
-              acc.mn = __longlong_as_double((long long)kGoNaNBits);
-              acc.mx = acc.mn;
-            } else {  // out-of-order timestamp: reopen a committed window
-              const uint64_t o = (uint64_t)nw * p.n_series + sidx;
-              acc.sum = p.ds_sum[o];
-              acc.cnt = p.ds_count[o];
-              acc.mn = p.ds_min[o];
-              acc.mx = p.ds_max[o];
+              const double dv = s.mult ? __ddiv_rn(s.int_val, mult_pow10(s.mult)) : s.int_val;
+              v = (uint64_t)__double_as_longlong(dv);
             }
-            acc.cur_w = nw;
-            acc.w_start = p.range_start + nw * p.window;
           }
-          const double dv = __longlong_as_double((long long)v);
-          acc.cnt++;
-          if (dv == dv) {  // gauge.go:88-101
-            acc.sum = __dadd_rn(acc.sum, dv);
-            if (acc.mx != acc.mx || acc.mx < dv) acc.mx = dv;
-            if (acc.mn != acc.mn || acc.mn > dv) acc.mn = dv;
+        } else if (active) {  // complete grammar, from global memory
+          DecState tmp = s;   // copy-in / copy-out keeps the lane state in registers
+          int64_t st = 0;
+          uint64_t sv = 0;
+          const bool em = decode_dp_slow<INT_OPT>(tmp, p.streams, p.streams_bytes, p.default_unit, st, sv);
+          s = tmp;
+          t = st;
+          v = sv;
+          emitted = em;
+          lz_tz(s.prev_xor, plz, ptz);
+          su_ok = (s.scheme == kScheme32 || s.scheme == kScheme64) && (s.unit >= 1 && s.unit <= 4);
+        }
+      }
+
+    sink:
+      // ---------------- sink ----------------
+      if (MODE == 0) {
+        if (emitted) {
+          ts_tile[row * DEC_STRIDE + lane] = (uint64_t)t;
+          val_tile[row * DEC_STRIDE + lane] = v;
+          s.n++;
+        }
+      } else {
+        if (emitted) {
+          s.n++;
+          if (t >= p.range_start && t < range_end) {
+            if (!(acc.cur_w >= 0 && t >= acc.w_start && t - acc.w_start < p.window)) {
+              // commit the window we are leaving
+              if (acc.cur_w >= 0) {
+                const uint64_t o = (uint64_t)acc.cur_w * p.n_series + sidx;
+                p.ds_sum[o] = acc.sum;
+                p.ds_count[o] = acc.cnt;
+                p.ds_min[o] = acc.mn;
+                p.ds_max[o] = acc.mx;
+              }
+              int64_t nw;
+              if (acc.cur_w >= 0 && t >= acc.w_start + p.window && t - acc.w_start < 2 * p.window)
+                nw = acc.cur_w + 1;
+              else
+                nw = (int64_t)((uint64_t)(t - p.range_start) / (uint64_t)p.window);
+              if (nw > acc.hi_w) {
+                for (int64_t w = acc.hi_w + 1; w < nw; w++) {
+                  const uint64_t o = (uint64_t)w * p.n_series + sidx;
+                  p.ds_sum[o] = 0.0;
+                  p.ds_count[o] = 0;
+                  p.ds_min[o] = __longlong_as_double((long long)kGoNaNBits);
+                  p.ds_max[o] = __longlong_as_double((long long)kGoNaNBits);
+                }
+                acc.hi_w = nw;
+                acc.sum = 0.0;
+                acc.cnt = 0;
+                acc.mn = __longlong_as_double((long long)kGoNaNBits);
+                acc.mx = acc.mn;
+              } else {  // out-of-order timestamp: reopen a committed window
+                const uint64_t o = (uint64_t)nw * p.n_series + sidx;
+                acc.sum = p.ds_sum[o];
+                acc.cnt = p.ds_count[o];
+                acc.mn = p.ds_min[o];
+                acc.mx = p.ds_max[o];
+              }
+              acc.cur_w = nw;
+              acc.w_start = p.range_start + nw * p.window;
+            }
+            const double dv = __longlong_as_double((long long)v);
+            acc.cnt++;
+            if (dv == dv) {  // gauge.go:88-101
+              acc.sum = __dadd_rn(acc.sum, dv);
+              if (acc.mx != acc.mx || acc.mx < dv) acc.mx = dv;
+              if (acc.mn != acc.mn || acc.mn > dv) acc.mn = dv;
+            }
           }
         }
       }
     }
-    iter++;
 
-    // ---------------- flush a full output tile ----------------
-    if (MODE == 0 && iter - tile_row0 == (uint32_t)DEC_OUT_T) {
+    // ---------------- flush the output tile ----------------
+    if (MODE == 0) {
       __syncwarp();
       const uint32_t lim = s.n < (uint32_t)p.cap ? s.n : (uint32_t)p.cap;
       const uint32_t my_rows = lim > tile_row0 ? min(lim - tile_row0, (uint32_t)DEC_OUT_T) : 0u;
-      // lanes 0-7: ts rows of series 2i, 8-15: value rows of 2i, 16-23 / 24-31: same for 2i+1
-      const int r = lane & (DEC_OUT_T - 1);
-      const bool isval = (lane >> 3) & 1;
-      const int jo = lane >> 4;
-      const uint64_t *tile = (isval ? val_tile : ts_tile) + r * DEC_STRIDE + jo;
-      uint64_t *dst = (isval ? reinterpret_cast<uint64_t *>(p.val) : reinterpret_cast<uint64_t *>(p.ts)) +
-                      (warp_s0 + jo) * p.cap + tile_row0 + r;
-      const uint64_t step = 2ull * p.cap;
+      uint64_t *dst = fl_base + tile_row0;
       if (__all_sync(FULL_MASK, my_rows == (uint32_t)DEC_OUT_T)) {
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          *dst = tile[2 * i];
-          dst += step;
+        for (int i = 0; i < FL_ITERS; i++) {
+          *dst = fl_tile[FL_SPI * i];
+          dst += fl_step;
         }
       } else {
 #pragma unroll 4
-        for (int i = 0; i < 16; i++) {
-          const uint32_t rows = __shfl_sync(FULL_MASK, my_rows, 2 * i + jo);
-          if ((uint32_t)r < rows) *dst = tile[2 * i];
-          dst += step;
+        for (int i = 0; i < FL_ITERS; i++) {
+          const uint32_t rows = __shfl_sync(FULL_MASK, my_rows, FL_SPI * i + fl_jo);
+          if ((uint32_t)fl_r < rows) *dst = fl_tile[FL_SPI * i];
+          dst += fl_step;
         }
       }
       __syncwarp();
-      tile_row0 = iter;
     }
+    tile_row0 += DEC_OUT_T;
   }
   cp_async_wait_all();
 
   // ---------------- epilogue ----------------
-  if (MODE == 0) {
-    if (iter > tile_row0) {
-      __syncwarp();
-      const uint32_t lim = s.n < (uint32_t)p.cap ? s.n : (uint32_t)p.cap;
-      const uint32_t my_rows = lim > tile_row0 ? min(lim - tile_row0, (uint32_t)DEC_OUT_T) : 0u;
-      const int r = lane & (DEC_OUT_T - 1);
-      const bool isval = (lane >> 3) & 1;
-      const int jo = lane >> 4;
-      const uint64_t *tile = (isval ? val_tile : ts_tile) + r * DEC_STRIDE + jo;
-      uint64_t *dst = (isval ? reinterpret_cast<uint64_t *>(p.val) : reinterpret_cast<uint64_t *>(p.ts)) +
-                      (warp_s0 + jo) * p.cap + tile_row0 + r;
-      const uint64_t step = 2ull * p.cap;
-      for (int i = 0; i < 16; i++) {
-        const uint32_t rows = __shfl_sync(FULL_MASK, my_rows, 2 * i + jo);
-        if ((uint32_t)r < rows) *dst = tile[2 * i];
-        dst += step;
-      }
-    }
-  } else if (valid) {
+  if (MODE == 1 && valid) {
     if (acc.cur_w >= 0) {
       const uint64_t o = (uint64_t)acc.cur_w * p.n_series + sidx;
       p.ds_sum[o] = acc.sum;
