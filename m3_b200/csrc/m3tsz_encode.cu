@@ -33,7 +33,8 @@ constexpr size_t ENC_WARP_SMEM = 4 * (size_t)ENC_IN_TILE_DWORDS * 8 + (size_t)EN
 struct EncLane {
   uint32_t carry, sh, k, words_out;
   int64_t prev_time, prev_delta;
-  uint64_t prev_bits, prev_xor;
+  uint64_t prev_bits;
+  int plz, ptz;  // leading / trailing zeros of the previous XOR ((64, 0) for a zero XOR)
   double int_val;
   int unit;
   int num_sig, hi_lower_sig, n_lower_sig, max_mult;
@@ -219,29 +220,26 @@ __device__ __forceinline__ void sig_mult_hdr(EncLane &s, int sig, int mult, bool
 __device__ __forceinline__ void xor_code(EncLane &s, uint64_t fb, uint32_t &hdr, int &hb,
                                          uint64_t &payload, int &plen) {
   const uint64_t x = s.prev_bits ^ fb;
+  int cl, ct;
+  lz_tz(x, cl, ct);  // (64, 0) for x == 0
   if (x == 0) {
     hdr <<= 1;
     hb += 1;
     plen = 0;
+  } else if (cl >= s.plz && ct >= s.ptz) {
+    hdr = (hdr << 2) | 2u;
+    hb += 2;
+    payload = x >> s.ptz;
+    plen = 64 - s.plz - s.ptz;
   } else {
-    int pl, pt;
-    lz_tz(s.prev_xor, pl, pt);
-    const int cl = __clzll((long long)x);
-    const int ct = __ffsll((long long)x) - 1;
-    if (cl >= pl && ct >= pt) {
-      hdr = (hdr << 2) | 2u;
-      hb += 2;
-      payload = x >> pt;
-      plen = 64 - pl - pt;
-    } else {
-      const int nm = 64 - cl - ct;
-      hdr = (hdr << 14) | (3u << 12) | ((uint32_t)cl << 6) | (uint32_t)(nm - 1);
-      hb += 14;
-      payload = x >> ct;
-      plen = nm;
-    }
+    const int nm = 64 - cl - ct;
+    hdr = (hdr << 14) | (3u << 12) | ((uint32_t)cl << 6) | (uint32_t)(nm - 1);
+    hb += 14;
+    payload = x >> ct;
+    plen = nm;
   }
-  s.prev_xor = x;
+  s.plz = cl;  // PrevXOR := x
+  s.ptz = ct;
   s.prev_bits = fb;
 }
 
@@ -257,7 +255,7 @@ __device__ __forceinline__ void encode_value(EncLane &s, double v, uint32_t &hdr
   if (!INT_OPT) {
     if (first) {  // writeFullFloat
       s.prev_bits = vbits;
-      s.prev_xor = vbits;
+      lz_tz(vbits, s.plz, s.ptz);  // PrevXOR := bits
       payload = vbits;
       plen = 64;
     } else {
@@ -268,13 +266,23 @@ __device__ __forceinline__ void encode_value(EncLane &s, double v, uint32_t &hdr
   double val = v;
   int mult = 0;
   bool isf = true;
-  if (maybe_int(v)) convert_to_int_float(v, first ? 0 : s.max_mult, val, mult, isf);
+  if (maybe_int(v)) {
+    // out-parameters of the (noinline) exact classifier live on the stack: keep
+    // them out of the common path
+    double v2;
+    int m2;
+    bool f2;
+    convert_to_int_float(v, first ? 0 : s.max_mult, v2, m2, f2);
+    val = v2;
+    mult = m2;
+    isf = f2;
+  }
   if (first) {  // writeFirstValue :112-146
     if (isf) {
       hdr = (hdr << 1) | 1u;
       hb += 1;
       s.prev_bits = vbits;
-      s.prev_xor = vbits;
+      lz_tz(vbits, s.plz, s.ptz);  // PrevXOR := bits
       payload = vbits;
       plen = 64;
       s.is_float = true;
@@ -308,7 +316,7 @@ __device__ __forceinline__ void encode_value(EncLane &s, double v, uint32_t &hdr
       hdr = (hdr << 3) | 1u;  // update, no-repeat, float-mode
       hb += 3;
       s.prev_bits = fb;
-      s.prev_xor = fb;
+      lz_tz(fb, s.plz, s.ptz);  // PrevXOR := bits
       payload = fb;
       plen = 64;
       s.is_float = true;
@@ -437,7 +445,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) encode_kernel(const EncodeP
   s.prev_time = 0;
   s.prev_delta = 0;
   s.prev_bits = 0;
-  s.prev_xor = 0;
+  s.plz = 64;
+  s.ptz = 0;
   s.int_val = 0.0;
   s.unit = 0;
   s.num_sig = 0;
