@@ -630,23 +630,45 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) encode_kernel(const EncodeP
     }
 
     // ---- encode one datapoint ----
-    if (active && s.err == 0) {
-      if ((uint64_t)s.words_out + s.k + ENC_GUARD + 4 > slot_words) {
-        s.err = M3TSZ_ERR_CAPACITY;
-      } else {
-        const int row = (int)(iter & (ENC_IN_T - 1));
-        const int64_t t = (int64_t)ts_tile[row * ENC_STRIDE + lane];
-        const double v = __longlong_as_double((long long)val_tile[row * ENC_STRIDE + lane]);
-        const int u = p.units ? (int)p.units[sidx * p.points_stride + iter] : p.unit;
-        uint32_t hdr;
-        int hb;
-        encode_time(s, out_tile, lane, t, u, hdr, hb);
-        if (s.err == 0) {
-          uint64_t payload;
-          int plen;
-          encode_value<INT_OPT>(s, v, hdr, hb, payload, plen);
+    {
+      const int row = (int)(iter & (ENC_IN_T - 1));
+      const int64_t t = (int64_t)ts_tile[row * ENC_STRIDE + lane];
+      const uint64_t fb = val_tile[row * ENC_STRIDE + lane];
+      const double v = __longlong_as_double((long long)fb);
+      const bool room = (uint64_t)s.words_out + s.k + ENC_GUARD + 4 <= slot_words;
+      // hot candidate: same (valid s/ms/us/ns) unit, zero delta-of-delta, not the
+      // first datapoint, a float-mode XOR code (value is certainly not int-like)
+      const int64_t delta = (int64_t)((uint64_t)t - (uint64_t)s.prev_time);
+      bool hot = active && room && !p.units && p.unit == s.unit && (s.unit >= 1 && s.unit <= 4) &&
+                 s.n_enc > 0 && delta == s.prev_delta;
+      if (INT_OPT) hot = hot && s.is_float && fb != s.prev_bits && !maybe_int(v);
+      if (__all_sync(FULL_MASK, hot || !active)) {
+        // every live lane: '0' (zero DoD) [+ '1' no-update] + XOR code, one merge
+        s.prev_time = t;
+        uint32_t hdr = INT_OPT ? 1u : 0u;
+        int hb = INT_OPT ? 2 : 1;
+        uint64_t payload = 0;
+        int plen = 0;
+        xor_code(s, fb, hdr, hb, payload, plen);
+        if (active) {
           emit_code(s, out_tile, lane, hdr, hb, payload, plen);
           s.n_enc++;
+        }
+      } else if (active && s.err == 0) {
+        if (!room) {
+          s.err = M3TSZ_ERR_CAPACITY;
+        } else {
+          const int u = p.units ? (int)p.units[sidx * p.points_stride + iter] : p.unit;
+          uint32_t hdr;
+          int hb;
+          encode_time(s, out_tile, lane, t, u, hdr, hb);
+          if (s.err == 0) {
+            uint64_t payload;
+            int plen;
+            encode_value<INT_OPT>(s, v, hdr, hb, payload, plen);
+            emit_code(s, out_tile, lane, hdr, hb, payload, plen);
+            s.n_enc++;
+          }
         }
       }
     }
