@@ -29,6 +29,9 @@ namespace m3tsz {
 #ifndef M3_DEC_CHK
 #define M3_DEC_CHK 4  // ring bookkeeping every CHK datapoints
 #endif
+#ifndef M3_DEC_UNROLL
+#define M3_DEC_UNROLL 1  // unroll factor of the per-datapoint body between ring checks
+#endif
 #ifndef M3_DEC_SAFE_MIN
 #define M3_DEC_SAFE_MIN 12  // fewer landed words ahead than this: confirm the copy in flight
 #endif
@@ -43,6 +46,7 @@ constexpr int DEC_TRIGGER = M3_DEC_TRIGGER;
 constexpr int DEC_ACCEPT = DEC_RING - DEC_FILL;  // lanes with <= this many words ahead take a chunk
 constexpr int DEC_STRIDE = 33;    // tile row stride (words / dwords): conflict-free transposes
 constexpr int DEC_OUT_T = M3_DEC_OUT_T;
+constexpr int DEC_UNROLL = M3_DEC_UNROLL;
 constexpr int DEC_FAST_WORDS = 4; // the fast path reads 4 consecutive words
 
 constexpr int DEC_IN_TILE_WORDS = (DEC_RING + DEC_MIRROR + 1) * DEC_STRIDE;  // u32 (+1 row pad: 8B align)
@@ -509,6 +513,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
   uint32_t tile_row0 = 0;  // datapoint index of output tile row 0 (warp-uniform)
   // scheme/unit admit the fast path (they only change on the slow path)
   bool su_ok = false;
+  // maintained flags: `live` = lane still decoding; they change on the general path only
+  bool live = !s.done && s.err == 0;
 
   // flush geometry: one store instruction writes DEC_OUT_T rows of ts and of values
   // for FL_SPI series
@@ -523,7 +529,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
   const uint64_t fl_step = (uint64_t)FL_SPI * p.cap;
 
   for (;;) {  // one group of DEC_OUT_T datapoints per iteration
-    if (!__any_sync(FULL_MASK, !s.done && s.err == 0)) break;
+    if (!__any_sync(FULL_MASK, live)) break;
 
     // ---- ring maintenance (every M3_DEC_CHK datapoints) ----
     // A refill EVENT is warp-wide: it first waits for the previous event's copies
@@ -531,7 +537,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
     // takes another 16-word chunk.  Lanes that nevertheless run dry fall back to
     // the slow path (reads global memory), so the thresholds only tune speed.
     auto ring_service = [&]() {
-      const bool active = !s.done && s.err == 0;
+      const bool active = live;
       const uint32_t cw = s.pos >> 5;
       int avail = (int)(filled - cw);
       if (__any_sync(FULL_MASK, active && (avail <= DEC_TRIGGER ||
@@ -567,9 +573,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
     };
 
 #pragma unroll 1
-    for (int row = 0; row < DEC_OUT_T; row++) {
-      if ((row & (M3_DEC_CHK - 1)) == 0) ring_service();
-      const bool active = !s.done && s.err == 0;
+    for (int rb = 0; rb < DEC_OUT_T; rb += M3_DEC_CHK) {
+      ring_service();
+#pragma unroll DEC_UNROLL
+      for (int rr = 0; rr < M3_DEC_CHK; rr++) {
+      const int row = rb + rr;
+
+      const bool active = live;
       const uint32_t cw = s.pos >> 5;
       int64_t t = 0;
       uint64_t v = 0;
@@ -715,6 +725,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           lz_tz(s.prev_xor, plz, ptz);
           su_ok = (s.scheme == kScheme32 || s.scheme == kScheme64) && (s.unit >= 1 && s.unit <= 4);
         }
+        live = !s.done && s.err == 0;
       }
 
     sink:
@@ -776,6 +787,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           }
         }
       }
+    }
     }
 
     // ---------------- flush the output tile ----------------

@@ -746,7 +746,22 @@ __global__ void compact_gather_kernel(const uint8_t *slots, uint64_t slot_stride
   }
   const uint8_t *src = slots + w * slot_stride;
   uint8_t *dst = packed + o;
-  if ((((uintptr_t)dst | (uintptr_t)src) & 3u) == 0) {
+  if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0) {
+    // 16-byte vector copies, four in flight per lane
+    const uint64_t nv = l >> 4;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    uint64_t i = lane;
+    for (; i + 96 < nv; i += 128) {
+      const uint4 a = __ldg(s4 + i), b = __ldg(s4 + i + 32), c = __ldg(s4 + i + 64), d = __ldg(s4 + i + 96);
+      d4[i] = a;
+      d4[i + 32] = b;
+      d4[i + 64] = c;
+      d4[i + 96] = d;
+    }
+    for (; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+    for (uint64_t j = (nv << 4) + lane; j < l; j += 32) dst[j] = src[j];
+  } else if ((((uintptr_t)dst | (uintptr_t)src) & 3u) == 0) {
     const uint64_t nw = l >> 2;
     for (uint64_t i = lane; i < nw; i += 32)
       reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
