@@ -65,6 +65,8 @@ enum {
   M3TSZ_ERR_ITER_CLOSED = 10,      /* errClosed, m3tsz/iterator.go:33 */
   M3TSZ_ERR_VARINT_OVERFLOW = 11,  /* Go encoding/binary errOverflow */
   M3TSZ_ERR_UNEXPECTED_EOF = 12,   /* io.ErrUnexpectedEOF */
+  M3TSZ_ERR_OUT_OF_ORDER = 13,     /* errOutOfOrderIterator, encoding/iterators.go:229-236 */
+  M3TSZ_ERR_TOO_MANY_ITERATORS = 14, /* > 8 replicas per series or readers per block slice */
   /* library-level conditions */
   M3TSZ_ERR_CAPACITY = 100,        /* more datapoints / bytes than the caller's buffer holds */
   M3TSZ_ERR_INVALID_ARG = 101,
@@ -223,6 +225,32 @@ int m3tsz_decode_downsample_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts
                                        uint32_t n_windows, double *h_sum, int64_t *h_count,
                                        double *h_min, double *h_max, uint32_t *h_n_points,
                                        int32_t *h_status);
+
+/* ------------------------------------------------------------------------
+ * Series merge: the iterator layer directly above the codec.
+ * For every series, merges the DECODED streams of its replicas / blocks exactly
+ * like the reference's seriesIterator over multiReaderIterators:
+ *   iterators            src/dbnode/encoding/iterators.go:56-262
+ *   multiReaderIterator  src/dbnode/encoding/multi_reader_iterator.go:62-155
+ *   seriesIterator       src/dbnode/encoding/series_iterator.go:74-83,129-215
+ * i.e. k-way timestamp merge, equal-timestamp strategy (0 last-pushed = default,
+ * 1 highest value, 2 lowest value, 3 highest frequency; encoding/iterators_types.go),
+ * removal of consecutive equal timestamps, [start_ns, end_ns) filter (both 0 = no
+ * filter), errOutOfOrderIterator, propagation of reader (decode) errors.
+ *
+ * Inputs are the outputs of m3tsz_decode_batch over n_seq streams:
+ *   sequence q = (d_ts + q*cap, d_val + q*cap, d_n_points[q], d_seq_status[q])
+ *   slice k    = sequences [d_slice_off[k], d_slice_off[k+1])  readers of one block
+ *   replica r  = slices    [d_replica_off[r], d_replica_off[r+1])  in block order
+ *   series s   = replicas  [d_series_off[s], d_series_off[s+1])
+ * Outputs: merged datapoints [n_series][out_cap], count, status per series.
+ * ---------------------------------------------------------------------- */
+int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *d_val, uint64_t cap,
+                             const uint32_t *d_n_points, const int32_t *d_seq_status,
+                             const uint64_t *d_slice_off, const uint64_t *d_replica_off,
+                             const uint64_t *d_series_off, uint64_t n_series, int64_t start_ns,
+                             int64_t end_ns, int32_t strategy, int64_t *d_ts_out, double *d_val_out,
+                             uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, void *stream);
 
 #ifdef __cplusplus
 }

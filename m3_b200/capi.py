@@ -15,6 +15,8 @@ ERR_DOD_OVERFLOW = 4
 ERR_NO_TIME_SCHEME = 5
 ERR_UNRECOGNIZED_UNIT = 6
 ERR_INVALID_MULT = 7
+ERR_OUT_OF_ORDER = 13
+ERR_TOO_MANY_ITERATORS = 14
 ERR_CAPACITY = 100
 ERR_INVALID_ARG = 101
 ERR_CUDA = 102
@@ -51,7 +53,7 @@ EXPORTED_SYMBOLS = [
     "m3tsz_last_cuda_error", "m3tsz_ctx_launch_count", "m3tsz_decode_batch",
     "m3tsz_decode_batch_host", "m3tsz_encode_batch", "m3tsz_encode_bound",
     "m3tsz_compact_streams", "m3tsz_encode_batch_host", "m3tsz_decode_downsample_batch",
-    "m3tsz_decode_downsample_batch_host",
+    "m3tsz_decode_downsample_batch_host", "m3tsz_merge_series_batch",
 ]
 
 
@@ -99,6 +101,9 @@ def lib():
     L.m3tsz_decode_downsample_batch_host.restype = C.c_int
     L.m3tsz_decode_downsample_batch_host.argtypes = [vp, po, vp, u64, vp, u64, i64, i64, u32, vp, vp,
                                                      vp, vp, vp, vp]
+    L.m3tsz_merge_series_batch.restype = C.c_int
+    L.m3tsz_merge_series_batch.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp, u64, i64, i64, i32, vp, vp,
+                                           u64, vp, vp, vp]
     _lib = L
     return L
 

@@ -114,6 +114,8 @@ const char *m3tsz_status_string(int st) {
     case M3TSZ_ERR_ITER_CLOSED: return "iterator is closed";
     case M3TSZ_ERR_VARINT_OVERFLOW: return "binary: varint overflows a 64-bit integer";
     case M3TSZ_ERR_UNEXPECTED_EOF: return "unexpected EOF";
+    case M3TSZ_ERR_OUT_OF_ORDER: return "values are out of order from inner iterator";
+    case M3TSZ_ERR_TOO_MANY_ITERATORS: return "too many replicas / readers for one series";
     case M3TSZ_ERR_CAPACITY: return "output capacity exceeded";
     case M3TSZ_ERR_INVALID_ARG: return "invalid argument";
     case M3TSZ_ERR_CUDA: return "CUDA error";
@@ -300,6 +302,43 @@ int m3tsz_compact_streams(m3tsz_ctx *ctx, const uint8_t *d_slots, uint64_t slot_
   CK(cudaMemcpyAsync(&flag, ctx->d_flag, sizeof(flag), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return flag ? M3TSZ_ERR_CAPACITY : M3TSZ_OK;
+}
+
+int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *d_val, uint64_t cap,
+                             const uint32_t *d_n_points, const int32_t *d_seq_status,
+                             const uint64_t *d_slice_off, const uint64_t *d_replica_off,
+                             const uint64_t *d_series_off, uint64_t n_series, int64_t start_ns,
+                             int64_t end_ns, int32_t strategy, int64_t *d_ts_out, double *d_val_out,
+                             uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, void *stream) {
+  if (!ctx) return M3TSZ_ERR_INVALID_ARG;
+  if (n_series == 0) return M3TSZ_OK;
+  if (!d_ts || !d_val || !d_n_points || !d_slice_off || !d_replica_off || !d_series_off || !d_ts_out ||
+      !d_val_out || !d_n_out || !d_status || cap == 0 || out_cap == 0 || out_cap > 0xffffffffull ||
+      strategy < 0 || strategy > 3)
+    return M3TSZ_ERR_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  MergeParams p;
+  memset(&p, 0, sizeof(p));
+  p.ts = d_ts;
+  p.val = d_val;
+  p.cap = cap;
+  p.n_points = d_n_points;
+  p.seq_status = d_seq_status;
+  p.slice_off = d_slice_off;
+  p.replica_off = d_replica_off;
+  p.series_off = d_series_off;
+  p.n_series = n_series;
+  p.start = start_ns;
+  p.end = end_ns;
+  p.strategy = strategy;
+  p.ts_out = d_ts_out;
+  p.val_out = d_val_out;
+  p.out_cap = out_cap;
+  p.n_out = d_n_out;
+  p.status = d_status;
+  CK(launch_merge(p, (cudaStream_t)stream));
+  ctx->launches++;
+  return M3TSZ_OK;
 }
 
 // --------------------------------------------------------------------------

@@ -57,6 +57,25 @@ struct EncodeParams {
 
 cudaError_t launch_encode(const EncodeParams &p, bool int_optimized, cudaStream_t stream);
 
+// iterator layer above the codec (m3tsz_merge.cu)
+struct MergeParams {
+  const int64_t *ts;  // decoded reader sequences [n_seq][cap]
+  const double *val;
+  uint64_t cap;
+  const uint32_t *n_points;   // [n_seq]
+  const int32_t *seq_status;  // optional [n_seq]
+  const uint64_t *slice_off, *replica_off, *series_off;
+  uint64_t n_series;
+  int64_t start, end;
+  int strategy;
+  int64_t *ts_out;  // [n_series][out_cap]
+  double *val_out;
+  uint64_t out_cap;
+  uint32_t *n_out;
+  int32_t *status;
+};
+cudaError_t launch_merge(const MergeParams &p, cudaStream_t stream);
+
 // exclusive scan of aligned lengths + gather into a packed buffer
 cudaError_t launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint64_t *len,
                            uint64_t n_series, uint32_t align, uint8_t *packed,

@@ -54,7 +54,9 @@ enum {
   M3O_ERR_ANNOTATION_SHORT = 9,  /* errAnnotationTooFewBytes, m3tsz/timestamp_iterator.go:35 */
   M3O_ERR_ITER_CLOSED = 10,      /* errClosed, m3tsz/iterator.go:33 */
   M3O_ERR_VARINT_OVERFLOW = 11,  /* encoding/binary errOverflow (Go stdlib ReadUvarint) */
-  M3O_ERR_UNEXPECTED_EOF = 12    /* io.ErrUnexpectedEOF (Go stdlib ReadUvarint, i>0) */
+  M3O_ERR_UNEXPECTED_EOF = 12,   /* io.ErrUnexpectedEOF (Go stdlib ReadUvarint, i>0) */
+  M3O_ERR_OUT_OF_ORDER = 13,     /* errOutOfOrderIterator, encoding/iterators_types.go / iterators.go:229-236 */
+  M3O_ERR_TOO_MANY_ITERATORS = 14 /* more than 12 iterators at one level (restatement limit) */
 };
 
 /* ---- bit I/O (ostream.go / istream.go) exposed for the golden bit-I/O tests ---- */
@@ -162,6 +164,24 @@ int m3o_encode_batch(const int64_t *ts, const double *vals, size_t n_series, siz
 void m3o_downsample_series(const int64_t *ts, const double *vals, size_t n, int64_t range_start_ns,
                            int64_t window_ns, size_t n_windows, double *sum, int64_t *count,
                            double *min, double *max, double *last);
+
+/* ---- iterator layer above the codec (m3tsz_merge_oracle.c):
+ * iterators / multiReaderIterator / seriesIterator over decoded reader sequences.
+ * Sequence q = (ts + q*cap, val + q*cap, n_points[q], seq_status[q]); slice k = sequences
+ * [slice_off[k], slice_off[k+1]) (readers of one block); replica r = slices
+ * [replica_off[r], replica_off[r+1]) in block order; series s = replicas
+ * [series_off[s], series_off[s+1]).  start/end: [start, end) filter (both 0 = none);
+ * strategy: 0 last-pushed, 1 highest value, 2 lowest value, 3 highest frequency. ---- */
+int64_t m3o_series_merge(const int64_t *ts, const double *val, uint64_t cap, const uint32_t *n_points,
+                         const int32_t *seq_status, const uint64_t *slice_off,
+                         const uint64_t *replica_off, uint64_t rep0, uint64_t rep1, int64_t start,
+                         int64_t end, int strategy, int64_t *ts_out, double *val_out, uint64_t out_cap,
+                         int32_t *status);
+void m3o_series_merge_batch(const int64_t *ts, const double *val, uint64_t cap, const uint32_t *n_points,
+                            const int32_t *seq_status, const uint64_t *slice_off,
+                            const uint64_t *replica_off, const uint64_t *series_off, uint64_t n_series,
+                            int64_t start, int64_t end, int strategy, int64_t *ts_out, double *val_out,
+                            uint64_t out_cap, uint32_t *n_out, int32_t *status);
 
 #ifdef __cplusplus
 }

@@ -20,10 +20,9 @@ ERR_DOD_OVERFLOW = 4
 
 
 def build_oracle(force=False):
-    src = os.path.join(ORACLE_DIR, "m3tsz_oracle.c")
-    hdr = os.path.join(ORACLE_DIR, "m3tsz_oracle.h")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("m3tsz_oracle.c", "m3tsz_merge_oracle.c", "m3tsz_oracle.h")]
     if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(f) for f in srcs)):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
     return _LIB_PATH
@@ -108,6 +107,8 @@ def lib():
                                        vp, C.c_size_t, vp, vp, C.c_int]),
         "m3o_downsample_series": (None, [vp, vp, C.c_size_t, C.c_int64, C.c_int64, C.c_size_t, vp, vp,
                                          vp, vp, vp]),
+        "m3o_series_merge_batch": (None, [vp, vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, C.c_int64,
+                                          C.c_int64, C.c_int, vp, vp, C.c_uint64, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -351,3 +352,28 @@ def convert_to_int_float(v, cur_max_mult):
     err = lib().m3o_convert_to_int_float(float(v), cur_max_mult, C.byref(val), C.byref(mult),
                                          C.byref(isf))
     return val.value, mult.value, bool(isf.value), err
+
+
+def series_merge_batch(ts, vals, n_points, seq_status, slice_off, replica_off, series_off, start=0, end=0,
+                       strategy=0, out_cap=None):
+    """Oracle of the iterator layer (iterators / multiReaderIterator / seriesIterator).
+    ts, vals: [n_seq, cap]; returns (ts_out[S,out_cap], val_out, n_out[S], status[S])."""
+    ts = np.ascontiguousarray(ts, dtype=np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    n_points = np.ascontiguousarray(n_points, dtype=np.uint32)
+    seq_status = np.ascontiguousarray(seq_status, dtype=np.int32)
+    slice_off = np.ascontiguousarray(slice_off, dtype=np.uint64)
+    replica_off = np.ascontiguousarray(replica_off, dtype=np.uint64)
+    series_off = np.ascontiguousarray(series_off, dtype=np.uint64)
+    S = len(series_off) - 1
+    cap = ts.shape[1] if ts.ndim == 2 and ts.shape[0] else 1
+    if out_cap is None:
+        out_cap = max(1, int(n_points.sum()))
+    ts_out = np.zeros((S, out_cap), dtype=np.int64)
+    val_out = np.zeros((S, out_cap), dtype=np.float64)
+    n_out = np.zeros(S, dtype=np.uint32)
+    status = np.zeros(S, dtype=np.int32)
+    lib().m3o_series_merge_batch(_ptr(ts), _ptr(vals), cap, _ptr(n_points), _ptr(seq_status), _ptr(slice_off),
+                                 _ptr(replica_off), _ptr(series_off), S, int(start), int(end), int(strategy),
+                                 _ptr(ts_out), _ptr(val_out), out_cap, _ptr(n_out), _ptr(status))
+    return ts_out, val_out, n_out, status
