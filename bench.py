@@ -333,6 +333,20 @@ def run_ours(args):
     ds_ms = time_fn(lambda: codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC,
                                                     (P * 60 + 299) // 300, out=ds))
     n_win = ds.sum.shape[0]
+    del ds
+
+    # series merge (row N1): RF=3 fetch shape -- every 3 consecutive decoded streams are the
+    # replicas of one series (same timestamps => 3 inputs collapse to 1 output per timestamp)
+    Sm = (min(S, 300_000) // 3) * 3
+    m_slice = torch.arange(Sm + 1, dtype=torch.int64, device=dev)
+    m_rep = torch.arange(Sm + 1, dtype=torch.int64, device=dev)
+    m_ser = torch.arange(0, Sm + 1, 3, dtype=torch.int64, device=dev)
+    mg = lambda: codec.merge_series(dec.ts[:Sm], dec.values[:Sm], dec.n_points[:Sm], dec.status[:Sm], m_slice,
+                                    m_rep, m_ser, P)
+    m_out = mg()
+    assert int((m_out[3] != 0).sum()) == 0 and bool((m_out[2] == P).all())
+    del m_out
+    merge_ms = time_fn(mg, n=3)
 
     # ---- fetch-side all-gather (only when a query spans shards) ----
     allgather = None
@@ -449,6 +463,9 @@ def run_ours(args):
         "decode_downsample_dps": S * P / (ds_ms * 1e-3),
         "decode_downsample": {"windows": n_win, "ms": ds_ms,
                               "algorithmic_gbs": (compressed_bytes + n_win * S * 32) / (ds_ms * 1e-3) / 1e9},
+        "series_merge": {"replicas": 3, "series": Sm // 3, "ms": merge_ms,
+                         "input_dps": Sm * P / (merge_ms * 1e-3),
+                         "algorithmic_gbs": (Sm * P * 16 + (Sm // 3) * P * 16) / (merge_ms * 1e-3) / 1e9},
         "encode_ms": enc_ms, "decode_ms": dec_ms_max,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks, "fetch_allgather": allgather,
