@@ -70,12 +70,12 @@ __device__ __forceinline__ void put64(EncLane &s, uint32_t *tile, int lane, uint
   }
 }
 
-// appends header (low hb bits of hdr, hb 0..32) followed by payload (low plen
-// bits, plen 0..64): one merge of up to 96 bits into the accumulator.
-__device__ __forceinline__ void emit_code(EncLane &s, uint32_t *tile, int lane, uint32_t hdr, int hb,
-                                          uint64_t payload, int plen) {
+// appends header (low hb bits of hdr, hb 0..32) followed by a payload given
+// LEFT-ALIGNED in P (its top plen bits, plen 0..64; bits below must be zero): one
+// merge of up to 96 bits into the accumulator.
+__device__ __forceinline__ void emit_code_p(EncLane &s, uint32_t *tile, int lane, uint32_t hdr, int hb,
+                                            uint64_t P, int plen) {
   const uint32_t H = hb ? (hdr << (32 - hb)) : 0u;
-  const uint64_t P = plen ? (payload << (64 - plen)) : 0ull;
   const uint32_t Ph = (uint32_t)(P >> 32), Pl = (uint32_t)P;
   const uint32_t c0 = H | __funnelshift_rc(Ph, 0u, (uint32_t)hb);
   const uint32_t c1 = __funnelshift_rc(Pl, Ph, (uint32_t)hb);
@@ -94,6 +94,11 @@ __device__ __forceinline__ void emit_code(EncLane &s, uint32_t *tile, int lane, 
   s.k += full;
   s.sh = tot & 31u;
 }
+// same with the payload right-aligned (its low plen bits)
+__device__ __forceinline__ void emit_code(EncLane &s, uint32_t *tile, int lane, uint32_t hdr, int hb,
+                                          uint64_t payload, int plen) {
+  emit_code_p(s, tile, lane, hdr, hb, plen ? (payload << (64 - plen)) : 0ull, plen);
+}
 
 // ---- convertToIntFloat (m3tsz.go:78-119) ----------------------------------
 // Cheap NECESSARY condition for convertToIntFloat(v, cur) to return an int for
@@ -105,12 +110,13 @@ __device__ __forceinline__ bool maybe_int(double v) {
   const double a = fabs(v);
   const double p = __dmul_rn(a, 1000000.0);
   const uint64_t pb = (uint64_t)__double_as_longlong(p);
-  const int e = (int)(pb >> 52) & 0x7ff;
-  if (e >= 1023 + 48) return true;
-  if (e < 1023) return (e >= 1022) || (a < 1e-300);
-  const int f = 52 - (e - 1023);  // fractional mantissa bits, 5..52
-  const uint64_t mask = (1ull << f) - 1ull;
-  return ((pb + 8ull) & mask) <= 16ull;
+  const int e = (int)(pb >> 52);  // sign bit is clear
+  const int f = 1075 - e;         // fractional mantissa bits of p when 5 <= f <= 52
+  const uint64_t mask = (1ull << (f & 63)) - 1ull;
+  const bool far_from_int = ((pb + 8ull) & mask) > 16ull;
+  const bool in_range = (unsigned)(f - 5) <= 47u;          // 1 <= p < 2^48
+  const bool tiny = (e < 1022) && (a >= 1e-300);          // p < 0.5: only N = 0 is near, i.e. v ~ 0
+  return !((in_range && far_from_int) || tiny);
 }
 
 // Go int64(float64) on amd64 (CVTTSD2SQ): out of range / NaN -> 0x8000000000000000
@@ -645,13 +651,26 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) encode_kernel(const EncodeP
       if (__all_sync(FULL_MASK, hot || !active)) {
         // every live lane: '0' (zero DoD) [+ '1' no-update] + XOR code, one merge
         s.prev_time = t;
-        uint32_t hdr = INT_OPT ? 1u : 0u;
-        int hb = INT_OPT ? 2 : 1;
-        uint64_t payload = 0;
-        int plen = 0;
-        xor_code(s, fb, hdr, hb, payload, plen);
+        const uint32_t pre = INT_OPT ? 1u : 0u;  // '0' zero DoD [+ '1' no-update]
+        const int pb = INT_OPT ? 2 : 1;
+        const uint64_t x = s.prev_bits ^ fb;
+        int cl, ct;
+        lz_tz(x, cl, ct);  // (64, 0) for x == 0
+        const bool zero = (x == 0);  // only possible without the int optimisation
+        const bool cont = !zero && cl >= s.plz && ct >= s.ptz;
+        const int nm = 64 - cl - ct;
+        // payload left-aligned: (x >> ptz) << (64 - plen) == x << plz, (x >> ct) << (64 - nm) == x << cl
+        const uint64_t P = shl64(x, cont ? s.plz : cl);
+        const int plen = zero ? 0 : (cont ? 64 - s.plz - s.ptz : nm);
+        const uint32_t hdr = zero ? (pre << 1)
+                                  : (cont ? ((pre << 2) | 2u)
+                                          : ((pre << 14) | (3u << 12) | ((uint32_t)cl << 6) | (uint32_t)(nm - 1)));
+        const int hb = pb + (zero ? 1 : (cont ? 2 : 14));
+        s.plz = cl;  // PrevXOR := x
+        s.ptz = ct;
+        s.prev_bits = fb;
         if (active) {
-          emit_code(s, out_tile, lane, hdr, hb, payload, plen);
+          emit_code_p(s, out_tile, lane, hdr, hb, P, plen);
           s.n_enc++;
         }
       } else if (active && s.err == 0) {
