@@ -79,14 +79,33 @@ struct DecState {
 // generic bit reader over global memory (slow path: first datapoint, markers,
 // annotations, unit changes, 32/64-bit delta-of-delta, int-mode headers)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t gpeek64(const uint8_t *base, uint64_t nbytes, uint64_t wbase,
-                                            uint32_t pos) {
-  uint64_t w = wbase + (pos >> 5);
-  uint32_t w0 = load_be32(base, nbytes, w);
-  uint32_t w1 = load_be32(base, nbytes, w + 1);
-  uint32_t w2 = load_be32(base, nbytes, w + 2);
-  uint32_t hi = __funnelshift_l(w1, w0, pos);
-  uint32_t lo = __funnelshift_l(w2, w1, pos);
+// Where the slow path reads from: the lane's ring column while the words it
+// needs have landed there (words [.., ring_safe) relative to wbase), global
+// memory otherwise (first datapoint before the first refill, annotations that
+// run past the ring, lanes that ran dry).
+struct SlowSrc {
+  const uint8_t *base;
+  uint64_t nbytes;
+  const uint32_t *ring_lane;  // ring + lane
+  uint32_t ring_safe;
+};
+
+__device__ __forceinline__ uint64_t gpeek64(const SlowSrc &src, uint64_t wbase, uint32_t pos) {
+  const uint32_t wr = pos >> 5;
+  uint32_t w0, w1, w2;
+  if (wr + 3u <= src.ring_safe) {
+    const uint32_t *tp = src.ring_lane + (wr & (DEC_RING - 1)) * DEC_STRIDE;
+    w0 = __byte_perm(tp[0], 0, 0x0123);
+    w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123);
+    w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123);
+  } else {
+    const uint64_t w = wbase + wr;
+    w0 = load_be32(src.base, src.nbytes, w);
+    w1 = load_be32(src.base, src.nbytes, w + 1);
+    w2 = load_be32(src.base, src.nbytes, w + 2);
+  }
+  const uint32_t hi = __funnelshift_l(w1, w0, pos);
+  const uint32_t lo = __funnelshift_l(w2, w1, pos);
   return ((uint64_t)hi << 32) | lo;
 }
 
@@ -98,7 +117,7 @@ __device__ __forceinline__ uint64_t gpeek64(const uint8_t *base, uint64_t nbytes
       s.err = M3TSZ_ERR_EOF;                                                     \
       return false;                                                              \
     }                                                                            \
-    var = _n ? (gpeek64(base, nbytes, s.wbase, s.pos) >> (64 - _n)) : 0ull;       \
+    var = _n ? (gpeek64(src, s.wbase, s.pos) >> (64 - _n)) : 0ull;               \
     s.pos += (uint32_t)_n;                                                       \
   }
 
@@ -106,8 +125,8 @@ __device__ __forceinline__ uint64_t gpeek64(const uint8_t *base, uint64_t nbytes
 // datapoint was produced (iterator.Next() == true *or* the value was read
 // without error); false on end-of-stream (s.done) or error (s.err).
 template <bool INT_OPT>
-__device__ __noinline__ bool decode_dp_slow(DecState &s, const uint8_t *base, uint64_t nbytes,
-                                            int default_unit, int64_t &out_t, uint64_t &out_v) {
+__device__ __noinline__ bool decode_dp_slow(DecState &s, const SlowSrc src, int default_unit,
+                                            int64_t &out_t, uint64_t &out_v) {
   // ---- ReadTimestamp, timestamp_iterator.go:80-113 ----
   const bool first = (s.prev_time == 0);
   int64_t nt = 0;
@@ -126,7 +145,7 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const uint8_t *base, ui
   // readMarkerOrDeltaOfDelta :233-244 / tryReadMarker :175-231 (recursion unrolled)
   for (;;) {
     if (s.pos + kMarkerBits <= s.end) {
-      uint32_t p = (uint32_t)(gpeek64(base, nbytes, s.wbase, s.pos) >> 53);
+      uint32_t p = (uint32_t)(gpeek64(src, s.wbase, s.pos) >> 53);
       if ((p >> 2) == kMarkerOpcode) {
         int m = (int)(p & 3);
         if (m == kMarkerEOS) {
@@ -144,7 +163,7 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const uint8_t *base, ui
               s.err = (i > 0) ? M3TSZ_ERR_UNEXPECTED_EOF : M3TSZ_ERR_EOF;
               return false;
             }
-            uint32_t b = (uint32_t)(gpeek64(base, nbytes, s.wbase, s.pos) >> 56);
+            uint32_t b = (uint32_t)(gpeek64(src, s.wbase, s.pos) >> 56);
             s.pos += 8;
             if (b < 0x80) {
               if (i == 9 && b > 1) {
@@ -221,7 +240,7 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const uint8_t *base, ui
           swallowed = true;
           break;
         }
-        uint64_t b = gpeek64(base, nbytes, s.wbase, s.pos) >> 63;
+        uint64_t b = gpeek64(src, s.wbase, s.pos) >> 63;
         s.pos += 1;
         if (b == 0) {
           nb = (i == 0) ? 7 : (i == 1 ? 9 : 12);
@@ -717,7 +736,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           DecState tmp = s;   // copy-in / copy-out keeps the lane state in registers
           int64_t st = 0;
           uint64_t sv = 0;
-          const bool em = decode_dp_slow<INT_OPT>(tmp, p.streams, p.streams_bytes, p.default_unit, st, sv);
+          SlowSrc src;
+          src.base = p.streams;
+          src.nbytes = p.streams_bytes;
+          src.ring_lane = ring + lane;
+          src.ring_safe = ((int)(filled - cw) >= 0) ? safe : 0u;  // ring abandoned after a skip
+          const bool em = decode_dp_slow<INT_OPT>(tmp, src, p.default_unit, st, sv);
           s = tmp;
           t = st;
           v = sv;
