@@ -674,17 +674,49 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           dod = (int64_t)((uint64_t)(int64_t)f * (uint64_t)s.unit_ns);
         }
         uint32_t x = h << c;
-        // value grammar (iterator.go:128-176); kinds: float-next / int-diff / repeat
-        bool k_float = true, k_int = false;
+        // value grammar (iterator.go:128-176); kinds: float-next / int-diff / repeat /
+        // update to float mode (full 64-bit value) / update of the int header + diff
+        bool k_float = true, k_int = false, k_full = false, k_hdr = false;
+        int nsig = s.sig, nmult = s.mult;
         if (INT_OPT) {
           const bool b0 = (x >> 31) != 0;
           const bool rep = !b0 && ((x >> 30) & 1u);
-          ok = ok && (b0 || rep);
           k_float = b0 && s.is_float;
           k_int = b0 && !s.is_float;
-          ok = ok && !(k_int && s.sig == 64);
           c += b0 ? 1u : 2u;
           x <<= 1;
+          if (!b0 && !rep) {  // opcodeUpdate, not a repeat (divergent, infrequent)
+            c += 1;           // float / int mode flag
+            if ((x >> 30) & 1u) {
+              k_full = true;
+            } else {  // readIntSigMult, iterator.go:178-193; <= 12 more header bits
+              k_hdr = true;
+              k_int = true;
+              uint32_t y = x << 2;
+              if (y >> 31) {
+                if ((y >> 30) & 1u) {
+                  nsig = (int)((y >> 24) & 63u) + 1;
+                  y <<= 8;
+                  c += 8;
+                } else {
+                  nsig = 0;
+                  y <<= 2;
+                  c += 2;
+                }
+              } else {
+                y <<= 1;
+                c += 1;
+              }
+              if (y >> 31) {
+                nmult = (int)((y >> 28) & 7u);
+                c += 4;
+              } else {
+                c += 1;
+              }
+              ok = ok && (nmult <= kMaxMult);  // the error case is the slow path's
+            }
+          }
+          ok = ok && !(k_int && nsig == 64);
         }
         const bool zero = !(x >> 31);
         const bool cont = (x >> 30) == 2u;
@@ -699,7 +731,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
         }
         if (INT_OPT && !k_float) {
           hb = 0;
-          n = k_int ? s.sig + 1 : 0;
+          n = k_int ? nsig + 1 : (k_full ? 64 : 0);
         }
         c += hb;
         const uint64_t field = extract64(w0, w1, w2, w3, sh + c);
@@ -717,6 +749,17 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
               s.prev_xor = xr;
               s.prev_bits ^= xr;
               lz_tz(xr, plz, ptz);
+            }
+            if (INT_OPT && k_full) {  // readFullFloat, float_encoder_iterator.go:105-115
+              s.prev_bits = payload;
+              s.prev_xor = payload;
+              lz_tz(payload, plz, ptz);
+              s.is_float = true;
+            }
+            if (INT_OPT && k_hdr) {
+              s.sig = nsig;
+              s.mult = nmult;
+              s.is_float = false;
             }
             t = s.prev_time;
             v = s.prev_bits;
