@@ -421,6 +421,155 @@ __device__ __forceinline__ void encode_time(EncLane &s, uint32_t *tile, int lane
   }
 }
 
+// ---- second-tier candidate (see the kernel's datapoint step) ---------------
+struct Tier2 {
+  uint32_t thdr;  // delta-of-delta code
+  int thb;
+  int kind;       // 0 float XOR, 1 float repeat, 2 int diff, 3 int repeat
+  uint32_t neg;
+  uint64_t db;    // |diff| as integer (kind 2)
+  double val;     // converted value (kind 2)
+  int n_lower, hi_lower;  // tracker state after this datapoint (kind 2)
+  int new_sig;            // significant bits in force after this datapoint (kind 2)
+};
+
+// ToNormalizedDuration (x/time/time.go:55-57) with the unit's constant divisor
+__device__ __forceinline__ int64_t div_unit(int64_t dd, int u) {
+  switch (u) {
+    case 1: return dd / 1000000000LL;
+    case 2: return dd / 1000000LL;
+    case 3: return dd / 1000LL;
+    default: return dd;
+  }
+}
+
+// True when this datapoint can be coded without touching the mode / header
+// state: same s/ms/us/ns unit, not the first datapoint, delta-of-delta within the
+// 12-bit bucket, and the value is (a) float mode, certainly not int-like, or
+// (b) int mode, int-like at the current multiplier, diff in int64 range (a
+// significant-bits update is fine, a multiplier or mode change is not).
+// Nothing in `s` is modified.
+template <bool INT_OPT>
+__device__ __forceinline__ bool tier2_candidate(const EncLane &s, bool base, int64_t delta, uint64_t fb,
+                                                double v, Tier2 &c) {
+  bool ok = base && (s.unit >= 1 && s.unit <= 4) && s.n_enc > 0;
+  const int64_t dd = (int64_t)((uint64_t)delta - (uint64_t)s.prev_delta);
+  const int64_t dod = div_unit(dd, s.unit);
+  ok = ok && (dod >= -2048 && dod <= 2047);
+  const uint32_t ud = (uint32_t)dod;
+  if (dod == 0) {
+    c.thdr = 0;
+    c.thb = 1;
+  } else if (dod >= -64 && dod <= 63) {
+    c.thdr = (2u << 7) | (ud & 0x7fu);
+    c.thb = 9;
+  } else if (dod >= -256 && dod <= 255) {
+    c.thdr = (6u << 9) | (ud & 0x1ffu);
+    c.thb = 12;
+  } else {
+    c.thdr = (14u << 12) | (ud & 0xfffu);
+    c.thb = 16;
+  }
+  c.kind = 0;
+  c.neg = 0;
+  c.db = 0;
+  c.val = 0.0;
+  c.n_lower = s.n_lower_sig;
+  c.hi_lower = s.hi_lower_sig;
+  c.new_sig = s.num_sig;
+  if (!INT_OPT) return ok;
+  if (s.is_float) {
+    c.kind = (fb == s.prev_bits) ? 1 : 0;
+    return ok && !maybe_int(v);
+  }
+  // convertToIntFloat at m = max_mult only (m3tsz.go:78-119); anything that would
+  // move on to a larger multiplier is left to the general path
+  const double sign = (v < 0.0) ? -1.0 : 1.0;
+  const double x = __dmul_rn(__dmul_rn(v, mult_pow10(s.max_mult)), sign);
+  const double i = trunc(x);
+  const double r = __dsub_rn(x, i);
+  const bool exact = (r == 0.0);
+  const bool lo = (r < 0.1) && (__longlong_as_double(__double_as_longlong(x) - 1) <= i);
+  const double next = __dadd_rn(i, 1.0);
+  const bool hi = (r > 0.9) && (__longlong_as_double(__double_as_longlong(x) + 1) >= next);
+  ok = ok && (x < 1e13) && (exact || lo || hi);
+  c.val = __dmul_rn(sign, (hi && !exact) ? next : i);
+  double diff = __dsub_rn(s.int_val, c.val);
+  ok = ok && (diff < 9223372036854775807.0) && (diff > -9223372036854775808.0);
+  if (diff == 0.0) {
+    c.kind = 3;
+    return ok;
+  }
+  c.kind = 2;
+  if (diff < 0.0) {
+    c.neg = 1;
+    diff = -diff;
+  }
+  c.db = ok ? (uint64_t)__double2ll_rz(diff) : 1ull;
+  const int ns = num_sig(c.db);
+  // IntSigBitsTracker.TrackNewSig without committing (int_sig_bits_tracker.go:68-91)
+  c.new_sig = s.num_sig;
+  if (ns > s.num_sig) {
+    c.new_sig = ns;
+  } else if (s.num_sig - ns >= 3) {
+    c.hi_lower = (c.n_lower == 0 || ns > c.hi_lower) ? ns : c.hi_lower;
+    c.n_lower++;
+    if (c.n_lower >= 5) {
+      c.new_sig = c.hi_lower;
+      c.n_lower = 0;
+    }
+  } else {
+    c.n_lower = 0;
+  }
+  return ok;
+}
+
+template <bool INT_OPT>
+__device__ __forceinline__ void tier2_commit(EncLane &s, uint32_t *tile, int lane, uint64_t fb, const Tier2 &c) {
+  if (!INT_OPT || c.kind == 0) {
+    const uint32_t pre = INT_OPT ? ((c.thdr << 1) | 1u) : c.thdr;  // + '1' no-update
+    const int pb = c.thb + (INT_OPT ? 1 : 0);
+    const uint64_t x = s.prev_bits ^ fb;
+    int cl, ct;
+    lz_tz(x, cl, ct);
+    const bool zero = (x == 0);
+    const bool cont = !zero && cl >= s.plz && ct >= s.ptz;
+    const int nm = 64 - cl - ct;
+    const uint64_t P = shl64(x, cont ? s.plz : cl);
+    const int plen = zero ? 0 : (cont ? 64 - s.plz - s.ptz : nm);
+    const uint32_t hdr = zero ? (pre << 1)
+                              : (cont ? ((pre << 2) | 2u)
+                                      : ((pre << 14) | (3u << 12) | ((uint32_t)cl << 6) | (uint32_t)(nm - 1)));
+    const int hb = pb + (zero ? 1 : (cont ? 2 : 14));
+    s.plz = cl;
+    s.ptz = ct;
+    s.prev_bits = fb;
+    emit_code_p(s, tile, lane, hdr, hb, P, plen);
+  } else if (c.kind == 2) {  // '1' no-update + sign + num_sig bits (encoder.go:224-230)
+    s.n_lower_sig = c.n_lower;
+    s.hi_lower_sig = c.hi_lower;
+    s.int_val = c.val;
+    uint32_t hdr = (c.thdr << 1) | 1u;  // '1' no-update
+    int hb = c.thb + 1;
+    if (c.new_sig != s.num_sig) {
+      // '0' update '0' no-repeat '0' int mode, new significant bits, '0' same multiplier
+      // (writeIntSigMult, encoder.go:235-250)
+      if (c.new_sig == 0) {
+        hdr = (c.thdr << 6) | (2u << 1);
+        hb = c.thb + 6;
+      } else {
+        hdr = (c.thdr << 12) | (3u << 7) | ((uint32_t)(c.new_sig - 1) << 1);
+        hb = c.thb + 12;
+      }
+      s.num_sig = c.new_sig;
+    }
+    const uint64_t P = s.num_sig ? (c.db << (64 - s.num_sig)) : 0ull;
+    emit_code_p(s, tile, lane, (hdr << 1) | c.neg, hb + 1, P, s.num_sig);
+  } else {  // '0' update + '1' repeat (float: encoder.go:186-189, int: :202-206)
+    emit_code_p(s, tile, lane, (c.thdr << 2) | 1u, c.thb + 2, 0ull, 0);
+  }
+}
+
 __device__ __forceinline__ uint32_t enc_smem_addr(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -648,6 +797,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) encode_kernel(const EncodeP
       bool hot = active && room && !p.units && p.unit == s.unit && (s.unit >= 1 && s.unit <= 4) &&
                  s.n_enc > 0 && delta == s.prev_delta;
       if (INT_OPT) hot = hot && s.is_float && fb != s.prev_bits && !maybe_int(v);
+      Tier2 c2;
       if (__all_sync(FULL_MASK, hot || !active)) {
         // every live lane: '0' (zero DoD) [+ '1' no-update] + XOR code, one merge
         s.prev_time = t;
@@ -671,6 +821,17 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) encode_kernel(const EncodeP
         s.prev_bits = fb;
         if (active) {
           emit_code_p(s, out_tile, lane, hdr, hb, P, plen);
+          s.n_enc++;
+        }
+      } else if (__all_sync(FULL_MASK, tier2_candidate<INT_OPT>(s, active && room && !p.units && p.unit == s.unit,
+                                                                 delta, fb, v, c2) ||
+                                           !active)) {
+        // second tier: small delta-of-delta + (float XOR | float repeat | int diff | int
+        // repeat) without a mode / header update, still one merge per lane
+        if (active) {
+          s.prev_time = t;
+          s.prev_delta = delta;
+          tier2_commit<INT_OPT>(s, out_tile, lane, fb, c2);
           s.n_enc++;
         }
       } else if (active && s.err == 0) {

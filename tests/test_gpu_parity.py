@@ -133,13 +133,13 @@ def test_reencode_fixtures_byte_identical(codecs):
 
 
 # ------------------------------------------------------------------ batch parity vs oracle
-def _mixed_series(rng, S, P):
+def _mixed_series(rng, S, P, fam_of=lambda s: s % 12):
     """Series families that exercise every branch of the value grammar."""
     start = 1599955200 * SEC
     ts = np.zeros((S, P), dtype=np.int64)
     vals = np.zeros((S, P), dtype=np.float64)
     for s in range(S):
-        fam = s % 12
+        fam = fam_of(s)
         if fam in (0, 1):  # regular cadence
             ts[s] = start + np.arange(P) * 60 * SEC
         elif fam in (2, 3):  # jittered seconds
@@ -218,6 +218,64 @@ def test_batch_encode_decode_mixed_vs_oracle(codecs, int_opt):
         _, ovals, oerr, _ = oracle_decode(o_out[s, : o_len[s]].tobytes(), int_opt)
         assert oerr == 0
         assert (gv[s] == ovals).all(), (s, s % 12)
+
+
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_homogeneous_warps_vs_oracle(codecs, int_opt):
+    """Same families, but one family per warp (32 consecutive series), so the kernels'
+    warp-voted fast tiers (zero / small delta-of-delta with float XOR, int diff, repeat,
+    significant-bits updates) are the code that runs; plus pairs of families per warp."""
+    rng = np.random.default_rng(23)
+    S, P = 12 * 32 + 6 * 32, 257
+    def fam_of(s):
+        w = s // 32
+        if w < 12:
+            return w
+        a, b = [(0, 1), (1, 3), (3, 6), (5, 11), (6, 2), (1, 7)][w - 12]  # two families per warp
+        return a if (s & 1) else b
+    ts, vals, start = _mixed_series(rng, S, P, fam_of)
+    codec = codecs[int_opt]
+    o_out, o_len, o_st = O.encode_batch(ts, vals, start, O.UNIT_S, int_opt, n_threads=8)
+    assert (o_st == 0).all()
+    enc = codec.encode(torch.from_numpy(ts).cuda(), torch.from_numpy(vals).cuda(),
+                       torch.full((S,), start, dtype=torch.int64, device="cuda"), unit=O.UNIT_S)
+    torch.cuda.synchronize()
+    g_len, g_st, g_out = enc.out_len.cpu().numpy(), enc.status.cpu().numpy(), enc.out.cpu().numpy()
+    assert (g_st == 0).all()
+    for s in range(S):
+        assert g_len[s] == o_len[s], (s, fam_of(s), g_len[s], o_len[s])
+        assert (g_out[s, : g_len[s]] == o_out[s, : o_len[s]]).all(), (s, fam_of(s))
+    packed, offsets = codec.compact(enc, align=16)
+    dec = codec.decode(packed, offsets, P)
+    torch.cuda.synchronize()
+    assert (dec.status.cpu().numpy() == 0).all() and (dec.n_points.cpu().numpy() == P).all()
+    assert (dec.ts.cpu().numpy() == ts).all()
+    gv = dec.values.cpu().numpy().view(np.uint64)
+    for s in range(S):
+        _, ovals, oerr, _ = oracle_decode(o_out[s, : o_len[s]].tobytes(), int_opt)
+        assert oerr == 0 and (gv[s] == ovals).all(), (s, fam_of(s))
+    # millisecond unit, millisecond-jittered timestamps, int and decimal values
+    S2 = 96
+    ts2 = start + np.cumsum(rng.integers(900, 1100, size=(S2, P)), axis=1) * 1_000_000
+    walk = 50.0 + np.cumsum(rng.normal(size=(S2, P)), axis=1)
+    vals2 = np.where((np.arange(S2) // 32 == 0)[:, None], walk,
+                     np.where((np.arange(S2) // 32 == 1)[:, None], np.round(walk * 4), np.round(walk, 1)))
+    o_out, o_len, o_st = O.encode_batch(ts2, vals2, start, O.UNIT_MS, int_opt, n_threads=8)
+    assert (o_st == 0).all()
+    enc = codec.encode(torch.from_numpy(ts2).cuda(), torch.from_numpy(vals2).cuda(),
+                       torch.full((S2,), start, dtype=torch.int64, device="cuda"), unit=O.UNIT_MS)
+    torch.cuda.synchronize()
+    g_len, g_out = enc.out_len.cpu().numpy(), enc.out.cpu().numpy()
+    assert (enc.status.cpu().numpy() == 0).all()
+    for s in range(S2):
+        assert g_len[s] == o_len[s] and (g_out[s, : g_len[s]] == o_out[s, : o_len[s]]).all(), s
+    packed, offsets = codec.compact(enc, align=16)
+    dec = codec.decode(packed, offsets, P)
+    torch.cuda.synchronize()
+    gv = dec.values.cpu().numpy().view(np.uint64)
+    for s in range(S2):
+        ots, ovals, oerr, _ = oracle_decode(o_out[s, : o_len[s]].tobytes(), int_opt)
+        assert oerr == 0 and (gv[s] == ovals).all() and (dec.ts[s].cpu().numpy() == ots).all(), s
 
 
 @pytest.mark.parametrize("int_opt", [True, False])
