@@ -243,7 +243,7 @@ def run_ours(args):
                        status=torch.empty(S, dtype=torch.int32, device=dev))
     codec.encode(ts, vals, start, unit=1, out=enc)
     total = int(enc.out_len.sum().item())
-    cap_bytes = total + 16 * S + 64
+    cap_bytes = total + 64 * S + 64
     packed = torch.empty(cap_bytes, dtype=torch.uint8, device=dev)
     offsets = torch.empty(S + 1, dtype=torch.int64, device=dev)
     dec = DecodeResult(ts=torch.empty((S, P), dtype=torch.int64, device=dev),
@@ -257,7 +257,7 @@ def run_ours(args):
     def compact():
         rc = capi.lib().m3tsz_compact_streams(
             codec.ctx.handle, C.c_void_p(enc.out.data_ptr()), stride, C.c_void_p(enc.out_len.data_ptr()),
-            S, 16, C.c_void_p(packed.data_ptr()), cap_bytes, C.c_void_p(offsets.data_ptr()),
+            S, 64, C.c_void_p(packed.data_ptr()), cap_bytes, C.c_void_p(offsets.data_ptr()),
             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         codec.ctx.check(rc, "compact")
 
@@ -378,7 +378,7 @@ def run_ours(args):
         # whole 1M-series batch = ~80 GB of host memory would dominate the run time);
         # its throughput is PCIe-bound and does not depend on the batch size.
         Se = min(S, args.e2e_series)
-        e_cap = int(enc.out_len[:Se].sum().item()) + 16 * Se + 64
+        e_cap = int(enc.out_len[:Se].sum().item()) + 64 * Se + 64
         h_ts = ts[:Se].cpu().pin_memory()
         h_vals = vals[:Se].cpu().pin_memory()
         h_start = start[:Se].cpu().pin_memory()
@@ -391,7 +391,7 @@ def run_ours(args):
         h_n = torch.empty(Se, dtype=torch.int32).pin_memory()
 
         def host_step():
-            codec.encode_host(h_ts, h_vals, h_start, 1, h_packed, h_off, h_len, h_st, align=16)
+            codec.encode_host(h_ts, h_vals, h_start, 1, h_packed, h_off, h_len, h_st, align=64)
             nbytes = int(h_off[-1])
             codec.decode_host(h_packed[:nbytes], h_off, P, h_dts, h_dvals, h_n, h_st)
             return nbytes

@@ -177,7 +177,9 @@ uint64_t m3tsz_encode_bound(uint64_t n_points);
 /* Packs the per-series slots written by m3tsz_encode_batch into one contiguous
  * buffer (the fileset data-file layout, src/dbnode/persist/fs/write.go): fills
  * d_offsets[n_series+1] (exclusive prefix sum of d_out_len, each start rounded
- * up to `align` bytes, align in {1,4,8,16}) and copies the bytes. */
+ * up to `align` bytes, align in {1,4,8,16,32,64}) and copies the bytes.  64-byte
+ * aligned starts let the decoder's lanes read their staging rings in phase (fewer
+ * shared-memory bank conflicts); any alignment decodes to the same result. */
 int m3tsz_compact_streams(m3tsz_ctx *ctx, const uint8_t *d_slots, uint64_t slot_stride,
                           const uint64_t *d_len, uint64_t n_series, uint32_t align,
                           uint8_t *d_packed, uint64_t packed_capacity, uint64_t *d_offsets,

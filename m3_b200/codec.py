@@ -140,7 +140,7 @@ class BatchCodec:
         self.ctx.check(rc, "m3tsz_encode_batch")
         return out
 
-    def compact(self, enc: EncodeResult, align=16, capacity: Optional[int] = None):
+    def compact(self, enc: EncodeResult, align=64, capacity: Optional[int] = None):
         """Packs slots into (packed uint8 [total], offsets int64 [S+1])."""
         S, stride = enc.out.shape
         dev = self.device
@@ -184,7 +184,7 @@ class BatchCodec:
         self.ctx.check(rc, "m3tsz_decode_batch_host")
 
     def encode_host(self, h_ts, h_values, h_start, unit, h_packed, h_offsets, h_out_len, h_status,
-                    align=16):
+                    align=64):
         """Host tensors in, ONE packed stream buffer + CSR offsets (int64 [S+1]) out."""
         S, P = h_ts.shape
         rc = capi.lib().m3tsz_encode_batch_host(

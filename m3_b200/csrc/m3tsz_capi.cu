@@ -185,8 +185,8 @@ int m3tsz_decode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t 
   if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
   if (n_series == 0) return M3TSZ_OK;
   if (!d_streams || !d_offsets || !d_ts || !d_val || max_points == 0 ||
-      max_points > 0xffffffffull || ((uintptr_t)d_streams & 15u) ||
-      streams_bytes >= (1ull << 34))  // 32-bit word indices inside the kernel; split larger batches
+      max_points >= (1ull << 27) || ((uintptr_t)d_streams & 15u) ||
+      streams_bytes >= (1ull << 34))  // 32-bit word / byte offsets inside the kernel; split larger batches
     return M3TSZ_ERR_INVALID_ARG;
   CK(cudaSetDevice(ctx->device));
   DecodeParams p;
@@ -287,7 +287,7 @@ int m3tsz_compact_streams(m3tsz_ctx *ctx, const uint8_t *d_slots, uint64_t slot_
                           uint8_t *d_packed, uint64_t packed_capacity, uint64_t *d_offsets,
                           void *stream) {
   if (!ctx || !d_offsets || (n_series && (!d_slots || !d_len || !d_packed))) return M3TSZ_ERR_INVALID_ARG;
-  if (!(align == 1 || align == 4 || align == 8 || align == 16)) return M3TSZ_ERR_INVALID_ARG;
+  if (!(align == 1 || align == 4 || align == 8 || align == 16 || align == 32 || align == 64)) return M3TSZ_ERR_INVALID_ARG;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   size_t tmp_bytes = compact_scan_tmp_bytes(n_series);
@@ -454,7 +454,7 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
   h_offsets[0] = 0;
   if (n_series == 0) return M3TSZ_OK;
   if (!h_ts || !h_val || !h_start || !h_packed) return M3TSZ_ERR_INVALID_ARG;
-  if (!(align == 1 || align == 4 || align == 8 || align == 16)) return M3TSZ_ERR_INVALID_ARG;
+  if (!(align == 1 || align == 4 || align == 8 || align == 16 || align == 32 || align == 64)) return M3TSZ_ERR_INVALID_ARG;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t sts[2] = {ctx->stream, ctx->stream2};
   const uint64_t ann_total = h_ann_series_off ? ann_bytes_len + 16 * h_ann_series_off[n_series] : 0;

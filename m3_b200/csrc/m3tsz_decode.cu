@@ -21,7 +21,7 @@ namespace m3tsz {
 // Tuning knobs (overridable with -D for sweeps; defaults = best of the round-1 sweep
 // at 100k x 1440, see profiles/r01_decode_history.md)
 #ifndef M3_DEC_OUT_T
-#define M3_DEC_OUT_T 8  // output tile rows (datapoints per flush)
+#define M3_DEC_OUT_T 4  // output tile rows (datapoints per flush)
 #endif
 #ifndef M3_DEC_TRIGGER
 #define M3_DEC_TRIGGER 24  // <= this many requested words ahead: the lane triggers a refill event
@@ -38,7 +38,16 @@ namespace m3tsz {
 #ifndef M3_DEC_MIN_BLOCKS
 #define M3_DEC_MIN_BLOCKS 4
 #endif
-constexpr int DEC_WARPS = 4;      // warps per block
+#ifndef M3_OPT_G
+#define M3_OPT_G 1  // per-group (M3_DEC_CHK datapoints) pre-check of the hot path's slow-changing conditions
+#endif
+#ifndef M3_OPT_X
+#define M3_OPT_X 1  // two-stage funnel extraction of the payload field
+#endif
+#ifndef M3_DEC_WARPS
+#define M3_DEC_WARPS 4
+#endif
+constexpr int DEC_WARPS = M3_DEC_WARPS;  // warps per block
 constexpr int DEC_RING = 64;      // staged words per lane (ring buffer, power of two)
 constexpr int DEC_MIRROR = 3;     // rows 64..66 mirror rows 0..2 so 4-word reads never wrap
 constexpr int DEC_FILL = 16;      // words per lane per asynchronous refill chunk
@@ -414,10 +423,14 @@ __device__ __forceinline__ void cp_async_wait_pending(uint32_t d) {
 // DEC_FILL (=16) words starting at global word index my_gw (of lane j, always a
 // multiple of 16) into lane j's ring column; one instruction serves two series
 // (lanes 0-15 -> series 2i, lanes 16-31 -> series 2i+1).  Ring slot of a word ==
-// its global word index & (DEC_RING-1) (every stream's base is DEC_RING-word
-// aligned); slots 0..2 are mirrored to 64..66 so 4-word reads never wrap.
+// its word index RELATIVE to the stream's base (the first word rounded down to a
+// DEC_FILL-word boundary) & (DEC_RING-1): lanes whose streams start DEC_FILL-word
+// (64-byte) aligned and consume at similar rates read the same rows, i.e.
+// different banks.  my_slot0 = the chunk's first slot (a multiple of DEC_FILL);
+// slots 0..2 are mirrored to 64..66 so 4-word reads never wrap.
 __device__ __forceinline__ void ring_fill(uint32_t *ring, const uint8_t *streams, uint64_t nbytes,
-                                          uint32_t mask, uint32_t my_gw, int lane) {
+                                          uint32_t mask, uint32_t my_gw, uint32_t my_slot0, int lane) {
+  const uint32_t my_packed = my_gw | (my_slot0 >> 4);  // gw is a multiple of 16: low bits carry slot0/16
   const int sub = lane & 15, half = lane >> 4;
   const uint32_t lane_dst = smem_addr(ring) + (uint32_t)sub * (DEC_STRIDE * 4u) + (uint32_t)half * 4u;
   const uint8_t *lane_src = streams + (uint32_t)sub * 4u;
@@ -426,8 +439,9 @@ __device__ __forceinline__ void ring_fill(uint32_t *ring, const uint8_t *streams
   if (mask == FULL_MASK && all_inb) {
 #pragma unroll 8
     for (int i = 0; i < 16; i++) {
-      const uint32_t gw = __shfl_sync(FULL_MASK, my_gw, 2 * i + half);
-      const uint32_t slot0 = gw & (DEC_RING - 1);
+      const uint32_t pk = __shfl_sync(FULL_MASK, my_packed, 2 * i + half);
+      const uint32_t gw = pk & ~15u;
+      const uint32_t slot0 = (pk & 3u) << 4;
       const uint32_t dst = lane_dst + slot0 * (DEC_STRIDE * 4u) + (uint32_t)i * 8u;
       const uint8_t *src = lane_src + (uint64_t)gw * 4ull;
       cp_async4(dst, src, 4u);
@@ -438,9 +452,10 @@ __device__ __forceinline__ void ring_fill(uint32_t *ring, const uint8_t *streams
   for (int i = 0; i < 16; i++) {
     if (!((mask >> (2 * i)) & 3u)) continue;  // warp-uniform
     const int j = 2 * i + half;
-    const uint32_t gw = __shfl_sync(FULL_MASK, my_gw, j);
+    const uint32_t pk = __shfl_sync(FULL_MASK, my_packed, j);
     if ((mask >> j) & 1u) {
-      const uint32_t slot0 = gw & (DEC_RING - 1);
+      const uint32_t gw = pk & ~15u;
+      const uint32_t slot0 = (pk & 3u) << 4;
       const uint32_t dst = lane_dst + slot0 * (DEC_STRIDE * 4u) + (uint32_t)i * 8u;
       const uint64_t b = ((uint64_t)gw + (uint32_t)sub) * 4ull;
       const uint32_t nb = (b + 4 <= nbytes) ? 4u : (b < nbytes ? (uint32_t)(nbytes - b) : 0u);
@@ -467,6 +482,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
   uint32_t *ring = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem) + warp * warp_smem);
   uint64_t *ts_tile = reinterpret_cast<uint64_t *>(ring + DEC_IN_TILE_WORDS);
   uint64_t *val_tile = ts_tile + DEC_OUT_TILE_DWORDS;
+  const uint32_t *ring_lane = ring + lane;  // this lane's ring column
+  uint64_t *ts_lane = ts_tile + lane;       // this lane's output tile columns (values: + DEC_OUT_TILE_DWORDS)
 
   const uint64_t warp_s0 = ((uint64_t)blockIdx.x * DEC_WARPS + warp) * 32ull;
   if (warp_s0 >= p.n_series) return;
@@ -503,9 +520,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
     } else if (o1 - o0 >= (1ull << 28)) {
       s.err = M3TSZ_ERR_STREAM_TOO_LARGE;
     } else {
-      // base = the stream's first word rounded down to a DEC_RING-word boundary
+      // base = the stream's first word rounded down to a DEC_FILL-word boundary
       const uint64_t w = o0 >> 2;
-      s.wbase = w & ~(uint64_t)(DEC_RING - 1);
+      s.wbase = w & ~(uint64_t)(DEC_FILL - 1);
       s.pos = (uint32_t)(w - s.wbase) * 32u + (uint32_t)(o0 & 3) * 8u;
       s.end = s.pos + (uint32_t)(o1 - o0) * 8u;
       pos0 = s.pos;
@@ -534,6 +551,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
   bool su_ok = false;
   // maintained flags: `live` = lane still decoding; they change on the general path only
   bool live = !s.done && s.err == 0;
+  bool fast_en = false;  // live && su_ok
 
   // flush geometry: one store instruction writes DEC_OUT_T rows of ts and of values
   // for FL_SPI series
@@ -545,7 +563,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
   const uint64_t *fl_tile = (fl_isval ? val_tile : ts_tile) + fl_r * DEC_STRIDE + fl_jo;
   uint64_t *fl_base = (fl_isval ? reinterpret_cast<uint64_t *>(p.val) : reinterpret_cast<uint64_t *>(p.ts)) +
                       (warp_s0 + fl_jo) * p.cap + fl_r;
-  const uint64_t fl_step = (uint64_t)FL_SPI * p.cap;
+  const uint32_t fl_step_bytes = (uint32_t)FL_SPI * (uint32_t)p.cap * 8u;  // cap < 2^27 (checked by the host)
 
   for (;;) {  // one group of DEC_OUT_T datapoints per iteration
     if (!__any_sync(FULL_MASK, live)) break;
@@ -577,7 +595,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           const uint32_t fmask =
               __ballot_sync(FULL_MASK, active && avail <= (rep == 0 ? DEC_ACCEPT : DEC_TRIGGER));
           if (!fmask) break;
-          ring_fill(ring, p.streams, p.streams_bytes, fmask, gbase + filled, lane);
+          ring_fill(ring, p.streams, p.streams_bytes, fmask, gbase + filled, filled & (DEC_RING - 1), lane);
           if ((fmask >> lane) & 1u) {
             filled += DEC_FILL;
             avail += DEC_FILL;
@@ -594,6 +612,16 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
 #pragma unroll 1
     for (int rb = 0; rb < DEC_OUT_T; rb += M3_DEC_CHK) {
       ring_service();
+#if M3_OPT_G
+      // Hot-path conditions that cannot change while the group stays on the hot path,
+      // checked once with margins for M3_DEC_CHK datapoints of <= 80 bits each: words
+      // landed, distance to the end of the stream, not the first datapoint and no
+      // wrap of prev_time to 0 (first <=> PrevTime == 0, timestamp_iterator.go:89),
+      // float mode.
+      bool pre_ok = fast_en && (((s.pos + 80u * (M3_DEC_CHK - 1)) >> 5) + DEC_FAST_WORDS <= safe) &&
+                    (s.pos + 80u * M3_DEC_CHK <= s.end) && (s.prev_time > 0) &&
+                    ((uint64_t)s.prev_delta < (1ull << 60)) && (!INT_OPT || s.is_float);
+#endif
 #pragma unroll DEC_UNROLL
       for (int rr = 0; rr < M3_DEC_CHK; rr++) {
       const int row = rb + rr;
@@ -604,24 +632,40 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
       uint64_t v = 0;
       bool emitted = false;
       // ---------------- parse 4 ring words ----------------
-      const uint32_t *tp = ring + (cw & (DEC_RING - 1)) * DEC_STRIDE + lane;
+      const uint32_t *tp = ring_lane + (cw & (DEC_RING - 1)) * DEC_STRIDE;
       const uint32_t w0 = __byte_perm(tp[0], 0, 0x0123), w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123),
                      w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123),
                      w3 = __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123);
       const uint32_t sh = s.pos & 31u;
       const uint32_t h = __funnelshift_l(w1, w0, sh);
-      const bool okb = active && su_ok && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
+#if M3_OPT_X
+      // 96-bit window at the bit position: (h, h1, h2); a field at offset c <= 32 is two more funnels
+      const uint32_t h1 = __funnelshift_l(w2, w1, sh), h2 = __funnelshift_l(w3, w2, sh);
+#define M3_FIELD64(c_) \
+  (((uint64_t)__funnelshift_lc(h1, h, (c_)) << 32) | (uint64_t)__funnelshift_lc(h2, h1, (c_)))
+#else
+#define M3_FIELD64(c_) extract64(w0, w1, w2, w3, sh + (c_))
+#endif
 
       // ---- hot candidate: zero delta-of-delta, float XOR code ----
       {
         uint32_t x = h << 1;
         uint32_t c = 1;
+#if M3_OPT_G
+        bool hot = pre_ok && (INT_OPT ? ((h >> 30) == 1u) : !(h >> 31));  // '0' zero DoD [+ '1' no update]
+        if (INT_OPT) {
+          x <<= 1;
+          c = 2;
+        }
+#else
+        const bool okb = fast_en && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
         bool hot = okb && !(h >> 31);
         if (INT_OPT) {
           hot = hot && (x >> 31) && s.is_float;  // '1' = no mode update
           x <<= 1;
           c = 2;
         }
+#endif
         const bool zero = !(x >> 31);
         const bool cont = (x >> 30) == 2u;
         const int lz = (int)((x >> 24) & 63u);
@@ -633,10 +677,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           n = 0;
           c -= cont ? 1u : 13u;
         }
-        const uint64_t field = extract64(w0, w1, w2, w3, sh + c);
+        const uint64_t field = M3_FIELD64(c);
         const uint64_t payload = n ? (field >> (64 - n)) : 0ull;
         c += (uint32_t)n;
+#if !M3_OPT_G
         hot = hot && (s.pos + c <= s.end);
+#endif
         if (__all_sync(FULL_MASK, hot || !active)) {
           // every live lane: unconditional update (finished lanes compute garbage
           // they never read again)
@@ -647,9 +693,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           s.prev_bits ^= xr;
           lz_tz(xr, plz, ptz);
           if (MODE == 0) {
-            ts_tile[row * DEC_STRIDE + lane] = (uint64_t)s.prev_time;
-            val_tile[row * DEC_STRIDE + lane] = s.prev_bits;
-            s.n += active ? 1u : 0u;
+            uint64_t *op = ts_lane + row * DEC_STRIDE;
+            op[0] = (uint64_t)s.prev_time;
+            op[DEC_OUT_TILE_DWORDS] = s.prev_bits;
+            s.n += (uint32_t)active;
             continue;
           }
           t = s.prev_time;
@@ -661,7 +708,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
 
       // ---------------- general path (any mix of cases) ----------------
       {
-        bool ok = okb;
+#if M3_OPT_G
+        pre_ok = false;  // the group's pre-check does not survive a general-path datapoint
+#endif
+        bool ok = fast_en && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
         uint32_t c = 1;  // bits consumed before the payload
         int64_t dod = 0;
         if (h >> 31) {
@@ -734,7 +784,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           n = k_int ? nsig + 1 : (k_full ? 64 : 0);
         }
         c += hb;
-        const uint64_t field = extract64(w0, w1, w2, w3, sh + c);
+        const uint64_t field = M3_FIELD64(c);
         const uint64_t payload = n ? (field >> (64 - n)) : 0ull;
         c += (uint32_t)n;
         if (ok) {
@@ -793,14 +843,16 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           su_ok = (s.scheme == kScheme32 || s.scheme == kScheme64) && (s.unit >= 1 && s.unit <= 4);
         }
         live = !s.done && s.err == 0;
+        fast_en = live && su_ok;
       }
 
     sink:
       // ---------------- sink ----------------
       if (MODE == 0) {
         if (emitted) {
-          ts_tile[row * DEC_STRIDE + lane] = (uint64_t)t;
-          val_tile[row * DEC_STRIDE + lane] = v;
+          uint64_t *op = ts_lane + row * DEC_STRIDE;
+          op[0] = (uint64_t)t;
+          op[DEC_OUT_TILE_DWORDS] = v;
           s.n++;
         }
       } else {
@@ -862,19 +914,18 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
       __syncwarp();
       const uint32_t lim = s.n < (uint32_t)p.cap ? s.n : (uint32_t)p.cap;
       const uint32_t my_rows = lim > tile_row0 ? min(lim - tile_row0, (uint32_t)DEC_OUT_T) : 0u;
-      uint64_t *dst = fl_base + tile_row0;
+      uint8_t *dst = reinterpret_cast<uint8_t *>(fl_base + tile_row0);
       if (__all_sync(FULL_MASK, my_rows == (uint32_t)DEC_OUT_T)) {
 #pragma unroll
-        for (int i = 0; i < FL_ITERS; i++) {
-          *dst = fl_tile[FL_SPI * i];
-          dst += fl_step;
-        }
+        for (int i = 0; i < FL_ITERS; i++)
+          *reinterpret_cast<uint64_t *>(dst + (uint64_t)(uint32_t)i * (uint64_t)fl_step_bytes) = fl_tile[FL_SPI * i];
       } else {
 #pragma unroll 4
         for (int i = 0; i < FL_ITERS; i++) {
           const uint32_t rows = __shfl_sync(FULL_MASK, my_rows, FL_SPI * i + fl_jo);
-          if ((uint32_t)fl_r < rows) *dst = fl_tile[FL_SPI * i];
-          dst += fl_step;
+          if ((uint32_t)fl_r < rows)
+            *reinterpret_cast<uint64_t *>(dst + (uint64_t)(uint32_t)i * (uint64_t)fl_step_bytes) =
+                fl_tile[FL_SPI * i];
         }
       }
       __syncwarp();
@@ -915,6 +966,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
     }
   }
 }
+
+#undef M3_FIELD64
 
 template <bool INT_OPT, int MODE>
 static cudaError_t launch_one(const DecodeParams &p, cudaStream_t stream) {

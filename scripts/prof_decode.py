@@ -9,7 +9,7 @@ P = 1440
 codec = BatchCodec(0, True)
 ts, vals, start = synth.gaussian_walk(S, P, "cuda", seed=1)
 enc = codec.encode(ts, vals, start, unit=1)
-packed, offsets = codec.compact(enc, align=16)
+packed, offsets = codec.compact(enc, align=64)
 dec = codec.decode(packed, offsets, P)
 for _ in range(2):
     codec.decode(packed, offsets, P, out=dec)

@@ -1,3 +1,4 @@
+import os
 """Rough first timing of the kernels (not the bench contract; see bench.py)."""
 import sys, os, time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -21,7 +22,7 @@ for int_opt in (True, False):
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
     t_enc = timeit(lambda: codec.encode(ts, vals, start, unit=1, out=enc))
-    packed, offsets = codec.compact(enc, align=16)
+    packed, offsets = codec.compact(enc, align=int(os.environ.get('M3_ALIGN', '64')))
     total = int(offsets[-1].item())
     dec = codec.decode(packed, offsets, P)
     t_dec = timeit(lambda: codec.decode(packed, offsets, P, out=dec))
