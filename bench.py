@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline step only (no downsample / merge / fixtures / all-gather side measurements)")
     return ap.parse_args()
 
 
@@ -191,6 +193,34 @@ def cpu_oracle_throughput(n_series, n_points, int_opt, budget_s, steps=1, warmup
     return dp / (tot_e + tot_d), info
 
 
+def fixture_set_throughput(codec, dev, time_fn, n_streams=200_000):
+    """Secondary realistic set: the reference's ten int-optimised production
+    fixtures (m3tsz/encoder_benchmark_test.go:36-47; millisecond unit, time-unit markers, int
+    mode, repeats), tiled to n_streams streams with 64-byte aligned starts and decoded in one
+    launch.  The zero padding after each stream's end-of-stream marker is never parsed."""
+    import base64
+    import torch
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden",
+                                    "m3tsz_goldens.json")))
+    raw = [base64.b64decode(x) for x in g["fixtures_b64"]["streams"]]
+    pts = g["fixtures_b64"]["expected_points"]
+    padded = [r + b"\0" * ((-len(r)) % 64) for r in raw]
+    reps = max(1, n_streams // len(raw))
+    lens = torch.tensor([len(x) for x in padded] * reps, dtype=torch.int64)
+    off = torch.zeros(len(lens) + 1, dtype=torch.int64)
+    off[1:] = lens.cumsum(0)
+    d_blob = torch.frombuffer(bytearray(b"".join(padded) * reps), dtype=torch.uint8).to(dev)
+    d_off = off.to(dev)
+    dec = codec.decode(d_blob, d_off, max(pts) + 8)
+    n = dec.n_points.cpu()
+    assert bool((dec.status.cpu() == 0).all()) and n[: len(pts)].tolist() == pts, "fixture decode mismatch"
+    total_dp = int(n.sum())
+    ms = time_fn(lambda: codec.decode(d_blob, d_off, max(pts) + 8, out=dec), n=3)
+    return {"streams": int(len(lens)), "datapoints": total_dp,
+            "compressed_bytes_per_dp": sum(len(x) for x in raw) / float(sum(pts)),
+            "decode_ms": ms, "decode_dps": total_dp / (ms * 1e-3)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -329,28 +359,32 @@ def run_ours(args):
         return a.elapsed_time(b) / n
 
     enc_ms = time_fn(lambda: codec.encode(ts, vals, start, unit=1, out=enc))
-    ds = codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC, (P * 60 + 299) // 300)
-    ds_ms = time_fn(lambda: codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC,
-                                                    (P * 60 + 299) // 300, out=ds))
-    n_win = ds.sum.shape[0]
-    del ds
+    extras = not args.no_extras
+    ds_ms, n_win, merge_ms, Sm, fixtures = None, 0, None, 0, None
+    if extras:
+        fixtures = fixture_set_throughput(codec, dev, time_fn)
+        ds = codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC, (P * 60 + 299) // 300)
+        ds_ms = time_fn(lambda: codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC,
+                                                        (P * 60 + 299) // 300, out=ds))
+        n_win = ds.sum.shape[0]
+        del ds
 
-    # series merge (row N1): RF=3 fetch shape -- every 3 consecutive decoded streams are the
-    # replicas of one series (same timestamps => 3 inputs collapse to 1 output per timestamp)
-    Sm = (min(S, 300_000) // 3) * 3
-    m_slice = torch.arange(Sm + 1, dtype=torch.int64, device=dev)
-    m_rep = torch.arange(Sm + 1, dtype=torch.int64, device=dev)
-    m_ser = torch.arange(0, Sm + 1, 3, dtype=torch.int64, device=dev)
-    mg = lambda: codec.merge_series(dec.ts[:Sm], dec.values[:Sm], dec.n_points[:Sm], dec.status[:Sm], m_slice,
-                                    m_rep, m_ser, P)
-    m_out = mg()
-    assert int((m_out[3] != 0).sum()) == 0 and bool((m_out[2] == P).all())
-    del m_out
-    merge_ms = time_fn(mg, n=3)
+        # series merge (row N1): RF=3 fetch shape -- every 3 consecutive decoded streams are the
+        # replicas of one series (same timestamps => 3 inputs collapse to 1 output per timestamp)
+        Sm = (min(S, 300_000) // 3) * 3
+        m_slice = torch.arange(Sm + 1, dtype=torch.int64, device=dev)
+        m_rep = torch.arange(Sm + 1, dtype=torch.int64, device=dev)
+        m_ser = torch.arange(0, Sm + 1, 3, dtype=torch.int64, device=dev)
+        mg = lambda: codec.merge_series(dec.ts[:Sm], dec.values[:Sm], dec.n_points[:Sm], dec.status[:Sm], m_slice,
+                                        m_rep, m_ser, P)
+        m_out = mg()
+        assert int((m_out[3] != 0).sum()) == 0 and bool((m_out[2] == P).all())
+        del m_out
+        merge_ms = time_fn(mg, n=3)
 
     # ---- fetch-side all-gather (only when a query spans shards) ----
     allgather = None
-    if world > 1:
+    if world > 1 and extras:
         from m3_b200.sharded import all_gather_blocks
         sub = min(S, max(1, (8 << 30) // (world * P * 16)))  # bound the gathered block to ~8 GiB
         blk_t, blk_v = dec.ts[:sub].contiguous(), dec.values[:sub].contiguous()
@@ -460,12 +494,15 @@ def run_ours(args):
                          % (S * P * 16 / 1e9, (compressed_bytes + S * P * 16) / 1e9),
                    "parallelism": "series sharded per GPU, no data-path collective"},
         "encode_dps": S * P / (enc_ms * 1e-3), "decode_dps": S * P / (dec_ms_max * 1e-3),
-        "decode_downsample_dps": S * P / (ds_ms * 1e-3),
+        "decode_downsample_dps": (S * P / (ds_ms * 1e-3)) if extras else None,
         "decode_downsample": {"windows": n_win, "ms": ds_ms,
-                              "algorithmic_gbs": (compressed_bytes + n_win * S * 32) / (ds_ms * 1e-3) / 1e9},
+                              "algorithmic_gbs": (compressed_bytes + n_win * S * 32) / (ds_ms * 1e-3) / 1e9}
+        if extras else None,
         "series_merge": {"replicas": 3, "series": Sm // 3, "ms": merge_ms,
                          "input_dps": Sm * P / (merge_ms * 1e-3),
-                         "algorithmic_gbs": (Sm * P * 16 + (Sm // 3) * P * 16) / (merge_ms * 1e-3) / 1e9},
+                         "algorithmic_gbs": (Sm * P * 16 + (Sm // 3) * P * 16) / (merge_ms * 1e-3) / 1e9}
+        if extras else None,
+        "fixture_set": fixtures,
         "encode_ms": enc_ms, "decode_ms": dec_ms_max,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks, "fetch_allgather": allgather,

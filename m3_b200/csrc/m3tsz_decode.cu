@@ -41,6 +41,9 @@ namespace m3tsz {
 #ifndef M3_OPT_G
 #define M3_OPT_G 1  // per-group (M3_DEC_CHK datapoints) pre-check of the hot path's slow-changing conditions
 #endif
+#ifndef M3_OPT_W3
+#define M3_OPT_W3 1  // load the window's 4th word only on lanes that can need it
+#endif
 #ifndef M3_OPT_X
 #define M3_OPT_X 1  // two-stage funnel extraction of the payload field
 #endif
@@ -633,14 +636,23 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
       bool emitted = false;
       // ---------------- parse 4 ring words ----------------
       const uint32_t *tp = ring_lane + (cw & (DEC_RING - 1)) * DEC_STRIDE;
-      const uint32_t w0 = __byte_perm(tp[0], 0, 0x0123), w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123),
-                     w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123),
-                     w3 = __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123);
       const uint32_t sh = s.pos & 31u;
+      // the 4th word only matters when the code can reach past bit 96 of the window: the
+      // hot path's codes are <= 80 bits, so only lanes with sh > 16 load it here (fewer
+      // active lanes = fewer bank conflicts); the general path reloads it when it needs it
+#if M3_OPT_W3
+      const bool need_w3 = sh > 16u;
+#else
+      const bool need_w3 = true;
+#endif
+      const uint32_t w0 = __byte_perm(tp[0], 0, 0x0123), w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123),
+                     w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123);
+      uint32_t w3 = need_w3 ? __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123) : 0u;
       const uint32_t h = __funnelshift_l(w1, w0, sh);
 #if M3_OPT_X
       // 96-bit window at the bit position: (h, h1, h2); a field at offset c <= 32 is two more funnels
-      const uint32_t h1 = __funnelshift_l(w2, w1, sh), h2 = __funnelshift_l(w3, w2, sh);
+      const uint32_t h1 = __funnelshift_l(w2, w1, sh);
+      uint32_t h2 = __funnelshift_l(w3, w2, sh);
 #define M3_FIELD64(c_) \
   (((uint64_t)__funnelshift_lc(h1, h, (c_)) << 32) | (uint64_t)__funnelshift_lc(h2, h1, (c_)))
 #else
@@ -711,6 +723,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
 #if M3_OPT_G
         pre_ok = false;  // the group's pre-check does not survive a general-path datapoint
 #endif
+        if (!need_w3) {  // general codes are up to 95 bits
+          w3 = __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123);
+#if M3_OPT_X
+          h2 = __funnelshift_l(w3, w2, sh);
+#endif
+        }
         bool ok = fast_en && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
         uint32_t c = 1;  // bits consumed before the payload
         int64_t dod = 0;
@@ -972,7 +990,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
 template <bool INT_OPT, int MODE>
 static cudaError_t launch_one(const DecodeParams &p, cudaStream_t stream) {
   constexpr size_t warp_smem = (MODE == 0) ? DEC_WARP_SMEM_PLAIN : DEC_WARP_SMEM_DS;
+#ifdef M3_DEC_PAD_SMEM
+  constexpr size_t smem = warp_smem * DEC_WARPS + M3_DEC_PAD_SMEM;  // diagnostic: caps resident blocks
+#else
   constexpr size_t smem = warp_smem * DEC_WARPS;
+#endif
   cudaError_t e = cudaFuncSetAttribute(decode_kernel<INT_OPT, MODE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

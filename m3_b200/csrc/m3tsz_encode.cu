@@ -86,11 +86,18 @@ __device__ __forceinline__ void emit_code_p(EncLane &s, uint32_t *tile, int lane
   const uint32_t m3 = __funnelshift_rc(0u, c2, s.sh);
   const uint32_t tot = s.sh + (uint32_t)(hb + plen);
   const uint32_t full = tot >> 5;
-  uint32_t *tp = tile + s.k * ENC_STRIDE + lane;
-  if (full > 0) tp[0] = m0;
-  if (full > 1) tp[ENC_STRIDE] = m1;
-  if (full > 2) tp[2 * ENC_STRIDE] = m2;
-  s.carry = full == 0 ? m0 : (full == 1 ? m1 : (full == 2 ? m2 : m3));
+  // predicated stores (kept out of the compiler's hands: it turns the chain into a
+  // divergent branch region otherwise)
+  const uint32_t ta = (uint32_t)__cvta_generic_to_shared(tile + s.k * ENC_STRIDE + lane);
+  asm volatile(
+      "{\n\t.reg .pred p0, p1, p2;\n\t"
+      "setp.gt.u32 p0, %0, 0;\n\tsetp.gt.u32 p1, %0, 1;\n\tsetp.gt.u32 p2, %0, 2;\n\t"
+      "@p0 st.shared.u32 [%1], %2;\n\t@p1 st.shared.u32 [%1+132], %3;\n\t@p2 st.shared.u32 [%1+264], %4;\n\t}"
+      ::"r"(full), "r"(ta), "r"(m0), "r"(m1), "r"(m2)
+      : "memory");
+  static_assert(ENC_STRIDE * 4 == 132, "store offsets above");
+  const uint32_t c01 = full == 0 ? m0 : m1, c23 = full == 2 ? m2 : m3;
+  s.carry = full < 2 ? c01 : c23;
   s.k += full;
   s.sh = tot & 31u;
 }
@@ -710,6 +717,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) encode_kernel(const EncodeP
   asm volatile("cp.async.commit_group;\n" ::: "memory");
 
   uint32_t iter = 0;
+  int64_t t_pf = 0;
+  uint64_t fb_pf = 0;
   for (;;) {
     const bool active = valid && s.err == 0 && iter < n_pts;
     if (!__any_sync(FULL_MASK, active)) break;
@@ -786,9 +795,20 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, 4) encode_kernel(const EncodeP
 
     // ---- encode one datapoint ----
     {
+      // rows 1..7 of a tile were fetched from shared memory at the end of the previous
+      // datapoint (the load latency hides behind its bit packing); row 0 follows the
+      // tile's cp.async wait
       const int row = (int)(iter & (ENC_IN_T - 1));
-      const int64_t t = (int64_t)ts_tile[row * ENC_STRIDE + lane];
-      const uint64_t fb = val_tile[row * ENC_STRIDE + lane];
+      if (row == 0) {
+        t_pf = (int64_t)ts_tile[lane];
+        fb_pf = val_tile[lane];
+      }
+      const int64_t t = t_pf;
+      const uint64_t fb = fb_pf;
+      if (row + 1 < ENC_IN_T) {
+        t_pf = (int64_t)ts_tile[(row + 1) * ENC_STRIDE + lane];
+        fb_pf = val_tile[(row + 1) * ENC_STRIDE + lane];
+      }
       const double v = __longlong_as_double((long long)fb);
       const bool room = (uint64_t)s.words_out + s.k + ENC_GUARD + 4 <= slot_words;
       // hot candidate: same (valid s/ms/us/ns) unit, zero delta-of-delta, not the

@@ -10,7 +10,9 @@
 //
 // Mapping: one THREAD per series; the per-series state machine is small and
 // sequential, the decoded inputs are read through L1 (each thread walks its own
-// arrays front to back, 16 consecutive elements per 128-byte line).
+// arrays front to back).  Two kernels: a register-resident fast path for the
+// shape a fetch normally has, and the general restatement for everything else
+// (run only on the series the fast path gave up on).
 #include "m3tsz_common.cuh"
 #include "m3tsz_kernels.h"
 
@@ -289,9 +291,179 @@ struct ReplicaSet {  // member set of the series iterator: its replicas
   __device__ int err(int id) { return reps[id].err; }
 };
 
-__global__ void __launch_bounds__(128) merge_kernel(const MergeParams p) {
+// ---------------------------------------------------------------------------
+// Fast path: the shape a fetch normally has.  <= MRG_FAST_R replicas per series,
+// every slice holds at most one reader, every reader decoded without error, the
+// default (last pushed) equal-timestamp strategy, and every replica's
+// concatenated blocks are STRICTLY increasing in time.  Under those conditions
+// the three nested iterators reduce to a k-way merge of increasing sequences
+// whose value on a tie comes from the member that sits last in `values`
+// (iterators.go:60-74 with the swap-removal order of :178-196) -- restated here
+// with the whole state in registers.  Anything else (several readers in a slice,
+// a decode error, a duplicate or out-of-order timestamp, another strategy) makes
+// the thread give up and mark the series for the general kernel, which restarts
+// it from scratch.
+// ---------------------------------------------------------------------------
+constexpr int MRG_FAST_R = 4;  // replicas per series the fast kernel is instantiated for
+constexpr int32_t MRG_REDO = -1;  // status marker: "run the general kernel on this series"
+
+template <int R>
+struct FastState {
+  uint64_t slice_cur[R], slice_end[R], base[R];
+  int32_t idx[R], n[R];
+  int64_t t[R];
+  bool bail;
+};
+
+// moves replica r to its next datapoint inside [f.start, f.end) (when the filter
+// is on); false = exhausted (or past the end of the range: same thing to the caller)
+template <int R>
+__device__ __forceinline__ bool fast_advance(FastState<R> &st, const MergeParams &p, const Filter &f, int r,
+                                             bool have_prev) {
+  for (;;) {
+    bool got = false;
+    int64_t tn = 0;
+    if (st.idx[r] + 1 < st.n[r]) {
+      st.idx[r]++;
+      tn = p.ts[st.base[r] + (uint64_t)st.idx[r]];
+      got = true;
+    } else {
+      while (st.slice_cur[r] < st.slice_end[r]) {
+        const uint64_t k = st.slice_cur[r]++;
+        const uint64_t q0 = p.slice_off[k], q1 = p.slice_off[k + 1];
+        if (q1 == q0) continue;
+        if (q1 - q0 > 1 || (p.seq_status && p.seq_status[q0] != 0)) {
+          st.bail = true;
+          return false;
+        }
+        const uint32_t np = p.n_points[q0];
+        const int32_t n = (int32_t)(np < p.cap ? np : p.cap);
+        if (n == 0) continue;
+        st.base[r] = q0 * p.cap;
+        st.idx[r] = 0;
+        st.n[r] = n;
+        tn = p.ts[st.base[r]];
+        got = true;
+        break;
+      }
+    }
+    if (!got) return false;
+    if (have_prev && tn <= st.t[r]) {  // duplicate / out of order: the general path decides
+      st.bail = true;
+      return false;
+    }
+    st.t[r] = tn;
+    have_prev = true;
+    if (f.on) {
+      if (tn < f.start) continue;
+      if (tn >= f.end) return false;
+    }
+    return true;
+  }
+}
+
+template <int R>
+__device__ void merge_fast(const MergeParams &p, uint64_t s, uint64_t rep0) {
+  FastState<R> st;
+  st.bail = false;
+  Filter f;
+  f.on = (p.start != 0 && p.end != 0);
+  f.start = p.start;
+  f.end = p.end;
+  uint32_t order = 0;  // `values`: member ids by position, 4 bits each
+  int nv = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    st.slice_cur[r] = p.replica_off[rep0 + r];
+    st.slice_end[r] = p.replica_off[rep0 + r + 1];
+    st.base[r] = 0;
+    st.idx[r] = 0;
+    st.n[r] = 0;
+    st.t[r] = 0;
+    if (fast_advance<R>(st, p, f, r, false)) {
+      order |= (uint32_t)r << (4 * nv);
+      nv++;
+    }
+  }
+  int64_t *ts_out = p.ts_out + s * p.out_cap;
+  double *val_out = p.val_out + s * p.out_cap;
+  uint32_t n_out = 0;
+  while (nv > 0 && !st.bail) {
+    // earliest timestamp and its members in position order; the value of the last one
+    int64_t tmin = kTimeMax;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      bool in = false;
+      for (int q = 0; q < nv; q++) in = in || (((order >> (4 * q)) & 15u) == (uint32_t)r);
+      if (in && st.t[r] < tmin) tmin = st.t[r];
+    }
+    uint32_t e_ids = 0;
+    int ne = 0;
+    uint64_t win_addr = 0;
+    for (int q = 0; q < nv; q++) {
+      const uint32_t id = (order >> (4 * q)) & 15u;
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if ((uint32_t)r == id && st.t[r] == tmin) {
+          e_ids |= id << (4 * ne);
+          ne++;
+          win_addr = st.base[r] + (uint64_t)st.idx[r];
+        }
+      }
+    }
+    if (n_out < p.out_cap) {
+      ts_out[n_out] = tmin;
+      val_out[n_out] = p.val[win_addr];
+    }
+    n_out++;
+    // advance the earliest members in list order; an exhausted member's place in
+    // `values` is taken by the tail (iterators.go:188-192)
+    for (int k = 0; k < ne; k++) {
+      const uint32_t id = (e_ids >> (4 * k)) & 15u;
+      bool alive = true;
+#pragma unroll
+      for (int r = 0; r < R; r++)
+        if ((uint32_t)r == id) alive = fast_advance<R>(st, p, f, r, true);
+      if (st.bail) break;
+      if (!alive) {
+        int at = 0;
+        for (int q = 0; q < nv; q++)
+          if (((order >> (4 * q)) & 15u) == id) {
+            at = q;
+            break;
+          }
+        const uint32_t last = (order >> (4 * (nv - 1))) & 15u;
+        order = (order & ~(15u << (4 * at))) | (last << (4 * at));
+        nv--;
+      }
+    }
+  }
+  if (st.bail) {
+    p.status[s] = MRG_REDO;
+    return;
+  }
+  p.n_out[s] = n_out;
+  p.status[s] = n_out > p.out_cap ? M3TSZ_ERR_CAPACITY : 0;
+}
+
+__global__ void __launch_bounds__(128) merge_fast_kernel(const MergeParams p) {
   const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= p.n_series) return;
+  const uint64_t rep0 = p.series_off[s], rep1 = p.series_off[s + 1];
+  switch (rep1 - rep0) {
+    case 1: merge_fast<1>(p, s, rep0); break;
+    case 2: merge_fast<2>(p, s, rep0); break;
+    case 3: merge_fast<3>(p, s, rep0); break;
+    case 4: merge_fast<4>(p, s, rep0); break;
+    default: static_assert(MRG_FAST_R == 4, "one case per replica count"); p.status[s] = MRG_REDO; break;
+  }
+}
+
+// general kernel; redo_only: handle only the series the fast kernel gave up on
+__global__ void __launch_bounds__(128) merge_kernel(const MergeParams p, bool redo_only) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= p.n_series) return;
+  if (redo_only && p.status[s] != MRG_REDO) return;
   const uint64_t rep0 = p.series_off[s], rep1 = p.series_off[s + 1];
   int err = 0;
   uint32_t n_out = 0;
@@ -360,7 +532,9 @@ cudaError_t launch_merge(const MergeParams &p, cudaStream_t stream) {
   const unsigned tb = 128;
   const uint64_t blocks = (p.n_series + tb - 1) / tb;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
-  merge_kernel<<<(unsigned)blocks, tb, 0, stream>>>(p);
+  const bool fast = (p.strategy == 0);
+  if (fast) merge_fast_kernel<<<(unsigned)blocks, tb, 0, stream>>>(p);
+  merge_kernel<<<(unsigned)blocks, tb, 0, stream>>>(p, fast);
   return cudaGetLastError();
 }
 
