@@ -120,6 +120,10 @@ typedef struct m3tsz_annotation_ref {
  * d_status  : per-series iterator Err() (M3TSZ_OK on a clean end-of-stream).
  * d_unit    : optional [n_series], time unit in force at the last datapoint.
  * d_ann     : optional [n_series], first annotation reference.
+ * Limits (M3TSZ_ERR_INVALID_ARG beyond): streams_bytes < 2^34, max_points < 2^27,
+ * one stream < 2^28 bytes (M3TSZ_ERR_STREAM_TOO_LARGE for that series); split
+ * larger batches.  Stream starts may have any alignment; 64-byte aligned starts
+ * (m3tsz_compact_streams with align = 64) decode fastest.
  * ---------------------------------------------------------------------- */
 int m3tsz_decode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *d_streams,
                        uint64_t streams_bytes, const uint64_t *d_offsets, uint64_t n_series,

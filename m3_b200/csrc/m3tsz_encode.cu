@@ -24,7 +24,13 @@ namespace m3tsz {
 constexpr int ENC_WARPS = 4;
 constexpr int ENC_STRIDE = 33;
 constexpr int ENC_IN_T = 8;     // datapoints per input tile (double buffered, cp.async)
-constexpr int ENC_OUT_W = 40;   // output tile words per lane
+#ifndef M3_ENC_OUT_W
+#define M3_ENC_OUT_W 40
+#endif
+#ifndef M3_ENC_MIN_BLOCKS
+#define M3_ENC_MIN_BLOCKS 4
+#endif
+constexpr int ENC_OUT_W = M3_ENC_OUT_W;   // output tile words per lane
 constexpr int ENC_GUARD = 10;   // words a single datapoint (no annotation) may add
 constexpr int ENC_IN_TILE_DWORDS = ENC_IN_T * ENC_STRIDE;   // one array (ts or val), one buffer
 constexpr int ENC_OUT_TILE_WORDS = ENC_OUT_W * ENC_STRIDE;
@@ -585,7 +591,7 @@ __device__ __forceinline__ void enc_cp_async8(uint32_t dst, const void *src) {
 }
 
 template <bool INT_OPT>
-__global__ void __launch_bounds__(ENC_WARPS * 32, 4) encode_kernel(const EncodeParams p) {
+__global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kernel(const EncodeParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
