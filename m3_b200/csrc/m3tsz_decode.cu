@@ -41,6 +41,9 @@ namespace m3tsz {
 #ifndef M3_OPT_G
 #define M3_OPT_G 1  // per-group (M3_DEC_CHK datapoints) pre-check of the hot path's slow-changing conditions
 #endif
+#ifndef M3_DEC_QUAD
+#define M3_DEC_QUAD 0  // 1: ring of 16-byte quads ([quad][lane]), lane-local 16-byte cp.async, LDS.128 reads
+#endif
 #ifndef M3_OPT_W3
 #define M3_OPT_W3 1  // load the window's 4th word only on lanes that can need it
 #endif
@@ -61,7 +64,12 @@ constexpr int DEC_OUT_T = M3_DEC_OUT_T;
 constexpr int DEC_UNROLL = M3_DEC_UNROLL;
 constexpr int DEC_FAST_WORDS = 4; // the fast path reads 4 consecutive words
 
+#if M3_DEC_QUAD
+constexpr int DEC_QUADS = DEC_RING / 4;  // + 1 mirror quad (copy of quad 0) so quad q+1 is always at +1
+constexpr int DEC_IN_TILE_WORDS = (DEC_QUADS + 1) * 32 * 4;
+#else
 constexpr int DEC_IN_TILE_WORDS = (DEC_RING + DEC_MIRROR + 1) * DEC_STRIDE;  // u32 (+1 row pad: 8B align)
+#endif
 constexpr int DEC_OUT_TILE_DWORDS = DEC_OUT_T * DEC_STRIDE;                  // u64
 constexpr size_t DEC_WARP_SMEM_PLAIN =
     (size_t)DEC_IN_TILE_WORDS * 4 + 2 * (size_t)DEC_OUT_TILE_DWORDS * 8;
@@ -106,10 +114,18 @@ __device__ __forceinline__ uint64_t gpeek64(const SlowSrc &src, uint64_t wbase, 
   const uint32_t wr = pos >> 5;
   uint32_t w0, w1, w2;
   if (wr + 3u <= src.ring_safe) {
+#if M3_DEC_QUAD
+    // ring_lane = ring + lane * 4 (words); word w lives at quad (w >> 2) & 15, element w & 3
+    const uint32_t a0 = wr, a1 = wr + 1, a2 = wr + 2;
+    w0 = __byte_perm(src.ring_lane[((a0 >> 2) & (DEC_QUADS - 1)) * 128 + (a0 & 3)], 0, 0x0123);
+    w1 = __byte_perm(src.ring_lane[((a1 >> 2) & (DEC_QUADS - 1)) * 128 + (a1 & 3)], 0, 0x0123);
+    w2 = __byte_perm(src.ring_lane[((a2 >> 2) & (DEC_QUADS - 1)) * 128 + (a2 & 3)], 0, 0x0123);
+#else
     const uint32_t *tp = src.ring_lane + (wr & (DEC_RING - 1)) * DEC_STRIDE;
     w0 = __byte_perm(tp[0], 0, 0x0123);
     w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123);
     w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123);
+#endif
   } else {
     const uint64_t w = wbase + wr;
     w0 = load_be32(src.base, src.nbytes, w);
@@ -469,6 +485,31 @@ __device__ __forceinline__ void ring_fill(uint32_t *ring, const uint8_t *streams
   }
 }
 
+#if M3_DEC_QUAD
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+// Lane-local refill: the lane copies the 64-byte chunk at global word index gw
+// (a multiple of 16) of ITS OWN stream into quads slot_q0..slot_q0+3 of its own
+// column with four 16-byte cp.async (a warp instruction writes 32 x 16 B =
+// 4 conflict-free wavefronts; no shuffles).  Quad 0 is mirrored to quad 16.
+__device__ __forceinline__ void ring_fill_quad(uint32_t ring_lane_addr, const uint8_t *streams, uint64_t nbytes,
+                                               bool take, uint32_t gw, uint32_t slot_q0) {
+  if (take) {
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+      const uint64_t b = ((uint64_t)gw + 4u * k) * 4ull;
+      const uint32_t nb = (b + 16 <= nbytes) ? 16u : (b < nbytes ? (uint32_t)(nbytes - b) : 0u);
+      const uint8_t *src = nb ? (streams + b) : streams;
+      const uint32_t dst = ring_lane_addr + (slot_q0 + k) * 512u;
+      cp_async16(dst, src, nb);
+      if (k == 0 && slot_q0 == 0) cp_async16(ring_lane_addr + DEC_QUADS * 512u, src, nb);
+    }
+  }
+}
+#endif
+
 struct DsAcc {  // fused-downsample per-lane accumulator (aggregation.Gauge, gauge.go:31-106)
   int64_t cur_w, hi_w, w_start;
   double sum, mn, mx;
@@ -485,7 +526,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
   uint32_t *ring = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem) + warp * warp_smem);
   uint64_t *ts_tile = reinterpret_cast<uint64_t *>(ring + DEC_IN_TILE_WORDS);
   uint64_t *val_tile = ts_tile + DEC_OUT_TILE_DWORDS;
+#if M3_DEC_QUAD
+  const uint32_t *ring_lane = ring + lane * 4;  // this lane's 16-byte cell of quad 0
+  const uint32_t ring_lane_addr = smem_addr(ring_lane);
+#else
   const uint32_t *ring_lane = ring + lane;  // this lane's ring column
+#endif
   uint64_t *ts_lane = ts_tile + lane;       // this lane's output tile columns (values: + DEC_OUT_TILE_DWORDS)
 
   const uint64_t warp_s0 = ((uint64_t)blockIdx.x * DEC_WARPS + warp) * 32ull;
@@ -598,7 +644,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           const uint32_t fmask =
               __ballot_sync(FULL_MASK, active && avail <= (rep == 0 ? DEC_ACCEPT : DEC_TRIGGER));
           if (!fmask) break;
+#if M3_DEC_QUAD
+          ring_fill_quad(ring_lane_addr, p.streams, p.streams_bytes, (fmask >> lane) & 1u, gbase + filled,
+                         (filled >> 2) & (DEC_QUADS - 1));
+#else
           ring_fill(ring, p.streams, p.streams_bytes, fmask, gbase + filled, filled & (DEC_RING - 1), lane);
+#endif
           if ((fmask >> lane) & 1u) {
             filled += DEC_FILL;
             avail += DEC_FILL;
@@ -635,7 +686,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
       uint64_t v = 0;
       bool emitted = false;
       // ---------------- parse 4 ring words ----------------
+#if !M3_DEC_QUAD
       const uint32_t *tp = ring_lane + (cw & (DEC_RING - 1)) * DEC_STRIDE;
+#endif
       const uint32_t sh = s.pos & 31u;
       // the 4th word only matters when the code can reach past bit 96 of the window: the
       // hot path's codes are <= 80 bits, so only lanes with sh > 16 load it here (fewer
@@ -645,9 +698,24 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
 #else
       const bool need_w3 = true;
 #endif
+#if M3_DEC_QUAD
+      // two aligned quads (8 words) hold the window; pick words j..j+3 (j = cw & 3): the
+      // j & 2 level with selects on the raw words, the j & 1 level fused with the byte swap
+      (void)need_w3;
+      const uint4 *qp = reinterpret_cast<const uint4 *>(ring_lane) + ((cw >> 2) & (DEC_QUADS - 1)) * 32;
+      const uint4 qa = qp[0], qb = qp[32];
+      const bool j2 = (cw & 2u) != 0;
+      const uint32_t u0 = j2 ? qa.z : qa.x, u1 = j2 ? qa.w : qa.y, u2 = j2 ? qb.x : qa.z,
+                     u3 = j2 ? qb.y : qa.w, u4 = j2 ? qb.z : qb.x;
+      const uint32_t psel = 0x0123u + (cw & 1u) * 0x4444u;  // 0x0123: swap(a), 0x4567: swap(b)
+      const uint32_t w0 = __byte_perm(u0, u1, psel), w1 = __byte_perm(u1, u2, psel),
+                     w2 = __byte_perm(u2, u3, psel);
+      uint32_t w3 = __byte_perm(u3, u4, psel);
+#else
       const uint32_t w0 = __byte_perm(tp[0], 0, 0x0123), w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123),
                      w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123);
       uint32_t w3 = need_w3 ? __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123) : 0u;
+#endif
       const uint32_t h = __funnelshift_l(w1, w0, sh);
 #if M3_OPT_X
       // 96-bit window at the bit position: (h, h1, h2); a field at offset c <= 32 is two more funnels
@@ -723,12 +791,14 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
 #if M3_OPT_G
         pre_ok = false;  // the group's pre-check does not survive a general-path datapoint
 #endif
+#if !M3_DEC_QUAD
         if (!need_w3) {  // general codes are up to 95 bits
           w3 = __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123);
 #if M3_OPT_X
           h2 = __funnelshift_l(w3, w2, sh);
 #endif
         }
+#endif
         bool ok = fast_en && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
         uint32_t c = 1;  // bits consumed before the payload
         int64_t dod = 0;
