@@ -67,6 +67,7 @@ enum {
   M3TSZ_ERR_UNEXPECTED_EOF = 12,   /* io.ErrUnexpectedEOF */
   M3TSZ_ERR_OUT_OF_ORDER = 13,     /* errOutOfOrderIterator, encoding/iterators.go:229-236 */
   M3TSZ_ERR_TOO_MANY_ITERATORS = 14, /* > 8 replicas per series or readers per block slice */
+  M3TSZ_ERR_CHECKSUM_MISMATCH = 15, /* errSeekChecksumMismatch, persist/fs/seek.go:50-51, read.go:395-397 */
   /* library-level conditions */
   M3TSZ_ERR_CAPACITY = 100,        /* more datapoints / bytes than the caller's buffer holds */
   M3TSZ_ERR_INVALID_ARG = 101,
@@ -231,6 +232,25 @@ int m3tsz_decode_downsample_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts
                                        uint32_t n_windows, double *h_sum, int64_t *h_count,
                                        double *h_min, double *h_max, uint32_t *h_n_points,
                                        int32_t *h_status);
+
+/* ------------------------------------------------------------------------
+ * Segment checksums (fileset ingestion).  The fileset data file
+ * is the concatenated streams and every index entry carries (Offset, Size,
+ * DataChecksum) (src/dbnode/persist/schema/types.go:70-78) -- i.e. this library's
+ * CSR layout plus the Adler-32 that the reference verifies on every read:
+ *   ts.Segment.CalculateChecksum  src/dbnode/ts/segment.go:60-76  (head then tail)
+ *   digest.Checksum               src/dbnode/digest/digest.go:36-38
+ *   check                         src/dbnode/persist/fs/read.go:395-397, seek.go:370-373
+ * Computes the Adler-32 of every stream [d_offsets[s], d_offsets[s+1]) -- or
+ * [d_offsets[s], d_offsets[s] + d_lengths[s]) when d_lengths is given (padded
+ * starts) -- into d_checksums (optional) and, when d_expected (the index entries'
+ * DataChecksum) is given, sets d_status[s] to M3TSZ_ERR_CHECKSUM_MISMATCH where
+ * it differs.  One of d_checksums / d_status is required.
+ * ---------------------------------------------------------------------- */
+int m3tsz_checksum_batch(m3tsz_ctx *ctx, const uint8_t *d_streams, uint64_t streams_bytes,
+                         const uint64_t *d_offsets, const uint64_t *d_lengths, uint64_t n_series,
+                         const uint32_t *d_expected, uint32_t *d_checksums, int32_t *d_status,
+                         void *stream);
 
 /* ------------------------------------------------------------------------
  * Series merge: the iterator layer directly above the codec.

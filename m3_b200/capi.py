@@ -53,7 +53,7 @@ EXPORTED_SYMBOLS = [
     "m3tsz_last_cuda_error", "m3tsz_ctx_launch_count", "m3tsz_decode_batch",
     "m3tsz_decode_batch_host", "m3tsz_encode_batch", "m3tsz_encode_bound",
     "m3tsz_compact_streams", "m3tsz_encode_batch_host", "m3tsz_decode_downsample_batch",
-    "m3tsz_decode_downsample_batch_host", "m3tsz_merge_series_batch",
+    "m3tsz_decode_downsample_batch_host", "m3tsz_merge_series_batch", "m3tsz_checksum_batch",
 ]
 
 
@@ -104,6 +104,8 @@ def lib():
     L.m3tsz_merge_series_batch.restype = C.c_int
     L.m3tsz_merge_series_batch.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp, u64, i64, i64, i32, vp, vp,
                                            u64, vp, vp, vp]
+    L.m3tsz_checksum_batch.restype = C.c_int
+    L.m3tsz_checksum_batch.argtypes = [vp, vp, u64, vp, vp, u64, vp, vp, vp, vp]
     _lib = L
     return L
 

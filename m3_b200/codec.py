@@ -174,6 +174,23 @@ class BatchCodec:
         self.ctx.check(rc, "m3tsz_merge_series_batch")
         return ts_out, val_out, n_out, status
 
+    def segment_checksums(self, streams, offsets, lengths=None, expected=None):
+        """Adler-32 of every stream (ts.Segment.CalculateChecksum, src/dbnode/ts/segment.go:60-76)
+        over the decoder's CSR layout; `lengths` (int64 [S]) gives exact sizes when the starts are
+        padded; `expected` (int32/uint32 [S], the index entries' DataChecksum) turns differences
+        into status M3TSZ_ERR_CHECKSUM_MISMATCH.  Returns (checksums int32-viewed-as-uint32 [S],
+        status int32 [S])."""
+        S = offsets.numel() - 1
+        dev = self.device
+        out = torch.empty(S, dtype=torch.int32, device=dev)
+        status = torch.empty(S, dtype=torch.int32, device=dev)
+        rc = capi.lib().m3tsz_checksum_batch(
+            self.ctx.handle, _ptr(streams), streams.numel(), _ptr(offsets),
+            None if lengths is None else _ptr(lengths), S, None if expected is None else _ptr(expected),
+            _ptr(out), _ptr(status), _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_checksum_batch")
+        return out, status
+
     # ------------------------------------------------------------ host-buffer calls
     def decode_host(self, h_streams, h_offsets, max_points, h_ts, h_values, h_n_points, h_status):
         """All arguments are host tensors (pinned or pageable); copies are inside the call."""

@@ -116,6 +116,7 @@ const char *m3tsz_status_string(int st) {
     case M3TSZ_ERR_UNEXPECTED_EOF: return "unexpected EOF";
     case M3TSZ_ERR_OUT_OF_ORDER: return "values are out of order from inner iterator";
     case M3TSZ_ERR_TOO_MANY_ITERATORS: return "too many replicas / readers for one series";
+    case M3TSZ_ERR_CHECKSUM_MISMATCH: return "checksum does not match expected checksum";
     case M3TSZ_ERR_CAPACITY: return "output capacity exceeded";
     case M3TSZ_ERR_INVALID_ARG: return "invalid argument";
     case M3TSZ_ERR_CUDA: return "CUDA error";
@@ -337,6 +338,30 @@ int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *
   p.n_out = d_n_out;
   p.status = d_status;
   CK(launch_merge(p, (cudaStream_t)stream));
+  ctx->launches++;
+  return M3TSZ_OK;
+}
+
+int m3tsz_checksum_batch(m3tsz_ctx *ctx, const uint8_t *d_streams, uint64_t streams_bytes,
+                         const uint64_t *d_offsets, const uint64_t *d_lengths, uint64_t n_series,
+                         const uint32_t *d_expected, uint32_t *d_checksums, int32_t *d_status,
+                         void *stream) {
+  if (!ctx) return M3TSZ_ERR_INVALID_ARG;
+  if (n_series == 0) return M3TSZ_OK;
+  if (!d_streams || !d_offsets || (!d_checksums && !d_status) || (d_expected && !d_status))
+    return M3TSZ_ERR_INVALID_ARG;
+  CK(cudaSetDevice(ctx->device));
+  ChecksumParams p;
+  memset(&p, 0, sizeof(p));
+  p.streams = d_streams;
+  p.streams_bytes = streams_bytes;
+  p.offsets = d_offsets;
+  p.lengths = d_lengths;
+  p.n_series = n_series;
+  p.expected = d_expected;
+  p.out = d_checksums;
+  p.status = d_status;
+  CK(launch_checksum(p, (cudaStream_t)stream));
   ctx->launches++;
   return M3TSZ_OK;
 }

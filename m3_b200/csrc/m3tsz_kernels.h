@@ -76,6 +76,18 @@ struct MergeParams {
 };
 cudaError_t launch_merge(const MergeParams &p, cudaStream_t stream);
 
+struct ChecksumParams {
+  const uint8_t *streams;
+  uint64_t streams_bytes;
+  const uint64_t *offsets;  // CSR [n_series + 1]
+  const uint64_t *lengths;  // optional [n_series]: exact sizes when the starts are padded
+  uint64_t n_series;
+  const uint32_t *expected;  // optional: index-entry DataChecksum per stream
+  uint32_t *out;             // optional: Adler-32 per stream
+  int32_t *status;           // optional: OK / CHECKSUM_MISMATCH / INVALID_ARG / STREAM_TOO_LARGE
+};
+cudaError_t launch_checksum(const ChecksumParams &p, cudaStream_t stream);
+
 // exclusive scan of aligned lengths + gather into a packed buffer
 cudaError_t launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint64_t *len,
                            uint64_t n_series, uint32_t align, uint8_t *packed,

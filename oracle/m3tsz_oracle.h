@@ -56,7 +56,8 @@ enum {
   M3O_ERR_VARINT_OVERFLOW = 11,  /* encoding/binary errOverflow (Go stdlib ReadUvarint) */
   M3O_ERR_UNEXPECTED_EOF = 12,   /* io.ErrUnexpectedEOF (Go stdlib ReadUvarint, i>0) */
   M3O_ERR_OUT_OF_ORDER = 13,     /* errOutOfOrderIterator, encoding/iterators_types.go / iterators.go:229-236 */
-  M3O_ERR_TOO_MANY_ITERATORS = 14 /* more than 12 iterators at one level (restatement limit) */
+  M3O_ERR_TOO_MANY_ITERATORS = 14, /* more than 12 iterators at one level (restatement limit) */
+  M3O_ERR_CHECKSUM = 15           /* errSeekChecksumMismatch / errReadChecksum..., persist/fs/read.go:395-397 */
 };
 
 /* ---- bit I/O (ostream.go / istream.go) exposed for the golden bit-I/O tests ---- */
@@ -182,6 +183,12 @@ void m3o_series_merge_batch(const int64_t *ts, const double *val, uint64_t cap, 
                             const uint64_t *replica_off, const uint64_t *series_off, uint64_t n_series,
                             int64_t start, int64_t end, int strategy, int64_t *ts_out, double *val_out,
                             uint64_t out_cap, uint32_t *n_out, int32_t *status);
+
+/* ---- segment checksum (m3tsz_segment_oracle.c): Adler-32 of
+ * a stream = ts.Segment.CalculateChecksum (src/dbnode/ts/segment.go:60-76). ---- */
+uint32_t m3o_adler32(const uint8_t *data, size_t n);
+void m3o_adler32_batch(const uint8_t *streams, const uint64_t *offsets, uint64_t n_series,
+                       const uint32_t *expected, uint32_t *out, int32_t *status);
 
 #ifdef __cplusplus
 }

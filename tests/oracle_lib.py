@@ -20,7 +20,8 @@ ERR_DOD_OVERFLOW = 4
 
 
 def build_oracle(force=False):
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("m3tsz_oracle.c", "m3tsz_merge_oracle.c", "m3tsz_oracle.h")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("m3tsz_oracle.c", "m3tsz_merge_oracle.c",
+                                                  "m3tsz_segment_oracle.c", "m3tsz_oracle.h")]
     if (not force and os.path.exists(_LIB_PATH)
             and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(f) for f in srcs)):
         return _LIB_PATH
@@ -109,6 +110,8 @@ def lib():
                                          vp, vp, vp]),
         "m3o_series_merge_batch": (None, [vp, vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, C.c_int64,
                                           C.c_int64, C.c_int, vp, vp, C.c_uint64, vp, vp]),
+        "m3o_adler32": (C.c_uint32, [C.c_char_p, C.c_size_t]),
+        "m3o_adler32_batch": (None, [vp, vp, C.c_uint64, vp, vp, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -377,3 +380,24 @@ def series_merge_batch(ts, vals, n_points, seq_status, slice_off, replica_off, s
                                  _ptr(replica_off), _ptr(series_off), S, int(start), int(end), int(strategy),
                                  _ptr(ts_out), _ptr(val_out), out_cap, _ptr(n_out), _ptr(status))
     return ts_out, val_out, n_out, status
+
+
+def adler32(data: bytes) -> int:
+    """Segment checksum oracle (Adler-32 of the stream bytes)."""
+    return int(lib().m3o_adler32(bytes(data), len(data)))
+
+
+def adler32_batch(blob, offsets, expected=None):
+    """Checksums of the CSR streams blob[offsets[s]:offsets[s+1]]; returns (checksums u32[S], status i32[S])."""
+    blob = np.ascontiguousarray(np.frombuffer(bytes(blob), dtype=np.uint8)) if not isinstance(blob, np.ndarray) \
+        else np.ascontiguousarray(blob, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    S = len(offsets) - 1
+    out = np.zeros(S, dtype=np.uint32)
+    status = np.zeros(S, dtype=np.int32)
+    exp = None if expected is None else np.ascontiguousarray(expected, dtype=np.uint32)
+    if len(blob) == 0:
+        blob = np.zeros(1, dtype=np.uint8)
+    lib().m3o_adler32_batch(_ptr(blob), _ptr(offsets), S, None if exp is None else _ptr(exp), _ptr(out),
+                            _ptr(status))
+    return out, status
