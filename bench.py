@@ -360,9 +360,16 @@ def run_ours(args):
 
     enc_ms = time_fn(lambda: codec.encode(ts, vals, start, unit=1, out=enc))
     extras = not args.no_extras
-    ds_ms, n_win, merge_ms, Sm, fixtures = None, 0, None, 0, None
+    ds_ms, n_win, merge_ms, Sm, fixtures, cks = None, 0, None, 0, None, None
     if extras:
         fixtures = fixture_set_throughput(codec, dev, time_fn)
+        # segment checksums (row N2): Adler-32 of every stream of the packed batch
+        ck, ck_st = codec.segment_checksums(packed, offsets, lengths=enc.out_len)
+        assert int((ck_st != 0).sum()) == 0
+        ck_ms = time_fn(lambda: codec.segment_checksums(packed, offsets, lengths=enc.out_len))
+        cks = {"streams": S, "bytes": compressed_bytes, "ms": ck_ms,
+               "algorithmic_gbs": compressed_bytes / (ck_ms * 1e-3) / 1e9}
+        del ck, ck_st
         ds = codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC, (P * 60 + 299) // 300)
         ds_ms = time_fn(lambda: codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC,
                                                         (P * 60 + 299) // 300, out=ds))
@@ -502,7 +509,7 @@ def run_ours(args):
                          "input_dps": Sm * P / (merge_ms * 1e-3),
                          "algorithmic_gbs": (Sm * P * 16 + (Sm // 3) * P * 16) / (merge_ms * 1e-3) / 1e9}
         if extras else None,
-        "fixture_set": fixtures,
+        "fixture_set": fixtures, "segment_checksum": cks,
         "encode_ms": enc_ms, "decode_ms": dec_ms_max,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
         "clocks": clocks, "fetch_allgather": allgather,
