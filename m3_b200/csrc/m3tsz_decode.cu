@@ -4,11 +4,12 @@
 // a serial bit-dependency chain (every field width depends on decoded state),
 // so the per-series state machine runs on one lane while the WARP cooperates
 // on memory: each lane's compressed words are staged into a shared-memory ring
-// ([word][lane], stride 33) by asynchronous 128-byte-coalesced copies
-// (cp.async / LDGSTS) issued one refill ahead of consumption, every datapoint
-// is parsed branch-free from four ring words with funnel shifts, and decoded
-// (ts, value) pairs go through a second transposed tile so global stores are
-// coalesced per series.
+// of 16-byte quads ([quad][lane]) by asynchronous 16-byte copies (cp.async /
+// LDGSTS, conflict-free, 64-byte chunks per lane) issued one refill ahead of
+// consumption, every datapoint is parsed branch-free from two LDS.128 (eight
+// words, no bank conflicts wherever the lanes stand) with selects and funnel
+// shifts, and decoded (ts, value) pairs go through a transposed tile so global
+// stores are whole 32-byte sectors per series.
 //
 // Format: SURVEY.md Appendix A; reference decode path
 //   m3tsz/iterator.go:81-219, m3tsz/timestamp_iterator.go:80-326,
@@ -18,8 +19,8 @@
 
 namespace m3tsz {
 
-// Tuning knobs (overridable with -D for sweeps; defaults = best of the round-1 sweep
-// at 100k x 1440, see profiles/r01_decode_history.md)
+// Tuning knobs (overridable with -D for sweeps; defaults = best of the round-1 sweeps
+// at 1M x 1440, see profiles/r01_decode_history.md)
 #ifndef M3_DEC_OUT_T
 #define M3_DEC_OUT_T 4  // output tile rows (datapoints per flush)
 #endif
@@ -38,43 +39,32 @@ namespace m3tsz {
 #ifndef M3_DEC_MIN_BLOCKS
 #define M3_DEC_MIN_BLOCKS 4
 #endif
-#ifndef M3_OPT_G
-#define M3_OPT_G 1  // per-group (M3_DEC_CHK datapoints) pre-check of the hot path's slow-changing conditions
-#endif
-#ifndef M3_DEC_QUAD
-#define M3_DEC_QUAD 0  // 1: ring of 16-byte quads ([quad][lane]), lane-local 16-byte cp.async, LDS.128 reads
-#endif
-#ifndef M3_OPT_W3
-#define M3_OPT_W3 1  // load the window's 4th word only on lanes that can need it
-#endif
-#ifndef M3_OPT_X
-#define M3_OPT_X 1  // two-stage funnel extraction of the payload field
+#ifndef M3_DEC_MIN_BLOCKS_DS
+#define M3_DEC_MIN_BLOCKS_DS 4  // fused-downsample kernel (5 blocks fit its shared memory but spill registers)
 #endif
 #ifndef M3_DEC_WARPS
 #define M3_DEC_WARPS 4
 #endif
 constexpr int DEC_WARPS = M3_DEC_WARPS;  // warps per block
-constexpr int DEC_RING = 64;      // staged words per lane (ring buffer, power of two)
-constexpr int DEC_MIRROR = 3;     // rows 64..66 mirror rows 0..2 so 4-word reads never wrap
+#ifndef M3_DEC_RING
+#define M3_DEC_RING 64
+#endif
+constexpr int DEC_RING = M3_DEC_RING;  // staged words per lane (ring buffer, power of two)
 constexpr int DEC_FILL = 16;      // words per lane per asynchronous refill chunk
 constexpr int DEC_TRIGGER = M3_DEC_TRIGGER;
 constexpr int DEC_ACCEPT = DEC_RING - DEC_FILL;  // lanes with <= this many words ahead take a chunk
-constexpr int DEC_STRIDE = 33;    // tile row stride (words / dwords): conflict-free transposes
+constexpr int DEC_STRIDE = 33;    // output tile row stride (dwords): conflict-free transposes
 constexpr int DEC_OUT_T = M3_DEC_OUT_T;
 constexpr int DEC_UNROLL = M3_DEC_UNROLL;
 constexpr int DEC_FAST_WORDS = 4; // the fast path reads 4 consecutive words
 
-#if M3_DEC_QUAD
 constexpr int DEC_QUADS = DEC_RING / 4;  // + 1 mirror quad (copy of quad 0) so quad q+1 is always at +1
 constexpr int DEC_IN_TILE_WORDS = (DEC_QUADS + 1) * 32 * 4;
-#else
-constexpr int DEC_IN_TILE_WORDS = (DEC_RING + DEC_MIRROR + 1) * DEC_STRIDE;  // u32 (+1 row pad: 8B align)
-#endif
 constexpr int DEC_OUT_TILE_DWORDS = DEC_OUT_T * DEC_STRIDE;                  // u64
 constexpr size_t DEC_WARP_SMEM_PLAIN =
     (size_t)DEC_IN_TILE_WORDS * 4 + 2 * (size_t)DEC_OUT_TILE_DWORDS * 8;
 constexpr size_t DEC_WARP_SMEM_DS = (size_t)DEC_IN_TILE_WORDS * 4;
-static_assert((DEC_IN_TILE_WORDS * 4) % 8 == 0, "u64 tiles must stay 8-byte aligned");
+static_assert(DEC_WARP_SMEM_PLAIN % 16 == 0 && DEC_WARP_SMEM_DS % 16 == 0, "every warp's ring must stay 16-byte aligned");
 
 constexpr uint64_t kGoNaNBits = 0x7FF8000000000001ull;  // math.NaN()
 
@@ -106,7 +96,7 @@ struct DecState {
 struct SlowSrc {
   const uint8_t *base;
   uint64_t nbytes;
-  const uint32_t *ring_lane;  // ring + lane
+  const uint32_t *ring_lane;  // the lane's 16-byte cell of quad 0 (ring + lane * 4 words)
   uint32_t ring_safe;
 };
 
@@ -114,18 +104,11 @@ __device__ __forceinline__ uint64_t gpeek64(const SlowSrc &src, uint64_t wbase, 
   const uint32_t wr = pos >> 5;
   uint32_t w0, w1, w2;
   if (wr + 3u <= src.ring_safe) {
-#if M3_DEC_QUAD
     // ring_lane = ring + lane * 4 (words); word w lives at quad (w >> 2) & 15, element w & 3
     const uint32_t a0 = wr, a1 = wr + 1, a2 = wr + 2;
     w0 = __byte_perm(src.ring_lane[((a0 >> 2) & (DEC_QUADS - 1)) * 128 + (a0 & 3)], 0, 0x0123);
     w1 = __byte_perm(src.ring_lane[((a1 >> 2) & (DEC_QUADS - 1)) * 128 + (a1 & 3)], 0, 0x0123);
     w2 = __byte_perm(src.ring_lane[((a2 >> 2) & (DEC_QUADS - 1)) * 128 + (a2 & 3)], 0, 0x0123);
-#else
-    const uint32_t *tp = src.ring_lane + (wr & (DEC_RING - 1)) * DEC_STRIDE;
-    w0 = __byte_perm(tp[0], 0, 0x0123);
-    w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123);
-    w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123);
-#endif
   } else {
     const uint64_t w = wbase + wr;
     w0 = load_be32(src.base, src.nbytes, w);
@@ -405,87 +388,11 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const SlowSrc src, int 
 }
 #undef M3_RD
 
-// 64 bits starting at bit q (0 <= q < 64) of the 128-bit window w0:w1:w2:w3
-__device__ __forceinline__ uint64_t extract64(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3,
-                                              uint32_t q) {
-  const bool up = q >= 32;
-  const uint32_t a = up ? w1 : w0, b = up ? w2 : w1, c = up ? w3 : w2;
-  const uint32_t hi = __funnelshift_l(b, a, q);
-  const uint32_t lo = __funnelshift_l(c, b, q);
-  return ((uint64_t)hi << 32) | lo;
-}
-
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
-// 4-byte asynchronous global->shared copy (LDGSTS); bytes past src_bytes are zero-filled
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes)
-               : "memory");
-}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-// waits until at most `d` of the most recently committed groups are still in flight
-__device__ __forceinline__ void cp_async_wait_pending(uint32_t d) {
-  switch (d) {
-    case 0: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;\n" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;\n" ::: "memory"); break;
-    case 3: asm volatile("cp.async.wait_group 3;\n" ::: "memory"); break;
-    case 4: asm volatile("cp.async.wait_group 4;\n" ::: "memory"); break;
-    case 5: asm volatile("cp.async.wait_group 5;\n" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 6;\n" ::: "memory"); break;  // stricter than needed
-  }
-}
 
-// Warp-cooperative asynchronous refill: for every lane j in `mask`, copies the
-// DEC_FILL (=16) words starting at global word index my_gw (of lane j, always a
-// multiple of 16) into lane j's ring column; one instruction serves two series
-// (lanes 0-15 -> series 2i, lanes 16-31 -> series 2i+1).  Ring slot of a word ==
-// its word index RELATIVE to the stream's base (the first word rounded down to a
-// DEC_FILL-word boundary) & (DEC_RING-1): lanes whose streams start DEC_FILL-word
-// (64-byte) aligned and consume at similar rates read the same rows, i.e.
-// different banks.  my_slot0 = the chunk's first slot (a multiple of DEC_FILL);
-// slots 0..2 are mirrored to 64..66 so 4-word reads never wrap.
-__device__ __forceinline__ void ring_fill(uint32_t *ring, const uint8_t *streams, uint64_t nbytes,
-                                          uint32_t mask, uint32_t my_gw, uint32_t my_slot0, int lane) {
-  const uint32_t my_packed = my_gw | (my_slot0 >> 4);  // gw is a multiple of 16: low bits carry slot0/16
-  const int sub = lane & 15, half = lane >> 4;
-  const uint32_t lane_dst = smem_addr(ring) + (uint32_t)sub * (DEC_STRIDE * 4u) + (uint32_t)half * 4u;
-  const uint8_t *lane_src = streams + (uint32_t)sub * 4u;
-  const uint32_t safe_words = (uint32_t)(nbytes >> 2);  // complete words in the buffer
-  const bool all_inb = __all_sync(FULL_MASK, my_gw + DEC_FILL <= safe_words);
-  if (mask == FULL_MASK && all_inb) {
-#pragma unroll 8
-    for (int i = 0; i < 16; i++) {
-      const uint32_t pk = __shfl_sync(FULL_MASK, my_packed, 2 * i + half);
-      const uint32_t gw = pk & ~15u;
-      const uint32_t slot0 = (pk & 3u) << 4;
-      const uint32_t dst = lane_dst + slot0 * (DEC_STRIDE * 4u) + (uint32_t)i * 8u;
-      const uint8_t *src = lane_src + (uint64_t)gw * 4ull;
-      cp_async4(dst, src, 4u);
-      if (sub < DEC_MIRROR && slot0 == 0) cp_async4(dst + DEC_RING * DEC_STRIDE * 4u, src, 4u);
-    }
-    return;
-  }
-  for (int i = 0; i < 16; i++) {
-    if (!((mask >> (2 * i)) & 3u)) continue;  // warp-uniform
-    const int j = 2 * i + half;
-    const uint32_t pk = __shfl_sync(FULL_MASK, my_packed, j);
-    if ((mask >> j) & 1u) {
-      const uint32_t gw = pk & ~15u;
-      const uint32_t slot0 = (pk & 3u) << 4;
-      const uint32_t dst = lane_dst + slot0 * (DEC_STRIDE * 4u) + (uint32_t)i * 8u;
-      const uint64_t b = ((uint64_t)gw + (uint32_t)sub) * 4ull;
-      const uint32_t nb = (b + 4 <= nbytes) ? 4u : (b < nbytes ? (uint32_t)(nbytes - b) : 0u);
-      const uint8_t *src = nb ? (streams + b) : streams;
-      cp_async4(dst, src, nb);
-      if (sub < DEC_MIRROR && slot0 == 0) cp_async4(dst + DEC_RING * DEC_STRIDE * 4u, src, nb);
-    }
-  }
-}
-
-#if M3_DEC_QUAD
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
@@ -494,7 +401,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 // (a multiple of 16) of ITS OWN stream into quads slot_q0..slot_q0+3 of its own
 // column with four 16-byte cp.async (a warp instruction writes 32 x 16 B =
 // 4 conflict-free wavefronts; no shuffles).  Quad 0 is mirrored to quad 16.
-__device__ __forceinline__ void ring_fill_quad(uint32_t ring_lane_addr, const uint8_t *streams, uint64_t nbytes,
+__device__ __forceinline__ void ring_fill(uint32_t ring_lane_addr, const uint8_t *streams, uint64_t nbytes,
                                                bool take, uint32_t gw, uint32_t slot_q0) {
   if (take) {
 #pragma unroll
@@ -508,7 +415,6 @@ __device__ __forceinline__ void ring_fill_quad(uint32_t ring_lane_addr, const ui
     }
   }
 }
-#endif
 
 struct DsAcc {  // fused-downsample per-lane accumulator (aggregation.Gauge, gauge.go:31-106)
   int64_t cur_w, hi_w, w_start;
@@ -517,7 +423,7 @@ struct DsAcc {  // fused-downsample per-lane accumulator (aggregation.Gauge, gau
 };
 
 template <bool INT_OPT, int MODE>
-__global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
+__global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCKS_DS : M3_DEC_MIN_BLOCKS)
     decode_kernel(const DecodeParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
@@ -526,12 +432,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
   uint32_t *ring = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem) + warp * warp_smem);
   uint64_t *ts_tile = reinterpret_cast<uint64_t *>(ring + DEC_IN_TILE_WORDS);
   uint64_t *val_tile = ts_tile + DEC_OUT_TILE_DWORDS;
-#if M3_DEC_QUAD
   const uint32_t *ring_lane = ring + lane * 4;  // this lane's 16-byte cell of quad 0
   const uint32_t ring_lane_addr = smem_addr(ring_lane);
-#else
-  const uint32_t *ring_lane = ring + lane;  // this lane's ring column
-#endif
   uint64_t *ts_lane = ts_tile + lane;       // this lane's output tile columns (values: + DEC_OUT_TILE_DWORDS)
 
   const uint64_t warp_s0 = ((uint64_t)blockIdx.x * DEC_WARPS + warp) * 32ull;
@@ -644,12 +546,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           const uint32_t fmask =
               __ballot_sync(FULL_MASK, active && avail <= (rep == 0 ? DEC_ACCEPT : DEC_TRIGGER));
           if (!fmask) break;
-#if M3_DEC_QUAD
-          ring_fill_quad(ring_lane_addr, p.streams, p.streams_bytes, (fmask >> lane) & 1u, gbase + filled,
+          ring_fill(ring_lane_addr, p.streams, p.streams_bytes, (fmask >> lane) & 1u, gbase + filled,
                          (filled >> 2) & (DEC_QUADS - 1));
-#else
-          ring_fill(ring, p.streams, p.streams_bytes, fmask, gbase + filled, filled & (DEC_RING - 1), lane);
-#endif
           if ((fmask >> lane) & 1u) {
             filled += DEC_FILL;
             avail += DEC_FILL;
@@ -666,7 +564,6 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
 #pragma unroll 1
     for (int rb = 0; rb < DEC_OUT_T; rb += M3_DEC_CHK) {
       ring_service();
-#if M3_OPT_G
       // Hot-path conditions that cannot change while the group stays on the hot path,
       // checked once with margins for M3_DEC_CHK datapoints of <= 80 bits each: words
       // landed, distance to the end of the stream, not the first datapoint and no
@@ -675,7 +572,6 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
       bool pre_ok = fast_en && (((s.pos + 80u * (M3_DEC_CHK - 1)) >> 5) + DEC_FAST_WORDS <= safe) &&
                     (s.pos + 80u * M3_DEC_CHK <= s.end) && (s.prev_time > 0) &&
                     ((uint64_t)s.prev_delta < (1ull << 60)) && (!INT_OPT || s.is_float);
-#endif
 #pragma unroll DEC_UNROLL
       for (int rr = 0; rr < M3_DEC_CHK; rr++) {
       const int row = rb + rr;
@@ -685,23 +581,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
       int64_t t = 0;
       uint64_t v = 0;
       bool emitted = false;
-      // ---------------- parse 4 ring words ----------------
-#if !M3_DEC_QUAD
-      const uint32_t *tp = ring_lane + (cw & (DEC_RING - 1)) * DEC_STRIDE;
-#endif
+      // ---------------- parse: the 128-bit window at the current word ----------------
       const uint32_t sh = s.pos & 31u;
-      // the 4th word only matters when the code can reach past bit 96 of the window: the
-      // hot path's codes are <= 80 bits, so only lanes with sh > 16 load it here (fewer
-      // active lanes = fewer bank conflicts); the general path reloads it when it needs it
-#if M3_OPT_W3
-      const bool need_w3 = sh > 16u;
-#else
-      const bool need_w3 = true;
-#endif
-#if M3_DEC_QUAD
       // two aligned quads (8 words) hold the window; pick words j..j+3 (j = cw & 3): the
       // j & 2 level with selects on the raw words, the j & 1 level fused with the byte swap
-      (void)need_w3;
+      // (PRMT picks the swapped bytes of its first or its second operand)
       const uint4 *qp = reinterpret_cast<const uint4 *>(ring_lane) + ((cw >> 2) & (DEC_QUADS - 1)) * 32;
       const uint4 qa = qp[0], qb = qp[32];
       const bool j2 = (cw & 2u) != 0;
@@ -710,42 +594,22 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
       const uint32_t psel = 0x0123u + (cw & 1u) * 0x4444u;  // 0x0123: swap(a), 0x4567: swap(b)
       const uint32_t w0 = __byte_perm(u0, u1, psel), w1 = __byte_perm(u1, u2, psel),
                      w2 = __byte_perm(u2, u3, psel);
-      uint32_t w3 = __byte_perm(u3, u4, psel);
-#else
-      const uint32_t w0 = __byte_perm(tp[0], 0, 0x0123), w1 = __byte_perm(tp[DEC_STRIDE], 0, 0x0123),
-                     w2 = __byte_perm(tp[2 * DEC_STRIDE], 0, 0x0123);
-      uint32_t w3 = need_w3 ? __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123) : 0u;
-#endif
-      const uint32_t h = __funnelshift_l(w1, w0, sh);
-#if M3_OPT_X
+      const uint32_t w3 = __byte_perm(u3, u4, psel);
       // 96-bit window at the bit position: (h, h1, h2); a field at offset c <= 32 is two more funnels
-      const uint32_t h1 = __funnelshift_l(w2, w1, sh);
-      uint32_t h2 = __funnelshift_l(w3, w2, sh);
+      const uint32_t h = __funnelshift_l(w1, w0, sh), h1 = __funnelshift_l(w2, w1, sh),
+                     h2 = __funnelshift_l(w3, w2, sh);
 #define M3_FIELD64(c_) \
   (((uint64_t)__funnelshift_lc(h1, h, (c_)) << 32) | (uint64_t)__funnelshift_lc(h2, h1, (c_)))
-#else
-#define M3_FIELD64(c_) extract64(w0, w1, w2, w3, sh + (c_))
-#endif
 
       // ---- hot candidate: zero delta-of-delta, float XOR code ----
       {
         uint32_t x = h << 1;
         uint32_t c = 1;
-#if M3_OPT_G
         bool hot = pre_ok && (INT_OPT ? ((h >> 30) == 1u) : !(h >> 31));  // '0' zero DoD [+ '1' no update]
         if (INT_OPT) {
           x <<= 1;
           c = 2;
         }
-#else
-        const bool okb = fast_en && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
-        bool hot = okb && !(h >> 31);
-        if (INT_OPT) {
-          hot = hot && (x >> 31) && s.is_float;  // '1' = no mode update
-          x <<= 1;
-          c = 2;
-        }
-#endif
         const bool zero = !(x >> 31);
         const bool cont = (x >> 30) == 2u;
         const int lz = (int)((x >> 24) & 63u);
@@ -760,9 +624,6 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
         const uint64_t field = M3_FIELD64(c);
         const uint64_t payload = n ? (field >> (64 - n)) : 0ull;
         c += (uint32_t)n;
-#if !M3_OPT_G
-        hot = hot && (s.pos + c <= s.end);
-#endif
         if (__all_sync(FULL_MASK, hot || !active)) {
           // every live lane: unconditional update (finished lanes compute garbage
           // they never read again)
@@ -788,17 +649,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
 
       // ---------------- general path (any mix of cases) ----------------
       {
-#if M3_OPT_G
         pre_ok = false;  // the group's pre-check does not survive a general-path datapoint
-#endif
-#if !M3_DEC_QUAD
-        if (!need_w3) {  // general codes are up to 95 bits
-          w3 = __byte_perm(tp[3 * DEC_STRIDE], 0, 0x0123);
-#if M3_OPT_X
-          h2 = __funnelshift_l(w3, w2, sh);
-#endif
-        }
-#endif
         bool ok = fast_en && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
         uint32_t c = 1;  // bits consumed before the payload
         int64_t dod = 0;
@@ -920,7 +771,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, M3_DEC_MIN_BLOCKS)
           SlowSrc src;
           src.base = p.streams;
           src.nbytes = p.streams_bytes;
-          src.ring_lane = ring + lane;
+          src.ring_lane = ring_lane;
           src.ring_safe = ((int)(filled - cw) >= 0) ? safe : 0u;  // ring abandoned after a skip
           const bool em = decode_dp_slow<INT_OPT>(tmp, src, p.default_unit, st, sv);
           s = tmp;

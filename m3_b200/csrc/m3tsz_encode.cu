@@ -25,7 +25,7 @@ constexpr int ENC_WARPS = 4;
 constexpr int ENC_STRIDE = 33;
 constexpr int ENC_IN_T = 8;     // datapoints per input tile (double buffered, cp.async)
 #ifndef M3_ENC_OUT_W
-#define M3_ENC_OUT_W 40
+#define M3_ENC_OUT_W 24  // best of the 16/20/24/40 sweep at 1M x 1440 (smaller tile = more L1)
 #endif
 #ifndef M3_ENC_MIN_BLOCKS
 #define M3_ENC_MIN_BLOCKS 4
