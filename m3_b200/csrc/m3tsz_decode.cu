@@ -8,8 +8,8 @@
 // LDGSTS, conflict-free, 64-byte chunks per lane) issued one refill ahead of
 // consumption, every datapoint is parsed branch-free from two LDS.128 (eight
 // words, no bank conflicts wherever the lanes stand) with selects and funnel
-// shifts, and decoded (ts, value) pairs go through a transposed tile so global
-// stores are whole 32-byte sectors per series.
+// shifts, and a group of four decoded (ts, value) pairs stays in registers until
+// the lane stores it as one whole 32-byte sector per array (STG.256).
 //
 // Format: SURVEY.md Appendix A; reference decode path
 //   m3tsz/iterator.go:81-219, m3tsz/timestamp_iterator.go:80-326,
@@ -21,23 +21,17 @@ namespace m3tsz {
 
 // Tuning knobs (overridable with -D for sweeps; defaults = best of the round-1 sweeps
 // at 1M x 1440, see profiles/r01_decode_history.md)
-#ifndef M3_DEC_OUT_T
-#define M3_DEC_OUT_T 4  // output tile rows (datapoints per flush)
-#endif
 #ifndef M3_DEC_TRIGGER
 #define M3_DEC_TRIGGER 24  // <= this many requested words ahead: the lane triggers a refill event
 #endif
 #ifndef M3_DEC_CHK
 #define M3_DEC_CHK 4  // ring bookkeeping every CHK datapoints
 #endif
-#ifndef M3_DEC_UNROLL
-#define M3_DEC_UNROLL 1  // unroll factor of the per-datapoint body between ring checks
-#endif
 #ifndef M3_DEC_SAFE_MIN
 #define M3_DEC_SAFE_MIN 12  // fewer landed words ahead than this: confirm the copy in flight
 #endif
 #ifndef M3_DEC_MIN_BLOCKS
-#define M3_DEC_MIN_BLOCKS 4
+#define M3_DEC_MIN_BLOCKS 5
 #endif
 #ifndef M3_DEC_MIN_BLOCKS_DS
 #define M3_DEC_MIN_BLOCKS_DS 4  // fused-downsample kernel (5 blocks fit its shared memory but spill registers)
@@ -53,16 +47,13 @@ constexpr int DEC_RING = M3_DEC_RING;  // staged words per lane (ring buffer, po
 constexpr int DEC_FILL = 16;      // words per lane per asynchronous refill chunk
 constexpr int DEC_TRIGGER = M3_DEC_TRIGGER;
 constexpr int DEC_ACCEPT = DEC_RING - DEC_FILL;  // lanes with <= this many words ahead take a chunk
-constexpr int DEC_STRIDE = 33;    // output tile row stride (dwords): conflict-free transposes
-constexpr int DEC_OUT_T = M3_DEC_OUT_T;
-constexpr int DEC_UNROLL = M3_DEC_UNROLL;
+constexpr int DEC_GROUP = 4;      // datapoints per output group (one 32-byte sector per array)
 constexpr int DEC_FAST_WORDS = 4; // the fast path reads 4 consecutive words
 
 constexpr int DEC_QUADS = DEC_RING / 4;  // + 1 mirror quad (copy of quad 0) so quad q+1 is always at +1
 constexpr int DEC_IN_TILE_WORDS = (DEC_QUADS + 1) * 32 * 4;
-constexpr int DEC_OUT_TILE_DWORDS = DEC_OUT_T * DEC_STRIDE;                  // u64
-constexpr size_t DEC_WARP_SMEM_PLAIN =
-    (size_t)DEC_IN_TILE_WORDS * 4 + 2 * (size_t)DEC_OUT_TILE_DWORDS * 8;
+static_assert(M3_DEC_CHK == DEC_GROUP, "ring bookkeeping runs once per output group");
+constexpr size_t DEC_WARP_SMEM_PLAIN = (size_t)DEC_IN_TILE_WORDS * 4;
 constexpr size_t DEC_WARP_SMEM_DS = (size_t)DEC_IN_TILE_WORDS * 4;
 static_assert(DEC_WARP_SMEM_PLAIN % 16 == 0 && DEC_WARP_SMEM_DS % 16 == 0, "every warp's ring must stay 16-byte aligned");
 
@@ -430,11 +421,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
   const int warp = threadIdx.x >> 5;
   constexpr size_t warp_smem = (MODE == 0) ? DEC_WARP_SMEM_PLAIN : DEC_WARP_SMEM_DS;
   uint32_t *ring = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem) + warp * warp_smem);
-  uint64_t *ts_tile = reinterpret_cast<uint64_t *>(ring + DEC_IN_TILE_WORDS);
-  uint64_t *val_tile = ts_tile + DEC_OUT_TILE_DWORDS;
   const uint32_t *ring_lane = ring + lane * 4;  // this lane's 16-byte cell of quad 0
   const uint32_t ring_lane_addr = smem_addr(ring_lane);
-  uint64_t *ts_lane = ts_tile + lane;       // this lane's output tile columns (values: + DEC_OUT_TILE_DWORDS)
 
   const uint64_t warp_s0 = ((uint64_t)blockIdx.x * DEC_WARPS + warp) * 32ull;
   if (warp_s0 >= p.n_series) return;
@@ -497,26 +485,18 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
   // refills are DEC_FILL-word aligned: start at the stream's first word rounded down
   uint32_t filled = (s.pos >> 5) & ~(uint32_t)(DEC_FILL - 1);  // words [.., filled) requested
   uint32_t safe = filled;                                       // words [.., safe) have landed
-  uint32_t tile_row0 = 0;  // datapoint index of output tile row 0 (warp-uniform)
+  uint32_t tile_row0 = 0;  // datapoint index of the output group's row 0 (warp-uniform)
+  uint64_t o_t[4] = {0, 0, 0, 0}, o_v[4] = {0, 0, 0, 0};  // the group's datapoints
+  // row 0 of every group is 32-byte aligned when the arrays are and cap is a multiple of 4
+  const bool out_aligned =
+      MODE == 0 && (((uintptr_t)p.ts | (uintptr_t)p.val) & 31u) == 0 && (p.cap & 3u) == 0;
   // scheme/unit admit the fast path (they only change on the slow path)
   bool su_ok = false;
   // maintained flags: `live` = lane still decoding; they change on the general path only
   bool live = !s.done && s.err == 0;
   bool fast_en = false;  // live && su_ok
 
-  // flush geometry: one store instruction writes DEC_OUT_T rows of ts and of values
-  // for FL_SPI series
-  constexpr int FL_SPI = 32 / (2 * DEC_OUT_T);  // series per instruction
-  constexpr int FL_ITERS = 32 / FL_SPI;
-  const int fl_r = lane & (DEC_OUT_T - 1);
-  const bool fl_isval = (lane / DEC_OUT_T) & 1;
-  const int fl_jo = lane / (2 * DEC_OUT_T);
-  const uint64_t *fl_tile = (fl_isval ? val_tile : ts_tile) + fl_r * DEC_STRIDE + fl_jo;
-  uint64_t *fl_base = (fl_isval ? reinterpret_cast<uint64_t *>(p.val) : reinterpret_cast<uint64_t *>(p.ts)) +
-                      (warp_s0 + fl_jo) * p.cap + fl_r;
-  const uint32_t fl_step_bytes = (uint32_t)FL_SPI * (uint32_t)p.cap * 8u;  // cap < 2^27 (checked by the host)
-
-  for (;;) {  // one group of DEC_OUT_T datapoints per iteration
+  for (;;) {  // one group of DEC_GROUP datapoints per iteration
     if (!__any_sync(FULL_MASK, live)) break;
 
     // ---- ring maintenance (every M3_DEC_CHK datapoints) ----
@@ -562,7 +542,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
     };
 
 #pragma unroll 1
-    for (int rb = 0; rb < DEC_OUT_T; rb += M3_DEC_CHK) {
+    for (int rb = 0; rb < DEC_GROUP; rb += M3_DEC_CHK) {
       ring_service();
       // Hot-path conditions that cannot change while the group stays on the hot path,
       // checked once with margins for M3_DEC_CHK datapoints of <= 80 bits each: words
@@ -572,9 +552,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
       bool pre_ok = fast_en && (((s.pos + 80u * (M3_DEC_CHK - 1)) >> 5) + DEC_FAST_WORDS <= safe) &&
                     (s.pos + 80u * M3_DEC_CHK <= s.end) && (s.prev_time > 0) &&
                     ((uint64_t)s.prev_delta < (1ull << 60)) && (!INT_OPT || s.is_float);
-#pragma unroll DEC_UNROLL
+#pragma unroll
       for (int rr = 0; rr < M3_DEC_CHK; rr++) {
-      const int row = rb + rr;
 
       const bool active = live;
       const uint32_t cw = s.pos >> 5;
@@ -634,9 +613,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
           s.prev_bits ^= xr;
           lz_tz(xr, plz, ptz);
           if (MODE == 0) {
-            uint64_t *op = ts_lane + row * DEC_STRIDE;
-            op[0] = (uint64_t)s.prev_time;
-            op[DEC_OUT_TILE_DWORDS] = s.prev_bits;
+            o_t[rr] = (uint64_t)s.prev_time;
+            o_v[rr] = s.prev_bits;
             s.n += (uint32_t)active;
             continue;
           }
@@ -789,9 +767,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
       // ---------------- sink ----------------
       if (MODE == 0) {
         if (emitted) {
-          uint64_t *op = ts_lane + row * DEC_STRIDE;
-          op[0] = (uint64_t)t;
-          op[DEC_OUT_TILE_DWORDS] = v;
+          o_t[rr] = (uint64_t)t;
+          o_v[rr] = v;
           s.n++;
         }
       } else {
@@ -848,28 +825,32 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
     }
     }
 
-    // ---------------- flush the output tile ----------------
-    if (MODE == 0) {
-      __syncwarp();
+    // ---------------- store the group: each lane writes its own series ----------------
+    // Every live lane emits exactly one datapoint per step until it stops, so the group's
+    // rows are o_t/o_v[0 .. my_rows).  4 rows = one 32-byte sector per array (STG.256 when
+    // the row is 32-byte aligned).
+    if (MODE == 0 && valid) {
       const uint32_t lim = s.n < (uint32_t)p.cap ? s.n : (uint32_t)p.cap;
-      const uint32_t my_rows = lim > tile_row0 ? min(lim - tile_row0, (uint32_t)DEC_OUT_T) : 0u;
-      uint8_t *dst = reinterpret_cast<uint8_t *>(fl_base + tile_row0);
-      if (__all_sync(FULL_MASK, my_rows == (uint32_t)DEC_OUT_T)) {
-#pragma unroll
-        for (int i = 0; i < FL_ITERS; i++)
-          *reinterpret_cast<uint64_t *>(dst + (uint64_t)(uint32_t)i * (uint64_t)fl_step_bytes) = fl_tile[FL_SPI * i];
+      const uint32_t my_rows = lim > tile_row0 ? min(lim - tile_row0, 4u) : 0u;
+      uint64_t *dt = reinterpret_cast<uint64_t *>(p.ts) + sidx * p.cap + tile_row0;
+      uint64_t *dv = reinterpret_cast<uint64_t *>(p.val) + sidx * p.cap + tile_row0;
+      if (my_rows == 4u && out_aligned) {
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dt), "l"(o_t[0]), "l"(o_t[1]), "l"(o_t[2]),
+                     "l"(o_t[3])
+                     : "memory");
+        asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dv), "l"(o_v[0]), "l"(o_v[1]), "l"(o_v[2]),
+                     "l"(o_v[3])
+                     : "memory");
       } else {
-#pragma unroll 4
-        for (int i = 0; i < FL_ITERS; i++) {
-          const uint32_t rows = __shfl_sync(FULL_MASK, my_rows, FL_SPI * i + fl_jo);
-          if ((uint32_t)fl_r < rows)
-            *reinterpret_cast<uint64_t *>(dst + (uint64_t)(uint32_t)i * (uint64_t)fl_step_bytes) =
-                fl_tile[FL_SPI * i];
-        }
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if ((uint32_t)r < my_rows) {
+            dt[r] = o_t[r];
+            dv[r] = o_v[r];
+          }
       }
-      __syncwarp();
     }
-    tile_row0 += DEC_OUT_T;
+    tile_row0 += DEC_GROUP;
   }
   cp_async_wait_all();
 

@@ -27,9 +27,6 @@ constexpr int ENC_IN_T = 8;     // datapoints per input tile (double buffered, c
 #ifndef M3_ENC_OUT_W
 #define M3_ENC_OUT_W 24  // best of the 16/20/24/40 sweep at 1M x 1440 (smaller tile = more L1)
 #endif
-#ifndef M3_ENC_FP_FILTER
-#define M3_ENC_FP_FILTER 0  // 1: the int-likeness filter in FP64 arithmetic instead of integer ops
-#endif
 #ifndef M3_ENC_MIN_BLOCKS
 #define M3_ENC_MIN_BLOCKS 4
 #endif
@@ -125,23 +122,13 @@ __device__ __forceinline__ void emit_code(EncLane &s, uint32_t *tile, int lane, 
 __device__ __forceinline__ bool maybe_int(double v) {
   const double a = fabs(v);
   const double p = __dmul_rn(a, 1000000.0);
-#if M3_ENC_FP_FILTER
-  // the same test on the (idle) FP64 pipe: p - rint(p) is exact, and p * 2^-49 lies in
-  // [8, 16) ulps of p, so "far" still implies more than 8 ulps from the nearest integer
+  // on the (otherwise idle) FP64 pipe: p - rint(p) is exact, and p * 2^-49 lies in
+  // [8, 16) ulps of p, so "far" implies more than 8 ulps from the nearest integer
   const double r = __dsub_rn(p, rint(p));
   const bool far = fabs(r) > __dmul_rn(p, 0x1p-49);
-  const bool in_rng = (p >= 1.0) && (p < 0x1p48);
-  const bool tiny_v = (p < 0.5) && (a >= 1e-300);
+  const bool in_rng = (p >= 1.0) && (p < 0x1p48);   // NaN fails both: "maybe int"
+  const bool tiny_v = (p < 0.5) && (a >= 1e-300);   // only N = 0 is near, i.e. v ~ 0
   return !((in_rng && far) || tiny_v);
-#endif
-  const uint64_t pb = (uint64_t)__double_as_longlong(p);
-  const int e = (int)(pb >> 52);  // sign bit is clear
-  const int f = 1075 - e;         // fractional mantissa bits of p when 5 <= f <= 52
-  const uint64_t mask = (1ull << (f & 63)) - 1ull;
-  const bool far_from_int = ((pb + 8ull) & mask) > 16ull;
-  const bool in_range = (unsigned)(f - 5) <= 47u;          // 1 <= p < 2^48
-  const bool tiny = (e < 1022) && (a >= 1e-300);          // p < 0.5: only N = 0 is near, i.e. v ~ 0
-  return !((in_range && far_from_int) || tiny);
 }
 
 // Go int64(float64) on amd64 (CVTTSD2SQ): out of range / NaN -> 0x8000000000000000
