@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
   // refills are DEC_FILL-word aligned: start at the stream's first word rounded down
   uint32_t filled = (s.pos >> 5) & ~(uint32_t)(DEC_FILL - 1);  // words [.., filled) requested
   uint32_t safe = filled;                                       // words [.., safe) have landed
-  uint32_t tile_row0 = 0;  // datapoint index of the output group's row 0 (warp-uniform)
+  uint32_t group_row0 = 0;  // datapoint index of the output group's row 0 (warp-uniform)
   uint64_t o_t[4] = {0, 0, 0, 0}, o_v[4] = {0, 0, 0, 0};  // the group's datapoints
   // row 0 of every group is 32-byte aligned when the arrays are and cap is a multiple of 4
   const bool out_aligned =
@@ -831,9 +831,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
     // the row is 32-byte aligned).
     if (MODE == 0 && valid) {
       const uint32_t lim = s.n < (uint32_t)p.cap ? s.n : (uint32_t)p.cap;
-      const uint32_t my_rows = lim > tile_row0 ? min(lim - tile_row0, 4u) : 0u;
-      uint64_t *dt = reinterpret_cast<uint64_t *>(p.ts) + sidx * p.cap + tile_row0;
-      uint64_t *dv = reinterpret_cast<uint64_t *>(p.val) + sidx * p.cap + tile_row0;
+      const uint32_t my_rows = lim > group_row0 ? min(lim - group_row0, 4u) : 0u;
+      uint64_t *dt = reinterpret_cast<uint64_t *>(p.ts) + sidx * p.cap + group_row0;
+      uint64_t *dv = reinterpret_cast<uint64_t *>(p.val) + sidx * p.cap + group_row0;
       if (my_rows == 4u && out_aligned) {
         asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dt), "l"(o_t[0]), "l"(o_t[1]), "l"(o_t[2]),
                      "l"(o_t[3])
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
           }
       }
     }
-    tile_row0 += DEC_GROUP;
+    group_row0 += DEC_GROUP;
   }
   cp_async_wait_all();
 
