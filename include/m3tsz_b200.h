@@ -124,7 +124,9 @@ typedef struct m3tsz_annotation_ref {
  * Limits (M3TSZ_ERR_INVALID_ARG beyond): streams_bytes < 2^34, max_points < 2^27,
  * one stream < 2^28 bytes (M3TSZ_ERR_STREAM_TOO_LARGE for that series); split
  * larger batches.  Stream starts may have any alignment; 64-byte aligned starts
- * (m3tsz_compact_streams with align = 64) decode fastest.
+ * (m3tsz_compact_streams with align = 64) decode fastest.  Outputs are stored as
+ * whole 32-byte sectors when d_ts / d_val are 32-byte aligned and max_points is a
+ * multiple of 4 (any other shape is stored row by row: same result, slower).
  * ---------------------------------------------------------------------- */
 int m3tsz_decode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *d_streams,
                        uint64_t streams_bytes, const uint64_t *d_offsets, uint64_t n_series,
