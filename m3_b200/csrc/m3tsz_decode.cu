@@ -774,8 +774,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
       } else {
         if (emitted) {
           s.n++;
-          if (t >= p.range_start && t < range_end) {
-            if (!(acc.cur_w >= 0 && t >= acc.w_start && t - acc.w_start < p.window)) {
+          // inside the open window (one unsigned compare covers both bounds; an open window
+          // lies inside the range)?  Otherwise: inside the range at all?
+          bool in_win = acc.cur_w >= 0 && (uint64_t)(t - acc.w_start) < (uint64_t)p.window;
+          if (!in_win && t >= p.range_start && t < range_end) {
+            {
               // commit the window we are leaving
               if (acc.cur_w >= 0) {
                 const uint64_t o = (uint64_t)acc.cur_w * p.n_series + sidx;
@@ -812,6 +815,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
               acc.cur_w = nw;
               acc.w_start = p.range_start + nw * p.window;
             }
+            in_win = true;
+          }
+          if (in_win) {
             const double dv = __longlong_as_double((long long)v);
             acc.cnt++;
             if (dv == dv) {  // gauge.go:88-101
