@@ -724,6 +724,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   uint32_t iter = 0;
   int64_t t_pf = 0;
   uint64_t fb_pf = 0;
+  const uint64_t *in_next = in_tiles + lane;  // this lane's ts cell of the row to fetch next (value: + one tile)
   for (;;) {
     const bool active = valid && s.err == 0 && iter < n_pts;
     if (!__any_sync(FULL_MASK, active)) break;
@@ -735,9 +736,12 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
       asm volatile("cp.async.commit_group;\n" ::: "memory");
       asm volatile("cp.async.wait_group 1;\n" ::: "memory");
       __syncwarp();
+      // row 0 of the tile that just landed; rows 1..7 are fetched one datapoint ahead below
+      const uint64_t *tile = in_tiles + (((iter / ENC_IN_T) & 1u) * 2u) * ENC_IN_TILE_DWORDS + lane;
+      t_pf = (int64_t)tile[0];
+      fb_pf = tile[ENC_IN_TILE_DWORDS];
+      in_next = tile + ENC_STRIDE;
     }
-    const uint64_t *ts_tile = in_tiles + (((iter / ENC_IN_T) & 1u) * 2u) * ENC_IN_TILE_DWORDS;
-    const uint64_t *val_tile = ts_tile + ENC_IN_TILE_DWORDS;
 
     // ---- make room in the output tile ----
     const bool tight = active && (s.k > (uint32_t)(ENC_OUT_W - ENC_GUARD));
@@ -800,19 +804,14 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
 
     // ---- encode one datapoint ----
     {
-      // rows 1..7 of a tile were fetched from shared memory at the end of the previous
-      // datapoint (the load latency hides behind its bit packing); row 0 follows the
-      // tile's cp.async wait
-      const int row = (int)(iter & (ENC_IN_T - 1));
-      if (row == 0) {
-        t_pf = (int64_t)ts_tile[lane];
-        fb_pf = val_tile[lane];
-      }
+      // this datapoint was fetched from shared memory one datapoint ago (the load latency
+      // hides behind the previous bit packing); fetch the next row of the tile now
       const int64_t t = t_pf;
       const uint64_t fb = fb_pf;
-      if (row + 1 < ENC_IN_T) {
-        t_pf = (int64_t)ts_tile[(row + 1) * ENC_STRIDE + lane];
-        fb_pf = val_tile[(row + 1) * ENC_STRIDE + lane];
+      if ((iter & (ENC_IN_T - 1)) != ENC_IN_T - 1) {
+        t_pf = (int64_t)in_next[0];
+        fb_pf = in_next[ENC_IN_TILE_DWORDS];
+        in_next += ENC_STRIDE;
       }
       const double v = __longlong_as_double((long long)fb);
       const bool room = (uint64_t)s.words_out + s.k + ENC_GUARD + 4 <= slot_words;
