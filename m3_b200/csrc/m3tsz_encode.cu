@@ -724,6 +724,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   uint32_t iter = 0;
   int64_t t_pf = 0;
   uint64_t fb_pf = 0;
+  bool steady = false;  // same s/ms/us/ns unit as the batch's and not the first datapoint
   const uint64_t *in_next = in_tiles + lane;  // this lane's ts cell of the row to fetch next (value: + one tile)
   for (;;) {
     const bool active = valid && s.err == 0 && iter < n_pts;
@@ -814,12 +815,11 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
         in_next += ENC_STRIDE;
       }
       const double v = __longlong_as_double((long long)fb);
-      const bool room = (uint64_t)s.words_out + s.k + ENC_GUARD + 4 <= slot_words;
+      const bool room = s.words_out + s.k + (uint32_t)(ENC_GUARD + 4) <= slot_words;  // < 2^31 words
       // hot candidate: same (valid s/ms/us/ns) unit, zero delta-of-delta, not the
       // first datapoint, a float-mode XOR code (value is certainly not int-like)
       const int64_t delta = (int64_t)((uint64_t)t - (uint64_t)s.prev_time);
-      bool hot = active && room && !p.units && p.unit == s.unit && (s.unit >= 1 && s.unit <= 4) &&
-                 s.n_enc > 0 && delta == s.prev_delta;
+      bool hot = active && room && steady && delta == s.prev_delta;
       if (INT_OPT) hot = hot && s.is_float && fb != s.prev_bits && !maybe_int(v);
       Tier2 c2;
       if (__all_sync(FULL_MASK, hot || !active)) {
@@ -847,8 +847,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
           emit_code_p(s, out_tile, lane, hdr, hb, P, plen);
           s.n_enc++;
         }
-      } else if (__all_sync(FULL_MASK, tier2_candidate<INT_OPT>(s, active && room && !p.units && p.unit == s.unit,
-                                                                 delta, fb, v, c2) ||
+      } else if (__all_sync(FULL_MASK, tier2_candidate<INT_OPT>(s, active && room && steady, delta, fb, v, c2) ||
                                            !active)) {
         // second tier: small delta-of-delta + (float XOR | float repeat | int diff | int
         // repeat) without a mode / header update, still one merge per lane
@@ -873,6 +872,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
             emit_code(s, out_tile, lane, hdr, hb, payload, plen);
             s.n_enc++;
           }
+          // the fast tiers' slow-changing preconditions: the unit only changes here
+          steady = !p.units && p.unit == s.unit && (s.unit >= 1 && s.unit <= 4) && s.n_enc > 0;
         }
       }
     }
