@@ -727,8 +727,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   bool steady = false;  // same s/ms/us/ns unit as the batch's and not the first datapoint
   const uint64_t *in_next = in_tiles + lane;  // this lane's ts cell of the row to fetch next (value: + one tile)
   for (;;) {
+    if (iter >= max_pts) break;  // warp-uniform (n_pts is 0 for lanes without a series)
     const bool active = valid && s.err == 0 && iter < n_pts;
-    if (!__any_sync(FULL_MASK, active)) break;
 
     // ---- input pipeline: request tile t+1, wait for tile t ----
     if ((iter & (ENC_IN_T - 1)) == 0) {
