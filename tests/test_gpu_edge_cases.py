@@ -230,3 +230,30 @@ def test_downsample_window_edges(codecs):
             assert (gs[:, s].view(np.uint64) == es.view(np.uint64)).all()
             assert (gmn[:, s].view(np.uint64) == emn.view(np.uint64)).all()
             assert (gmx[:, s].view(np.uint64) == emx.view(np.uint64)).all()
+
+
+def test_output_arrays_not_sector_aligned(codecs):
+    """The decoder stores whole 32-byte sectors when it can; output arrays that are only
+    8-byte aligned (a view one element into an allocation) take the row-by-row path and
+    must give the same result."""
+    from m3_b200 import synth
+    from m3_b200.codec import DecodeResult
+    S, P = 70, 64  # P % 4 == 0
+    codec = codecs[True]
+    ts, vals, start = synth.gaussian_walk(S, P, "cuda", seed=5)
+    enc = codec.encode(ts, vals, start, unit=O.UNIT_S)
+    packed, offsets = codec.compact(enc, align=64)
+    ref = codec.decode(packed, offsets, P)
+    raw_t = torch.zeros(S * P + 1, dtype=torch.int64, device="cuda")
+    raw_v = torch.zeros(S * P + 1, dtype=torch.float64, device="cuda")
+    out = DecodeResult(ts=raw_t[1:].view(S, P), values=raw_v[1:].view(S, P),
+                       n_points=torch.empty(S, dtype=torch.int32, device="cuda"),
+                       status=torch.empty(S, dtype=torch.int32, device="cuda"),
+                       unit=torch.empty(S, dtype=torch.uint8, device="cuda"), annotations=None)
+    assert out.ts.data_ptr() % 32 == 8
+    codec.decode(packed, offsets, P, out=out)
+    torch.cuda.synchronize()
+    assert torch.equal(out.ts, ref.ts) and torch.equal(out.ts, ts)
+    assert torch.equal(out.values.view(torch.int64), ref.values.view(torch.int64))
+    assert bool((out.n_points == P).all()) and bool((out.status == 0).all())
+    assert int(raw_t[0]) == 0 and float(raw_v[0]) == 0.0  # nothing written before the view
