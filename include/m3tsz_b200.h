@@ -106,6 +106,41 @@ typedef struct m3tsz_annotation_ref {
   uint32_t count;
 } m3tsz_annotation_ref;
 
+/* Per-datapoint unit and annotation (ReaderIterator.Current() returns
+ * (datapoint, unit, annotation) for EVERY datapoint, encoding/types.go:184-187,
+ * m3tsz/iterator.go:229-231).  Both change rarely, so the decoder reports them as
+ * an event table instead of two dense [n_series][max_points] arrays:
+ *   M3TSZ_EVENT_TIME_UNIT  : from datapoint dp_index on, the unit in force is `unit`
+ *                            (a time-unit marker, timestamp_iterator.go:118-134; the unit of
+ *                            datapoint 0 is reported per series in d_unit_first)
+ *   M3TSZ_EVENT_ANNOTATION : datapoint dp_index carries an annotation of `length` bytes whose
+ *                            first payload bit is `bit_offset` bits after the start of the stream
+ *                            (timestamp_iterator.go:328-356); datapoints without an event have none.
+ * Events of one series appear in stream order but interleaved with other series';
+ * events whose dp_index >= n_points[series] belong to a datapoint that failed to decode. */
+enum { M3TSZ_EVENT_TIME_UNIT = 1, M3TSZ_EVENT_ANNOTATION = 2 };
+typedef struct m3tsz_dp_event {
+  uint64_t series;
+  uint32_t dp_index;
+  uint16_t kind;
+  uint16_t unit;
+  uint64_t bit_offset;
+  uint32_t length;
+  uint32_t reserved;
+} m3tsz_dp_event;
+
+/* Optional inputs / outputs of m3tsz_decode_batch_ex (all may be NULL / 0). */
+typedef struct m3tsz_decode_extras {
+  const uint64_t *d_lengths; /* [n_series] exact stream sizes: stream s = [d_offsets[s], +d_lengths[s]);
+                                lets the streams sit anywhere in d_streams (index-entry (Offset, Size),
+                                persist/schema/types.go:70-78); d_offsets then needs n_series entries */
+  uint8_t *d_unit_first;     /* [n_series] unit in force at the first datapoint */
+  m3tsz_dp_event *d_events;  /* event table, events_capacity entries */
+  uint64_t events_capacity;
+  uint64_t *d_event_count;   /* required with d_events; must be zero on entry; receives the number of
+                                events produced (may exceed events_capacity: re-run with a larger table) */
+} m3tsz_decode_extras;
+
 /* ------------------------------------------------------------------------
  * Batch decode.  Replaces, for n_series independent streams, the loop
  *   it := m3tsz.NewReaderIterator(reader, intOptimized, opts)   m3tsz/iterator.go:67-78
@@ -133,6 +168,14 @@ int m3tsz_decode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t 
                        int64_t *d_ts, double *d_val, uint64_t max_points, uint32_t *d_n_points,
                        int32_t *d_status, uint8_t *d_unit, m3tsz_annotation_ref *d_ann,
                        void *stream);
+
+/* m3tsz_decode_batch + the optional per-datapoint unit / annotation events and
+ * non-CSR stream placement (extras may be NULL). */
+int m3tsz_decode_batch_ex(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *d_streams,
+                          uint64_t streams_bytes, const uint64_t *d_offsets, uint64_t n_series,
+                          int64_t *d_ts, double *d_val, uint64_t max_points, uint32_t *d_n_points,
+                          int32_t *d_status, uint8_t *d_unit, m3tsz_annotation_ref *d_ann,
+                          const m3tsz_decode_extras *extras, void *stream);
 
 /* Same call with HOST buffers (pageable or pinned): copies the streams and
  * offsets to the device, decodes, copies the results back, synchronises. */
@@ -178,8 +221,59 @@ int m3tsz_encode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t 
                        uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_len, int32_t *d_status,
                        void *stream);
 
-/* Worst-case stream bytes for n points without annotations (rounded up to 16). */
+/* m3tsz_encode_batch + optional per-series encoder state that the reference's accessors
+ * expose (extras may be NULL):
+ *   d_last_value: Encoder.LastEncoded().Value (encoder.go:305-319) -- the float in float mode,
+ *                 else the encoder's intVal: the SCALED integer in int mode and 0 when
+ *                 int_optimized == 0 (the reference never sets isFloat there);
+ *   d_out_bits  : stream length in bits incl. the end-of-stream marker, before the zero
+ *                 padding (splits the bytes into ts.Segment head / tail: the tail is the
+ *                 last ceil((pos + 11) / 8) bytes, pos = ((bits - 12) mod 8) + 1,
+ *                 scheme.go:198-211). */
+typedef struct m3tsz_encode_extras {
+  double *d_last_value;
+  uint64_t *d_out_bits;
+} m3tsz_encode_extras;
+int m3tsz_encode_batch_ex(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *d_ts,
+                          const double *d_val, uint64_t n_series, uint64_t points_stride,
+                          const uint32_t *d_n_points, const int64_t *d_start, int32_t unit,
+                          const uint8_t *d_units, const uint64_t *d_ann_series_off,
+                          const m3tsz_annotation_entry *d_ann_entries, const uint8_t *d_ann_bytes,
+                          uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_len, int32_t *d_status,
+                          const m3tsz_encode_extras *extras, void *stream);
+
+/* Worst-case stream bytes for n points without annotations (rounded up to 16),
+ * for a batch-wide unit (m3tsz_encode_bound) or with per-datapoint units
+ * (d_units given: every datapoint may add a time-unit marker and a raw 64-bit
+ * delta-of-delta, timestamp_encoder.go:130-164,197-205). */
 uint64_t m3tsz_encode_bound(uint64_t n_points);
+uint64_t m3tsz_encode_bound_units(uint64_t n_points, int per_datapoint_units);
+
+/* ------------------------------------------------------------------------
+ * Batch encode straight into ONE packed buffer (the fileset data-file layout,
+ * src/dbnode/persist/fs/write.go: concatenated segments + index entries that
+ * carry (Offset, Size), persist/schema/types.go:70-78) -- no per-series slots,
+ * no separate compaction pass.  Same inputs as m3tsz_encode_batch.  Stream s is
+ *   d_packed[d_offsets[s] .. d_offsets[s] + d_out_len[s])
+ * with every start rounded up to `align` bytes (1,4,8,16,32,64; >= 16 copies
+ * fastest, 64 decodes fastest).  Streams are placed in completion order, NOT in
+ * series order: d_offsets has n_series entries and is not monotonic; decode with
+ * m3tsz_decode_batch_ex (extras.d_lengths = d_out_len).  *d_total_bytes (device)
+ * receives the bytes used; a series that does not fit packed_capacity gets
+ * M3TSZ_ERR_CAPACITY and length 0.  slot_bytes = per-series staging bound (0 =
+ * m3tsz_encode_bound_units(points_stride, d_units != NULL); add the annotation
+ * bytes of the largest series when annotations are given).  d_packed must be
+ * 64-byte aligned.  The context keeps the staging slots (resident warps x 32 x
+ * slot_bytes, ~2 GB for 1440-point series on a B200), reused by every call.
+ * ---------------------------------------------------------------------- */
+int m3tsz_encode_batch_packed(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *d_ts,
+                              const double *d_val, uint64_t n_series, uint64_t points_stride,
+                              const uint32_t *d_n_points, const int64_t *d_start, int32_t unit,
+                              const uint8_t *d_units, const uint64_t *d_ann_series_off,
+                              const m3tsz_annotation_entry *d_ann_entries, const uint8_t *d_ann_bytes,
+                              uint64_t slot_bytes, uint32_t align, uint8_t *d_packed,
+                              uint64_t packed_capacity, uint64_t *d_offsets, uint64_t *d_out_len,
+                              int32_t *d_status, uint64_t *d_total_bytes, void *stream);
 
 /* Packs the per-series slots written by m3tsz_encode_batch into one contiguous
  * buffer (the fileset data-file layout, src/dbnode/persist/fs/write.go): fills
@@ -226,6 +320,20 @@ int m3tsz_decode_downsample_batch(m3tsz_ctx *ctx, const m3tsz_options *opts,
                                   int64_t range_start_ns, int64_t window_ns, uint32_t n_windows,
                                   double *d_sum, int64_t *d_count, double *d_min, double *d_max,
                                   uint32_t *d_n_points, int32_t *d_status, void *stream);
+
+/* Same, plus Gauge.Last() per window (gauge.go:73-84: the value with the latest
+ * timestamp, first arrival among equal timestamps; 0 for an empty window) in
+ * d_last, and optionally Gauge.LastAt() (ns; 0 for an empty window) in d_last_at
+ * (NULL: the context keeps it in scratch -- it is what lets an out-of-order
+ * datapoint re-open a committed window exactly).  Gauge.Mean() = sum / count
+ * (0 when count == 0) is left to the consumer (gauge.go:117-122). */
+int m3tsz_decode_downsample_last_batch(m3tsz_ctx *ctx, const m3tsz_options *opts,
+                                       const uint8_t *d_streams, uint64_t streams_bytes,
+                                       const uint64_t *d_offsets, uint64_t n_series,
+                                       int64_t range_start_ns, int64_t window_ns, uint32_t n_windows,
+                                       double *d_sum, int64_t *d_count, double *d_min, double *d_max,
+                                       double *d_last, int64_t *d_last_at, uint32_t *d_n_points,
+                                       int32_t *d_status, void *stream);
 
 int m3tsz_decode_downsample_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts,
                                        const uint8_t *h_streams, uint64_t streams_bytes,
@@ -279,6 +387,134 @@ int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *
                              const uint64_t *d_series_off, uint64_t n_series, int64_t start_ns,
                              int64_t end_ns, int32_t strategy, int64_t *d_ts_out, double *d_val_out,
                              uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Prometheus conversion epilogue: iteratorToPromResult,
+ * src/query/storage/prom_converter.go:42-120, over decoded / merged series that are
+ * already in HBM -- the last per-datapoint host loop of a fetch:
+ *   - timestamps ns -> ms (TimeToPromTimestamp, converter.go:388-391, truncating);
+ *   - value_decrease_tolerance > 0: a value that dips below its predecessor by less
+ *     than the tolerance, before tolerance_until_ns, is replaced by the predecessor
+ *     (the replaced value is the next predecessor), :68-72;
+ *   - d_handle_resets[s] != 0 (the host sets it when the series' first annotation says
+ *     OpenMetricsHandleValueResets and maxResolution >= the normalisation threshold,
+ *     :74-82): one sample per resolution_ns window holding the reset-aware cumulative
+ *     sum, stamped with the window's last datapoint, :84-98,113-118.
+ * Inputs [n_series][cap] + d_n_points; outputs [n_series][out_cap] + d_n_out (the
+ * number of samples; > out_cap => d_status M3TSZ_ERR_CAPACITY, first out_cap stored).
+ * d_handle_resets and d_status may be NULL.  In-place (outputs == inputs, out_cap ==
+ * cap) is allowed.
+ * ---------------------------------------------------------------------- */
+int m3tsz_prom_convert_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *d_val, uint64_t cap,
+                             const uint32_t *d_n_points, uint64_t n_series, int64_t resolution_ns,
+                             const uint8_t *d_handle_resets, double value_decrease_tolerance,
+                             int64_t tolerance_until_ns, int64_t *d_ts_ms_out, double *d_val_out,
+                             uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Tile aggregation: the compute of a storage.TileAggregator
+ * (src/dbnode/storage/types.go:1444-1472, AggregateTilesOptions{Start, End, Step};
+ * the open-source default is a no-op, storage/options.go:949-951).  For every
+ * source stream: decode, fold the datapoints of [start_ns, start_ns + n_windows *
+ * step_ns) into step-sized windows with the aggregator's Gauge
+ * (aggregation/gauge.go:73-106), emit one datapoint per NON-EMPTY window --
+ * timestamp = the window's end boundary (aggregator/list.go:541-543), value =
+ * Gauge.ValueOf(agg_type) (gauge.go:144-165) -- and re-encode them as the target
+ * namespace's M3TSZ stream (encoder start = start_ns, unit = out_unit), straight
+ * into one packed buffer (layout of m3tsz_encode_batch_packed: d_out_offsets[s],
+ * d_out_len[s], *d_total_bytes).  d_lengths may be NULL (CSR offsets).
+ * d_status[s]: the source stream's decode error if any (no output for that series),
+ * else the encoder's status.  d_n_tiles (optional): datapoints written per series.
+ * ---------------------------------------------------------------------- */
+enum { /* aggregation.Type ids, src/metrics/aggregation/type.go:31-38 */
+  M3TSZ_AGG_LAST = 1,
+  M3TSZ_AGG_MIN = 2,
+  M3TSZ_AGG_MAX = 3,
+  M3TSZ_AGG_MEAN = 4,
+  M3TSZ_AGG_COUNT = 6,
+  M3TSZ_AGG_SUM = 7
+};
+int m3tsz_aggregate_tiles_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *d_streams,
+                                uint64_t streams_bytes, const uint64_t *d_offsets,
+                                const uint64_t *d_lengths, uint64_t n_series, int64_t start_ns,
+                                int64_t step_ns, uint32_t n_windows, int32_t agg_type, int32_t out_unit,
+                                uint32_t align, uint8_t *d_packed, uint64_t packed_capacity,
+                                uint64_t *d_out_offsets, uint64_t *d_out_len, int32_t *d_status,
+                                uint32_t *d_n_tiles, uint64_t *d_total_bytes, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Per-series streaming handles: what a cgo shim binds METHOD FOR METHOD to the
+ * reference's interfaces (INTEGRATION.md §2 is that shim):
+ *   encoding.Encoder         src/dbnode/encoding/types.go:39-91   -> m3tsz_encoder_*
+ *   encoding.ReaderIterator  types.go:180-203, Decoder :342-345   -> m3tsz_iter_*
+ *   EncoderPool / ReaderIteratorPool  encoder_pool.go:27-48, iterator_pool.go:27-47 -> *_pool_*
+ * The handles keep host state only; bitstreams are produced / consumed by the
+ * batch kernels (one series per launch) lazily: an encoder when Len / Stream /
+ * Discard / LastEncoded is called, an iterator on its first Next().  Handles of one
+ * context serialise on the context's scratch; a handle itself is single-threaded like
+ * the reference's objects.  Error conventions are the reference's:
+ *   Encode on a closed encoder -> M3TSZ_ERR_ENCODER_CLOSED; a second/millisecond
+ *   delta-of-delta that overflows 32 bits -> M3TSZ_ERR_DOD_OVERFLOW; invalid unit ->
+ *   M3TSZ_ERR_UNRECOGNIZED_UNIT (the failing datapoint is dropped as a whole);
+ *   LastEncoded / LastAnnotationChecksum on an empty encoder -> M3TSZ_ERR_NO_DATAPOINTS;
+ *   iterator Err(): sticky status, visible after the Next() that failed; closed ->
+ *   M3TSZ_ERR_ITER_CLOSED.
+ * ---------------------------------------------------------------------- */
+typedef struct m3tsz_encoder m3tsz_encoder;
+typedef struct m3tsz_iter m3tsz_iter;
+typedef struct m3tsz_encoder_pool m3tsz_encoder_pool;
+typedef struct m3tsz_iter_pool m3tsz_iter_pool;
+
+/* m3tsz.NewEncoder(start, nil, intOptimized, opts), m3tsz/encoder.go:64-85 */
+int m3tsz_encoder_create(m3tsz_ctx *ctx, const m3tsz_options *opts, int64_t start_ns, m3tsz_encoder **out);
+void m3tsz_encoder_destroy(m3tsz_encoder *enc);
+/* Reset(start, capacity, schema), encoder.go:262-279 (re-opens a closed encoder) */
+int m3tsz_encoder_reset(m3tsz_encoder *enc, int64_t start_ns, uint64_t capacity);
+/* Encode(dp, unit, annotation), encoder.go:90-110 */
+int m3tsz_encoder_encode(m3tsz_encoder *enc, int64_t ts_ns, double value, int32_t unit,
+                         const uint8_t *annotation, uint64_t annotation_len);
+/* the delta-of-delta (in time units) of the last Encode that returned M3TSZ_ERR_DOD_OVERFLOW: the
+ * value the reference formats into its error ("deltaOfDelta value %d %s overflows 32 bits") */
+int64_t m3tsz_encoder_failed_dod(const m3tsz_encoder *enc);
+uint64_t m3tsz_encoder_num_encoded(const m3tsz_encoder *enc); /* NumEncoded, :299-302 */
+/* LastEncoded, :305-319: PrevTime and -- the reference's quirk, kept -- the float value in
+ * float mode, else the encoder's intVal: the SCALED integer in int mode, 0 when int_optimized == 0 */
+int m3tsz_encoder_last_encoded(m3tsz_encoder *enc, int64_t *ts_ns, double *value);
+/* LastAnnotationChecksum, :321-327: XXH64 (cespare/xxhash/v2) of the last annotation written */
+int m3tsz_encoder_last_annotation_checksum(const m3tsz_encoder *enc, uint64_t *checksum);
+int m3tsz_encoder_empty(const m3tsz_encoder *enc);              /* Empty, :330-332 */
+int m3tsz_encoder_len(m3tsz_encoder *enc, uint64_t *len);        /* Len, :336-354 (with the tail) */
+/* Stream(ctx), :282-297: copies head||tail into buf; *len == 0 <=> (nil, false).  *tail_len
+ * (optional) = bytes of the ts.Segment tail, so head = buf[0 .. len - tail_len). */
+int m3tsz_encoder_stream(m3tsz_encoder *enc, uint8_t *buf, uint64_t cap, uint64_t *len, uint64_t *tail_len);
+int m3tsz_encoder_close(m3tsz_encoder *enc);                    /* Close, :357-370 (idempotent) */
+/* Discard, :374-381 (segment + Close) / DiscardReset, :385-392 (segment + Reset) */
+int m3tsz_encoder_discard(m3tsz_encoder *enc, uint8_t *buf, uint64_t cap, uint64_t *len, uint64_t *tail_len);
+int m3tsz_encoder_discard_reset(m3tsz_encoder *enc, int64_t start_ns, uint64_t capacity, uint8_t *buf,
+                                uint64_t cap, uint64_t *len, uint64_t *tail_len);
+
+/* m3tsz.NewReaderIterator(nil, intOptimized, opts), m3tsz/iterator.go:67-78 */
+int m3tsz_iter_create(m3tsz_ctx *ctx, const m3tsz_options *opts, m3tsz_iter **out);
+void m3tsz_iter_destroy(m3tsz_iter *it);
+/* Reset(reader, schema), iterator.go:253-263: the handle copies the stream bytes */
+int m3tsz_iter_reset(m3tsz_iter *it, const uint8_t *data, uint64_t len);
+int m3tsz_iter_next(m3tsz_iter *it); /* Next, :81-106: 1 while a datapoint is current, else 0 */
+/* Current, :229-231: datapoint, the unit in force AT THIS datapoint, and its annotation
+ * (valid until the next call on this iterator; NULL / 0 when the datapoint has none) */
+int m3tsz_iter_current(const m3tsz_iter *it, int64_t *ts_ns, double *value, int32_t *unit,
+                       const uint8_t **annotation, uint64_t *annotation_len);
+int m3tsz_iter_err(const m3tsz_iter *it); /* Err, :234-236 */
+int m3tsz_iter_close(m3tsz_iter *it);     /* Close, :267-278 */
+
+/* EncoderPool.Init(alloc) / Get() / Put via Close(), encoder_pool.go:27-48 */
+int m3tsz_encoder_pool_create(m3tsz_ctx *ctx, const m3tsz_options *opts, uint64_t size,
+                              m3tsz_encoder_pool **out);
+int m3tsz_encoder_pool_get(m3tsz_encoder_pool *pool, m3tsz_encoder **out);
+void m3tsz_encoder_pool_destroy(m3tsz_encoder_pool *pool);
+/* ReaderIteratorPool, iterator_pool.go:27-47 (the pooled iterators are created with a nil reader) */
+int m3tsz_iter_pool_create(m3tsz_ctx *ctx, const m3tsz_options *opts, uint64_t size, m3tsz_iter_pool **out);
+int m3tsz_iter_pool_get(m3tsz_iter_pool *pool, m3tsz_iter **out);
+void m3tsz_iter_pool_destroy(m3tsz_iter_pool *pool);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,8 @@ ERR_INVALID_ARG = 101
 ERR_CUDA = 102
 ERR_NO_DEVICE = 103
 
+AGG_LAST, AGG_MIN, AGG_MAX, AGG_MEAN, AGG_COUNT, AGG_SUM = 1, 2, 3, 4, 6, 7  # aggregation.Type ids
+
 UNIT_NONE, UNIT_S, UNIT_MS, UNIT_US, UNIT_NS, UNIT_MIN, UNIT_HOUR, UNIT_DAY, UNIT_YEAR = range(9)
 
 
@@ -32,6 +34,22 @@ class Options(C.Structure):
 
 class AnnotationRef(C.Structure):
     _fields_ = [("bit_offset", C.c_uint64), ("length", C.c_uint32), ("count", C.c_uint32)]
+
+
+class DpEvent(C.Structure):
+    """m3tsz_dp_event: per-datapoint unit change / annotation (include/m3tsz_b200.h)."""
+    _fields_ = [("series", C.c_uint64), ("dp_index", C.c_uint32), ("kind", C.c_uint16),
+                ("unit", C.c_uint16), ("bit_offset", C.c_uint64), ("length", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+EVENT_TIME_UNIT, EVENT_ANNOTATION = 1, 2
+
+
+class DecodeExtras(C.Structure):
+    """m3tsz_decode_extras."""
+    _fields_ = [("d_lengths", C.c_void_p), ("d_unit_first", C.c_void_p), ("d_events", C.c_void_p),
+                ("events_capacity", C.c_uint64), ("d_event_count", C.c_void_p)]
 
 
 class AnnotationEntry(C.Structure):
@@ -54,6 +72,17 @@ EXPORTED_SYMBOLS = [
     "m3tsz_decode_batch_host", "m3tsz_encode_batch", "m3tsz_encode_bound",
     "m3tsz_compact_streams", "m3tsz_encode_batch_host", "m3tsz_decode_downsample_batch",
     "m3tsz_decode_downsample_batch_host", "m3tsz_merge_series_batch", "m3tsz_checksum_batch",
+    "m3tsz_decode_batch_ex", "m3tsz_decode_downsample_last_batch", "m3tsz_encode_bound_units",
+    "m3tsz_encode_batch_packed", "m3tsz_prom_convert_batch", "m3tsz_aggregate_tiles_batch",
+    "m3tsz_encode_batch_ex",
+    "m3tsz_encoder_create", "m3tsz_encoder_destroy", "m3tsz_encoder_reset", "m3tsz_encoder_encode",
+    "m3tsz_encoder_num_encoded", "m3tsz_encoder_failed_dod", "m3tsz_encoder_last_encoded", "m3tsz_encoder_last_annotation_checksum",
+    "m3tsz_encoder_empty", "m3tsz_encoder_len", "m3tsz_encoder_stream", "m3tsz_encoder_close",
+    "m3tsz_encoder_discard", "m3tsz_encoder_discard_reset",
+    "m3tsz_iter_create", "m3tsz_iter_destroy", "m3tsz_iter_reset", "m3tsz_iter_next", "m3tsz_iter_current",
+    "m3tsz_iter_err", "m3tsz_iter_close",
+    "m3tsz_encoder_pool_create", "m3tsz_encoder_pool_get", "m3tsz_encoder_pool_destroy",
+    "m3tsz_iter_pool_create", "m3tsz_iter_pool_get", "m3tsz_iter_pool_destroy",
 ]
 
 
@@ -85,6 +114,77 @@ def lib():
     L.m3tsz_encode_bound.argtypes = [u64]
     L.m3tsz_decode_batch.restype = C.c_int
     L.m3tsz_decode_batch.argtypes = [vp, po, vp, u64, vp, u64, vp, vp, u64, vp, vp, vp, vp, vp]
+    L.m3tsz_encode_bound_units.restype = u64
+    L.m3tsz_encode_bound_units.argtypes = [u64, C.c_int]
+    L.m3tsz_encode_batch_packed.restype = C.c_int
+    L.m3tsz_encode_batch_packed.argtypes = [vp, po, vp, vp, u64, u64, vp, vp, i32, vp, vp, vp, vp, u64, u32,
+                                            vp, u64, vp, vp, vp, vp, vp]
+    pv, pu64 = C.POINTER(vp), C.POINTER(u64)
+    L.m3tsz_encode_batch_ex.restype = C.c_int
+    L.m3tsz_encode_batch_ex.argtypes = [vp, po, vp, vp, u64, u64, vp, vp, i32, vp, vp, vp, vp, vp, u64,
+                                        vp, vp, vp, vp]
+    L.m3tsz_encoder_create.restype = C.c_int
+    L.m3tsz_encoder_create.argtypes = [vp, po, i64, pv]
+    L.m3tsz_encoder_destroy.restype = None
+    L.m3tsz_encoder_destroy.argtypes = [vp]
+    L.m3tsz_encoder_reset.restype = C.c_int
+    L.m3tsz_encoder_reset.argtypes = [vp, i64, u64]
+    L.m3tsz_encoder_encode.restype = C.c_int
+    L.m3tsz_encoder_encode.argtypes = [vp, i64, C.c_double, i32, C.c_char_p, u64]
+    L.m3tsz_encoder_failed_dod.restype = i64
+    L.m3tsz_encoder_failed_dod.argtypes = [vp]
+    L.m3tsz_encoder_num_encoded.restype = u64
+    L.m3tsz_encoder_num_encoded.argtypes = [vp]
+    L.m3tsz_encoder_last_encoded.restype = C.c_int
+    L.m3tsz_encoder_last_encoded.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double)]
+    L.m3tsz_encoder_last_annotation_checksum.restype = C.c_int
+    L.m3tsz_encoder_last_annotation_checksum.argtypes = [vp, pu64]
+    L.m3tsz_encoder_empty.restype = C.c_int
+    L.m3tsz_encoder_empty.argtypes = [vp]
+    L.m3tsz_encoder_len.restype = C.c_int
+    L.m3tsz_encoder_len.argtypes = [vp, pu64]
+    for f in ("m3tsz_encoder_stream", "m3tsz_encoder_discard"):
+        getattr(L, f).restype = C.c_int
+        getattr(L, f).argtypes = [vp, vp, u64, pu64, pu64]
+    L.m3tsz_encoder_discard_reset.restype = C.c_int
+    L.m3tsz_encoder_discard_reset.argtypes = [vp, i64, u64, vp, u64, pu64, pu64]
+    L.m3tsz_encoder_close.restype = C.c_int
+    L.m3tsz_encoder_close.argtypes = [vp]
+    L.m3tsz_iter_create.restype = C.c_int
+    L.m3tsz_iter_create.argtypes = [vp, po, pv]
+    L.m3tsz_iter_destroy.restype = None
+    L.m3tsz_iter_destroy.argtypes = [vp]
+    L.m3tsz_iter_reset.restype = C.c_int
+    L.m3tsz_iter_reset.argtypes = [vp, C.c_char_p, u64]
+    L.m3tsz_iter_next.restype = C.c_int
+    L.m3tsz_iter_next.argtypes = [vp]
+    L.m3tsz_iter_current.restype = C.c_int
+    L.m3tsz_iter_current.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i32), pv, pu64]
+    L.m3tsz_iter_err.restype = C.c_int
+    L.m3tsz_iter_err.argtypes = [vp]
+    L.m3tsz_iter_close.restype = C.c_int
+    L.m3tsz_iter_close.argtypes = [vp]
+    for f in ("m3tsz_encoder_pool_create", "m3tsz_iter_pool_create"):
+        getattr(L, f).restype = C.c_int
+        getattr(L, f).argtypes = [vp, po, u64, pv]
+    for f in ("m3tsz_encoder_pool_get", "m3tsz_iter_pool_get"):
+        getattr(L, f).restype = C.c_int
+        getattr(L, f).argtypes = [vp, pv]
+    for f in ("m3tsz_encoder_pool_destroy", "m3tsz_iter_pool_destroy"):
+        getattr(L, f).restype = None
+        getattr(L, f).argtypes = [vp]
+    L.m3tsz_prom_convert_batch.restype = C.c_int
+    L.m3tsz_prom_convert_batch.argtypes = [vp, vp, vp, u64, vp, u64, i64, vp, C.c_double, i64, vp, vp, u64,
+                                           vp, vp, vp]
+    L.m3tsz_aggregate_tiles_batch.restype = C.c_int
+    L.m3tsz_aggregate_tiles_batch.argtypes = [vp, po, vp, u64, vp, vp, u64, i64, i64, u32, i32, i32, u32, vp,
+                                              u64, vp, vp, vp, vp, vp, vp]
+    L.m3tsz_decode_batch_ex.restype = C.c_int
+    L.m3tsz_decode_batch_ex.argtypes = [vp, po, vp, u64, vp, u64, vp, vp, u64, vp, vp, vp, vp,
+                                        C.POINTER(DecodeExtras), vp]
+    L.m3tsz_decode_downsample_last_batch.restype = C.c_int
+    L.m3tsz_decode_downsample_last_batch.argtypes = [vp, po, vp, u64, vp, u64, i64, i64, u32, vp, vp, vp,
+                                                     vp, vp, vp, vp, vp, vp]
     L.m3tsz_decode_batch_host.restype = C.c_int
     L.m3tsz_decode_batch_host.argtypes = [vp, po, vp, u64, vp, u64, vp, vp, u64, vp, vp, vp, vp]
     L.m3tsz_encode_batch.restype = C.c_int

@@ -29,6 +29,9 @@ class DecodeResult:
     status: torch.Tensor    # int32 [S]
     unit: torch.Tensor      # uint8 [S]
     annotations: Optional[torch.Tensor]  # uint8 view of m3tsz_annotation_ref [S, 16] or None
+    unit_first: Optional[torch.Tensor] = None   # uint8 [S]: unit in force at the first datapoint
+    events: Optional[torch.Tensor] = None       # uint8 [E, 32] view of m3tsz_dp_event (want_events)
+    event_count: Optional[torch.Tensor] = None  # int64 [1]: events produced (may exceed E)
 
 
 @dataclass
@@ -39,6 +42,15 @@ class EncodeResult:
 
 
 @dataclass
+class PackedResult:
+    packed: torch.Tensor   # uint8 [capacity]
+    offsets: torch.Tensor  # int64 [S] start of every stream (completion order, not monotonic)
+    out_len: torch.Tensor  # int64 [S]
+    status: torch.Tensor   # int32 [S]
+    total: torch.Tensor    # int64 [1] bytes used
+
+
+@dataclass
 class DownsampleResult:
     sum: torch.Tensor    # float64 [W, S] (window-major)
     count: torch.Tensor  # int64 [W, S]
@@ -46,6 +58,8 @@ class DownsampleResult:
     max: torch.Tensor    # float64 [W, S]
     n_points: torch.Tensor
     status: torch.Tensor
+    last: Optional[torch.Tensor] = None     # float64 [W, S] Gauge.Last() (want_last)
+    last_at: Optional[torch.Tensor] = None  # int64 [W, S] Gauge.LastAt() in ns
 
 
 class BatchCodec:
@@ -63,12 +77,45 @@ class BatchCodec:
 
     # ------------------------------------------------------------------ decode
     def decode(self, streams: torch.Tensor, offsets: torch.Tensor, max_points: int,
-               want_annotations=False, out: Optional[DecodeResult] = None) -> DecodeResult:
-        """streams: uint8 [total] on device; offsets: int64 [S+1] on device (byte offsets)."""
+               want_annotations=False, out: Optional[DecodeResult] = None,
+               lengths: Optional[torch.Tensor] = None, want_events=0) -> DecodeResult:
+        """streams: uint8 [total] on device; offsets: int64 [S+1] on device (byte offsets), or
+        int64 [S] starts + `lengths` int64 [S] (streams placed anywhere, index-entry style).
+        want_events = capacity of the per-datapoint unit / annotation event table (0: none)."""
         assert streams.dtype == torch.uint8 and streams.is_cuda and streams.is_contiguous()
         assert offsets.dtype == torch.int64 and offsets.is_cuda and offsets.is_contiguous()
-        S = offsets.numel() - 1
+        S = offsets.numel() - 1 if lengths is None else lengths.numel()
         dev = self.device
+        if lengths is not None or want_events:
+            if out is None:
+                out = DecodeResult(
+                    ts=torch.empty((S, max_points), dtype=torch.int64, device=dev),
+                    values=torch.empty((S, max_points), dtype=torch.float64, device=dev),
+                    n_points=torch.empty(S, dtype=torch.int32, device=dev),
+                    status=torch.empty(S, dtype=torch.int32, device=dev),
+                    unit=torch.empty(S, dtype=torch.uint8, device=dev),
+                    annotations=(torch.empty((S, 16), dtype=torch.uint8, device=dev)
+                                 if want_annotations else None))
+            ex = capi.DecodeExtras()
+            ex.d_lengths = lengths.data_ptr() if lengths is not None else None
+            if want_events:
+                if out.unit_first is None:
+                    out.unit_first = torch.empty(S, dtype=torch.uint8, device=dev)
+                if out.events is None or out.events.shape[0] < want_events:
+                    out.events = torch.zeros((int(want_events), 32), dtype=torch.uint8, device=dev)
+                if out.event_count is None:
+                    out.event_count = torch.zeros(1, dtype=torch.int64, device=dev)
+                out.event_count.zero_()
+                ex.d_unit_first = out.unit_first.data_ptr()
+                ex.d_events = out.events.data_ptr()
+                ex.events_capacity = int(out.events.shape[0])
+                ex.d_event_count = out.event_count.data_ptr()
+            rc = capi.lib().m3tsz_decode_batch_ex(
+                self.ctx.handle, C.byref(self.opts), _ptr(streams), streams.numel(), _ptr(offsets), S,
+                _ptr(out.ts), _ptr(out.values), max_points, _ptr(out.n_points), _ptr(out.status),
+                _ptr(out.unit), _ptr(out.annotations), C.byref(ex), _cuda_stream_ptr(dev))
+            self.ctx.check(rc, "m3tsz_decode_batch_ex")
+            return out
         if out is None:
             out = DecodeResult(
                 ts=torch.empty((S, max_points), dtype=torch.int64, device=dev),
@@ -86,11 +133,26 @@ class BatchCodec:
         return out
 
     def decode_downsample(self, streams, offsets, range_start_ns, window_ns, n_windows,
-                          out: Optional[DownsampleResult] = None) -> DownsampleResult:
+                          out: Optional[DownsampleResult] = None, want_last=False) -> DownsampleResult:
         assert streams.dtype == torch.uint8 and streams.is_cuda
         assert offsets.dtype == torch.int64 and offsets.is_cuda
         S = offsets.numel() - 1
         dev = self.device
+        if want_last:
+            if out is None:
+                mk = lambda dt: torch.empty((n_windows, S), dtype=dt, device=dev)
+                out = DownsampleResult(
+                    sum=mk(torch.float64), count=mk(torch.int64), min=mk(torch.float64),
+                    max=mk(torch.float64), n_points=torch.empty(S, dtype=torch.int32, device=dev),
+                    status=torch.empty(S, dtype=torch.int32, device=dev), last=mk(torch.float64),
+                    last_at=mk(torch.int64))
+            rc = capi.lib().m3tsz_decode_downsample_last_batch(
+                self.ctx.handle, C.byref(self.opts), _ptr(streams), streams.numel(), _ptr(offsets), S,
+                int(range_start_ns), int(window_ns), int(n_windows), _ptr(out.sum), _ptr(out.count),
+                _ptr(out.min), _ptr(out.max), _ptr(out.last), _ptr(out.last_at), _ptr(out.n_points),
+                _ptr(out.status), _cuda_stream_ptr(dev))
+            self.ctx.check(rc, "m3tsz_decode_downsample_last_batch")
+            return out
         if out is None:
             out = DownsampleResult(
                 sum=torch.empty((n_windows, S), dtype=torch.float64, device=dev),
@@ -140,6 +202,34 @@ class BatchCodec:
         self.ctx.check(rc, "m3tsz_encode_batch")
         return out
 
+    def encode_packed(self, ts, values, start, unit=capi.UNIT_S, n_points=None, units=None,
+                      annotations=None, align=64, capacity: Optional[int] = None, slot_bytes=0,
+                      out: Optional["PackedResult"] = None) -> "PackedResult":
+        """Encodes straight into one packed buffer (no slots, no compaction pass).  Streams are
+        placed in completion order: stream s = packed[offsets[s] : offsets[s] + out_len[s]]."""
+        S, P = ts.shape
+        dev = self.device
+        if out is None:
+            if capacity is None:
+                capacity = S * (self.encode_bound(P) if units is None else
+                                int(capi.lib().m3tsz_encode_bound_units(P, 1)))
+            out = PackedResult(
+                packed=torch.empty(capacity, dtype=torch.uint8, device=dev),
+                offsets=torch.empty(S, dtype=torch.int64, device=dev),
+                out_len=torch.empty(S, dtype=torch.int64, device=dev),
+                status=torch.empty(S, dtype=torch.int32, device=dev),
+                total=torch.zeros(1, dtype=torch.int64, device=dev))
+        a_off = a_ent = a_bytes = None
+        if annotations is not None:
+            a_off, a_ent, a_bytes = annotations
+        rc = capi.lib().m3tsz_encode_batch_packed(
+            self.ctx.handle, C.byref(self.opts), _ptr(ts), _ptr(values), S, P, _ptr(n_points),
+            _ptr(start), int(unit), _ptr(units), _ptr(a_off), _ptr(a_ent), _ptr(a_bytes),
+            int(slot_bytes), int(align), _ptr(out.packed), out.packed.numel(), _ptr(out.offsets),
+            _ptr(out.out_len), _ptr(out.status), _ptr(out.total), _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_encode_batch_packed")
+        return out
+
     def compact(self, enc: EncodeResult, align=64, capacity: Optional[int] = None):
         """Packs slots into (packed uint8 [total], offsets int64 [S+1])."""
         S, stride = enc.out.shape
@@ -173,6 +263,51 @@ class BatchCodec:
             _cuda_stream_ptr(dev))
         self.ctx.check(rc, "m3tsz_merge_series_batch")
         return ts_out, val_out, n_out, status
+
+    # ------------------------------------------------------------ query-side consumers (rows N3, N4)
+    def prom_convert(self, ts, values, n_points, resolution_ns=0, handle_resets=None, tolerance=0.0,
+                     tolerance_until_ns=0, out_cap=None):
+        """iteratorToPromResult over decoded / merged series in HBM.  Returns
+        (ts_ms int64 [S,out_cap], values float64 [S,out_cap], n_out int32 [S], status int32 [S])."""
+        S, cap = ts.shape
+        dev = self.device
+        if out_cap is None:
+            out_cap = cap + 1 if handle_resets is not None else cap
+        ts_out = torch.empty((S, out_cap), dtype=torch.int64, device=dev)
+        val_out = torch.empty((S, out_cap), dtype=torch.float64, device=dev)
+        n_out = torch.empty(S, dtype=torch.int32, device=dev)
+        status = torch.empty(S, dtype=torch.int32, device=dev)
+        rc = capi.lib().m3tsz_prom_convert_batch(
+            self.ctx.handle, _ptr(ts), _ptr(values), cap, _ptr(n_points), S, int(resolution_ns),
+            _ptr(handle_resets), float(tolerance), int(tolerance_until_ns), _ptr(ts_out), _ptr(val_out),
+            out_cap, _ptr(n_out), _ptr(status), _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_prom_convert_batch")
+        return ts_out, val_out, n_out, status
+
+    def aggregate_tiles(self, streams, offsets, start_ns, step_ns, n_windows, agg_type=capi.AGG_LAST,
+                        out_unit=capi.UNIT_S, lengths=None, align=64, capacity=None,
+                        out: Optional["PackedResult"] = None):
+        """storage.TileAggregator compute: decode -> Gauge per Step window -> re-encode (packed).
+        Returns (PackedResult, n_tiles int32 [S])."""
+        S = offsets.numel() - 1 if lengths is None else lengths.numel()
+        dev = self.device
+        if out is None:
+            if capacity is None:
+                capacity = S * self.encode_bound(n_windows)
+            out = PackedResult(
+                packed=torch.empty(capacity, dtype=torch.uint8, device=dev),
+                offsets=torch.empty(S, dtype=torch.int64, device=dev),
+                out_len=torch.empty(S, dtype=torch.int64, device=dev),
+                status=torch.empty(S, dtype=torch.int32, device=dev),
+                total=torch.zeros(1, dtype=torch.int64, device=dev))
+        n_tiles = torch.empty(S, dtype=torch.int32, device=dev)
+        rc = capi.lib().m3tsz_aggregate_tiles_batch(
+            self.ctx.handle, C.byref(self.opts), _ptr(streams), streams.numel(), _ptr(offsets),
+            _ptr(lengths), S, int(start_ns), int(step_ns), int(n_windows), int(agg_type), int(out_unit),
+            int(align), _ptr(out.packed), out.packed.numel(), _ptr(out.offsets), _ptr(out.out_len),
+            _ptr(out.status), _ptr(n_tiles), _ptr(out.total), _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_aggregate_tiles_batch")
+        return out, n_tiles
 
     def segment_checksums(self, streams, offsets, lengths=None, expected=None):
         """Adler-32 of every stream (ts.Segment.CalculateChecksum, src/dbnode/ts/segment.go:60-76)

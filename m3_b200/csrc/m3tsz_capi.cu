@@ -14,86 +14,11 @@
 #include "m3tsz_common.cuh"
 #include "m3tsz_kernels.h"
 
+#include "m3tsz_ctx.h"
+
 using namespace m3tsz;
 
-struct Scratch {
-  void *ptr = nullptr;
-  size_t bytes = 0;
-};
-
-struct m3tsz_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;   // used by the *_host entry points
-  cudaStream_t stream2 = nullptr;  // second lane of the chunked H2D / kernel / D2H pipeline
-  cudaEvent_t ev = nullptr;
-  uint64_t launches = 0;
-  char last_error[256] = {0};
-  Scratch s[40];
-  int32_t *d_flag = nullptr;  // [2]
-  void *h_stage[2] = {nullptr, nullptr};  // pinned staging for per-chunk offsets
-  size_t h_stage_bytes[2] = {0, 0};
-};
-
-namespace {
-
-int set_cuda_error(m3tsz_ctx *ctx, cudaError_t e, const char *where) {
-  if (ctx) snprintf(ctx->last_error, sizeof(ctx->last_error), "%s: %s", where, cudaGetErrorString(e));
-  return M3TSZ_ERR_CUDA;
-}
-
-#define CK(call)                                                 \
-  do {                                                           \
-    cudaError_t _e = (call);                                     \
-    if (_e != cudaSuccess) return set_cuda_error(ctx, _e, #call); \
-  } while (0)
-
-int ensure(m3tsz_ctx *ctx, int slot, size_t bytes, void **out) {
-  Scratch &sc = ctx->s[slot];
-  if (bytes == 0) bytes = 16;
-  if (sc.bytes < bytes) {
-    if (sc.ptr) CK(cudaFree(sc.ptr));
-    sc.ptr = nullptr;
-    sc.bytes = 0;
-    size_t want = bytes + bytes / 8;  // grow-only with slack
-    cudaError_t e = cudaMalloc(&sc.ptr, want);
-    if (e != cudaSuccess) {
-      (void)cudaGetLastError();
-      want = bytes;
-      CK(cudaMalloc(&sc.ptr, want));
-    }
-    sc.bytes = want;
-  }
-  *out = sc.ptr;
-  return M3TSZ_OK;
-}
-
-int ensure_stage(m3tsz_ctx *ctx, int i, size_t bytes) {
-  if (ctx->h_stage_bytes[i] >= bytes) return M3TSZ_OK;
-  if (ctx->h_stage[i]) CK(cudaFreeHost(ctx->h_stage[i]));
-  ctx->h_stage[i] = nullptr;
-  ctx->h_stage_bytes[i] = 0;
-  CK(cudaMallocHost(&ctx->h_stage[i], bytes));
-  ctx->h_stage_bytes[i] = bytes;
-  return M3TSZ_OK;
-}
-
-// Series per pipeline chunk: ~8 chunks per call, but never tiny ones.
-uint64_t pick_chunk(uint64_t n_series, uint64_t bytes_per_series) {
-  uint64_t ch = (n_series + 7) / 8;
-  uint64_t min_ch = (16ull << 20) / (bytes_per_series ? bytes_per_series : 1);
-  if (min_ch < 2048) min_ch = 2048;
-  if (ch < min_ch) ch = min_ch;
-  if (ch > n_series) ch = n_series;
-  ch = (ch + 127) & ~127ull;  // whole thread blocks
-  return ch;
-}
-
-bool valid_opts(const m3tsz_options *o) {
-  return o && (o->int_optimized == 0 || o->int_optimized == 1) && o->default_time_unit >= 0 &&
-         o->default_time_unit <= 8;
-}
-
-}  // namespace
+using namespace m3tsz::host;
 
 extern "C" {
 
@@ -169,27 +94,33 @@ void m3tsz_ctx_destroy(m3tsz_ctx *ctx) {
 const char *m3tsz_last_cuda_error(const m3tsz_ctx *ctx) { return ctx ? ctx->last_error : ""; }
 uint64_t m3tsz_ctx_launch_count(const m3tsz_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
-uint64_t m3tsz_encode_bound(uint64_t n) {
-  // 64-bit start + per datapoint <= 68 (timestamp) + 80 (value) bits + 11-bit
-  // end-of-stream marker, plus the write-ahead guard the kernel keeps.
-  uint64_t bits = 64 + n * 148 + 11;
+uint64_t m3tsz_encode_bound_units(uint64_t n, int per_datapoint_units) {
+  // 64-bit start + per datapoint <= 68 (timestamp: '1111' + 64-bit delta-of-delta) + 80 (value:
+  // 3 control bits + 13-bit int header + 64 bits) bits + 11-bit end-of-stream marker, plus the
+  // write-ahead guard the kernel keeps.  With per-datapoint units a datapoint may also carry a
+  // time-unit marker (11 + 8 bits) and then a raw 64-bit delta-of-delta: 83 bits of timestamp.
+  const uint64_t per_dp = per_datapoint_units ? (83 + 80) : (68 + 80);
+  uint64_t bits = 64 + n * per_dp + 11;
   uint64_t bytes = (bits + 7) / 8 + 64;
   return (bytes + 15) & ~15ull;
 }
+uint64_t m3tsz_encode_bound(uint64_t n) { return m3tsz_encode_bound_units(n, 0); }
 
 // --------------------------------------------------------------------------
-int m3tsz_decode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *d_streams,
-                       uint64_t streams_bytes, const uint64_t *d_offsets, uint64_t n_series,
-                       int64_t *d_ts, double *d_val, uint64_t max_points, uint32_t *d_n_points,
-                       int32_t *d_status, uint8_t *d_unit, m3tsz_annotation_ref *d_ann,
-                       void *stream) {
+int m3tsz_decode_batch_ex(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *d_streams,
+                          uint64_t streams_bytes, const uint64_t *d_offsets, uint64_t n_series,
+                          int64_t *d_ts, double *d_val, uint64_t max_points, uint32_t *d_n_points,
+                          int32_t *d_status, uint8_t *d_unit, m3tsz_annotation_ref *d_ann,
+                          const m3tsz_decode_extras *ex, void *stream) {
   if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
   if (n_series == 0) return M3TSZ_OK;
   if (!d_streams || !d_offsets || !d_ts || !d_val || max_points == 0 ||
       max_points >= (1ull << 27) || ((uintptr_t)d_streams & 15u) ||
       streams_bytes >= (1ull << 34))  // 32-bit word / byte offsets inside the kernel; split larger batches
     return M3TSZ_ERR_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+  if (ex && ex->d_events && (!ex->d_event_count || ex->events_capacity == 0)) return M3TSZ_ERR_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   DecodeParams p;
   memset(&p, 0, sizeof(p));
   p.streams = d_streams;
@@ -204,7 +135,73 @@ int m3tsz_decode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t 
   p.status = d_status;
   p.unit_out = d_unit;
   p.ann_out = d_ann;
-  CK(launch_decode(p, opts->int_optimized != 0, false, (cudaStream_t)stream));
+  if (ex) {
+    p.lengths = ex->d_lengths;
+    p.unit_first_out = ex->d_unit_first;
+    if (ex->d_events) {
+      p.events = ex->d_events;
+      p.events_capacity = ex->events_capacity;
+      p.event_count = reinterpret_cast<unsigned long long *>(ex->d_event_count);
+    }
+  }
+  CK(launch_decode(p, opts->int_optimized != 0, 0, (cudaStream_t)stream));
+  ctx->launches++;
+  return M3TSZ_OK;
+}
+
+int m3tsz_decode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *d_streams,
+                       uint64_t streams_bytes, const uint64_t *d_offsets, uint64_t n_series,
+                       int64_t *d_ts, double *d_val, uint64_t max_points, uint32_t *d_n_points,
+                       int32_t *d_status, uint8_t *d_unit, m3tsz_annotation_ref *d_ann,
+                       void *stream) {
+  return m3tsz_decode_batch_ex(ctx, opts, d_streams, streams_bytes, d_offsets, n_series, d_ts, d_val,
+                               max_points, d_n_points, d_status, d_unit, d_ann, nullptr, stream);
+}
+
+static int downsample_impl(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *d_streams,
+                           uint64_t streams_bytes, const uint64_t *d_offsets, const uint64_t *d_lengths,
+                           uint64_t n_series,
+                           int64_t range_start_ns, int64_t window_ns, uint32_t n_windows, double *d_sum,
+                           int64_t *d_count, double *d_min, double *d_max, double *d_last,
+                           int64_t *d_last_at, bool want_last, uint32_t *d_n_points, int32_t *d_status,
+                           void *stream) {
+  if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
+  if (n_series == 0) return M3TSZ_OK;
+  if (!d_streams || !d_offsets || !d_sum || !d_count || !d_min || !d_max || window_ns <= 0 ||
+      n_windows == 0 || n_windows > 0x7fffffffu || ((uintptr_t)d_streams & 15u) ||
+      streams_bytes >= (1ull << 34) || (want_last && !d_last))
+    return M3TSZ_ERR_INVALID_ARG;
+  // range_start + n_windows*window must not overflow int64
+  if ((__int128)range_start_ns + (__int128)n_windows * (__int128)window_ns > (__int128)INT64_MAX)
+    return M3TSZ_ERR_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
+  if (want_last && !d_last_at) {  // lastAt lives in context scratch
+    void *sc = nullptr;
+    int rc = ensure(ctx, 12, (size_t)n_series * n_windows * 8, &sc);
+    if (rc) return rc;
+    d_last_at = (int64_t *)sc;
+  }
+  DecodeParams p;
+  memset(&p, 0, sizeof(p));
+  p.streams = d_streams;
+  p.streams_bytes = streams_bytes;
+  p.offsets = d_offsets;
+  p.lengths = d_lengths;
+  p.n_series = n_series;
+  p.default_unit = opts->default_time_unit;
+  p.range_start = range_start_ns;
+  p.window = window_ns;
+  p.n_windows = n_windows;
+  p.ds_sum = d_sum;
+  p.ds_count = d_count;
+  p.ds_min = d_min;
+  p.ds_max = d_max;
+  p.ds_last = d_last;
+  p.ds_last_at = d_last_at;
+  p.n_points = d_n_points;
+  p.status = d_status;
+  CK(launch_decode(p, opts->int_optimized != 0, want_last ? 2 : 1, (cudaStream_t)stream));
   ctx->launches++;
   return M3TSZ_OK;
 }
@@ -215,43 +212,30 @@ int m3tsz_decode_downsample_batch(m3tsz_ctx *ctx, const m3tsz_options *opts,
                                   int64_t range_start_ns, int64_t window_ns, uint32_t n_windows,
                                   double *d_sum, int64_t *d_count, double *d_min, double *d_max,
                                   uint32_t *d_n_points, int32_t *d_status, void *stream) {
-  if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
-  if (n_series == 0) return M3TSZ_OK;
-  if (!d_streams || !d_offsets || !d_sum || !d_count || !d_min || !d_max || window_ns <= 0 ||
-      n_windows == 0 || ((uintptr_t)d_streams & 15u) || streams_bytes >= (1ull << 34))
-    return M3TSZ_ERR_INVALID_ARG;
-  // range_start + n_windows*window must not overflow int64
-  if ((__int128)range_start_ns + (__int128)n_windows * (__int128)window_ns > (__int128)INT64_MAX)
-    return M3TSZ_ERR_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
-  DecodeParams p;
-  memset(&p, 0, sizeof(p));
-  p.streams = d_streams;
-  p.streams_bytes = streams_bytes;
-  p.offsets = d_offsets;
-  p.n_series = n_series;
-  p.default_unit = opts->default_time_unit;
-  p.range_start = range_start_ns;
-  p.window = window_ns;
-  p.n_windows = n_windows;
-  p.ds_sum = d_sum;
-  p.ds_count = d_count;
-  p.ds_min = d_min;
-  p.ds_max = d_max;
-  p.n_points = d_n_points;
-  p.status = d_status;
-  CK(launch_decode(p, opts->int_optimized != 0, true, (cudaStream_t)stream));
-  ctx->launches++;
-  return M3TSZ_OK;
+  return downsample_impl(ctx, opts, d_streams, streams_bytes, d_offsets, nullptr, n_series, range_start_ns,
+                         window_ns, n_windows, d_sum, d_count, d_min, d_max, nullptr, nullptr, false,
+                         d_n_points, d_status, stream);
 }
 
-int m3tsz_encode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *d_ts,
-                       const double *d_val, uint64_t n_series, uint64_t points_stride,
-                       const uint32_t *d_n_points, const int64_t *d_start, int32_t unit,
-                       const uint8_t *d_units, const uint64_t *d_ann_series_off,
-                       const m3tsz_annotation_entry *d_ann_entries, const uint8_t *d_ann_bytes,
-                       uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_len, int32_t *d_status,
-                       void *stream) {
+int m3tsz_decode_downsample_last_batch(m3tsz_ctx *ctx, const m3tsz_options *opts,
+                                       const uint8_t *d_streams, uint64_t streams_bytes,
+                                       const uint64_t *d_offsets, uint64_t n_series,
+                                       int64_t range_start_ns, int64_t window_ns, uint32_t n_windows,
+                                       double *d_sum, int64_t *d_count, double *d_min, double *d_max,
+                                       double *d_last, int64_t *d_last_at, uint32_t *d_n_points,
+                                       int32_t *d_status, void *stream) {
+  return downsample_impl(ctx, opts, d_streams, streams_bytes, d_offsets, nullptr, n_series, range_start_ns,
+                         window_ns, n_windows, d_sum, d_count, d_min, d_max, d_last, d_last_at, true,
+                         d_n_points, d_status, stream);
+}
+
+int m3tsz_encode_batch_ex(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *d_ts,
+                          const double *d_val, uint64_t n_series, uint64_t points_stride,
+                          const uint32_t *d_n_points, const int64_t *d_start, int32_t unit,
+                          const uint8_t *d_units, const uint64_t *d_ann_series_off,
+                          const m3tsz_annotation_entry *d_ann_entries, const uint8_t *d_ann_bytes,
+                          uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_len, int32_t *d_status,
+                          const m3tsz_encode_extras *extras, void *stream) {
   if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
   if (n_series == 0) return M3TSZ_OK;
   if (!d_ts || !d_val || !d_start || !d_out || !d_out_len || points_stride > 0xffffffffull ||
@@ -259,7 +243,8 @@ int m3tsz_encode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t 
       ((uintptr_t)d_out & 15u) || ((uintptr_t)d_ts & 7u) || ((uintptr_t)d_val & 7u))
     return M3TSZ_ERR_INVALID_ARG;
   if (d_ann_series_off && (!d_ann_entries || !d_ann_bytes)) return M3TSZ_ERR_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   EncodeParams p;
   memset(&p, 0, sizeof(p));
   p.ts = d_ts;
@@ -278,7 +263,83 @@ int m3tsz_encode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t 
   p.out_stride = out_stride;
   p.out_len = d_out_len;
   p.status = d_status;
+  if (extras) {
+    p.last_value = extras->d_last_value;
+    p.out_bits = extras->d_out_bits;
+  }
   CK(launch_encode(p, opts->int_optimized != 0, (cudaStream_t)stream));
+  ctx->launches++;
+  return M3TSZ_OK;
+}
+
+int m3tsz_encode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *d_ts,
+                       const double *d_val, uint64_t n_series, uint64_t points_stride,
+                       const uint32_t *d_n_points, const int64_t *d_start, int32_t unit,
+                       const uint8_t *d_units, const uint64_t *d_ann_series_off,
+                       const m3tsz_annotation_entry *d_ann_entries, const uint8_t *d_ann_bytes,
+                       uint8_t *d_out, uint64_t out_stride, uint64_t *d_out_len, int32_t *d_status,
+                       void *stream) {
+  return m3tsz_encode_batch_ex(ctx, opts, d_ts, d_val, n_series, points_stride, d_n_points, d_start, unit,
+                               d_units, d_ann_series_off, d_ann_entries, d_ann_bytes, d_out, out_stride,
+                               d_out_len, d_status, nullptr, stream);
+}
+
+int m3tsz_encode_batch_packed(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *d_ts,
+                              const double *d_val, uint64_t n_series, uint64_t points_stride,
+                              const uint32_t *d_n_points, const int64_t *d_start, int32_t unit,
+                              const uint8_t *d_units, const uint64_t *d_ann_series_off,
+                              const m3tsz_annotation_entry *d_ann_entries, const uint8_t *d_ann_bytes,
+                              uint64_t slot_bytes, uint32_t align, uint8_t *d_packed,
+                              uint64_t packed_capacity, uint64_t *d_offsets, uint64_t *d_out_len,
+                              int32_t *d_status, uint64_t *d_total_bytes, void *stream) {
+  if (!ctx || !valid_opts(opts) || !d_total_bytes) return M3TSZ_ERR_INVALID_ARG;
+  if (!(align == 1 || align == 4 || align == 8 || align == 16 || align == 32 || align == 64))
+    return M3TSZ_ERR_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(d_total_bytes, 0, sizeof(uint64_t), st));
+  if (n_series == 0) return M3TSZ_OK;
+  if (!d_ts || !d_val || !d_start || !d_packed || !d_offsets || !d_out_len ||
+      points_stride > 0xffffffffull || ((uintptr_t)d_packed & 63u) || ((uintptr_t)d_ts & 7u) ||
+      ((uintptr_t)d_val & 7u))
+    return M3TSZ_ERR_INVALID_ARG;
+  if (d_ann_series_off && (!d_ann_entries || !d_ann_bytes)) return M3TSZ_ERR_INVALID_ARG;
+  if (slot_bytes == 0) slot_bytes = m3tsz_encode_bound_units(points_stride, d_units != nullptr);
+  slot_bytes = (slot_bytes + 15) & ~15ull;
+  if (slot_bytes > (1ull << 33)) return M3TSZ_ERR_INVALID_ARG;
+  const uint64_t slots = encode_packed_scratch_slots(n_series);
+  if (slots == 0) return set_cuda_error(ctx, cudaGetLastError(), "encode_packed_scratch_slots");
+  void *scratch = nullptr, *ctr = nullptr;
+  int rc;
+  if ((rc = ensure(ctx, 36, slots * slot_bytes, &scratch))) return rc;
+  if ((rc = ensure(ctx, 37, 64, &ctr))) return rc;
+  CK(cudaMemsetAsync(ctr, 0, 64, st));
+  EncodeParams p;
+  memset(&p, 0, sizeof(p));
+  p.ts = d_ts;
+  p.val = d_val;
+  p.n_series = n_series;
+  p.points_stride = points_stride;
+  p.n_points = d_n_points;
+  p.start = d_start;
+  p.unit = unit;
+  p.units = d_units;
+  p.ann_series_off = d_ann_series_off;
+  p.ann_entries = d_ann_entries;
+  p.ann_bytes = d_ann_bytes;
+  p.default_unit = opts->default_time_unit;
+  p.out = (uint8_t *)scratch;
+  p.out_stride = slot_bytes;
+  p.out_len = d_out_len;
+  p.status = d_status;
+  p.packed = d_packed;
+  p.packed_capacity = packed_capacity;
+  p.packed_off = d_offsets;
+  p.packed_cursor = reinterpret_cast<unsigned long long *>(d_total_bytes);
+  p.batch_counter = reinterpret_cast<unsigned long long *>(ctr);
+  p.align = align;
+  CK(launch_encode(p, opts->int_optimized != 0, st));
   ctx->launches++;
   return M3TSZ_OK;
 }
@@ -289,7 +350,8 @@ int m3tsz_compact_streams(m3tsz_ctx *ctx, const uint8_t *d_slots, uint64_t slot_
                           void *stream) {
   if (!ctx || !d_offsets || (n_series && (!d_slots || !d_len || !d_packed))) return M3TSZ_ERR_INVALID_ARG;
   if (!(align == 1 || align == 4 || align == 8 || align == 16 || align == 32 || align == 64)) return M3TSZ_ERR_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   cudaStream_t st = (cudaStream_t)stream;
   size_t tmp_bytes = compact_scan_tmp_bytes(n_series);
   void *tmp = nullptr;
@@ -305,6 +367,111 @@ int m3tsz_compact_streams(m3tsz_ctx *ctx, const uint8_t *d_slots, uint64_t slot_
   return flag ? M3TSZ_ERR_CAPACITY : M3TSZ_OK;
 }
 
+int m3tsz_prom_convert_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *d_val, uint64_t cap,
+                             const uint32_t *d_n_points, uint64_t n_series, int64_t resolution_ns,
+                             const uint8_t *d_handle_resets, double value_decrease_tolerance,
+                             int64_t tolerance_until_ns, int64_t *d_ts_ms_out, double *d_val_out,
+                             uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, void *stream) {
+  if (!ctx) return M3TSZ_ERR_INVALID_ARG;
+  if (n_series == 0) return M3TSZ_OK;
+  if (!d_ts || !d_val || !d_n_points || !d_ts_ms_out || !d_val_out || !d_n_out || cap == 0 || out_cap == 0 ||
+      resolution_ns < 0 || (d_handle_resets && resolution_ns == 0) ||
+      value_decrease_tolerance != value_decrease_tolerance)
+    return M3TSZ_ERR_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
+  PromParams p;
+  memset(&p, 0, sizeof(p));
+  p.ts = d_ts;
+  p.val = d_val;
+  p.cap = cap;
+  p.n_points = d_n_points;
+  p.n_series = n_series;
+  p.resolution = resolution_ns;
+  p.handle_resets = d_handle_resets;
+  p.tolerance = value_decrease_tolerance;
+  p.tolerance_until = tolerance_until_ns;
+  p.ts_out = d_ts_ms_out;
+  p.val_out = d_val_out;
+  p.out_cap = out_cap;
+  p.n_out = d_n_out;
+  p.status = d_status;
+  CK(launch_prom(p, (cudaStream_t)stream));
+  ctx->launches++;
+  return M3TSZ_OK;
+}
+
+int m3tsz_aggregate_tiles_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *d_streams,
+                                uint64_t streams_bytes, const uint64_t *d_offsets,
+                                const uint64_t *d_lengths, uint64_t n_series, int64_t start_ns,
+                                int64_t step_ns, uint32_t n_windows, int32_t agg_type, int32_t out_unit,
+                                uint32_t align, uint8_t *d_packed, uint64_t packed_capacity,
+                                uint64_t *d_out_offsets, uint64_t *d_out_len, int32_t *d_status,
+                                uint32_t *d_n_tiles, uint64_t *d_total_bytes, void *stream) {
+  if (!ctx || !valid_opts(opts) || !d_total_bytes || !d_status) return M3TSZ_ERR_INVALID_ARG;
+  if (!(agg_type == M3TSZ_AGG_LAST || agg_type == M3TSZ_AGG_MIN || agg_type == M3TSZ_AGG_MAX ||
+        agg_type == M3TSZ_AGG_MEAN || agg_type == M3TSZ_AGG_COUNT || agg_type == M3TSZ_AGG_SUM))
+    return M3TSZ_ERR_INVALID_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_series == 0) {
+    DeviceGuard guard(ctx->device);
+    CK(cudaMemsetAsync(d_total_bytes, 0, sizeof(uint64_t), st));
+    return M3TSZ_OK;
+  }
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
+  // context scratch: window-major aggregates, then series-major tiles
+  const size_t wb = (size_t)n_series * n_windows * 8;
+  void *d_sum, *d_cnt, *d_min, *d_max, *d_last, *d_lat, *d_tts, *d_tval, *d_nt, *d_sst, *d_np, *d_es;
+  int rc;
+  if ((rc = ensure(ctx, 8, wb, &d_sum))) return rc;
+  if ((rc = ensure(ctx, 9, wb, &d_cnt))) return rc;
+  if ((rc = ensure(ctx, 10, wb, &d_min))) return rc;
+  if ((rc = ensure(ctx, 11, wb, &d_max))) return rc;
+  if ((rc = ensure(ctx, 12, wb, &d_lat))) return rc;
+  if ((rc = ensure(ctx, 38, wb, &d_last))) return rc;
+  if ((rc = ensure(ctx, 2, wb, &d_tts))) return rc;
+  if ((rc = ensure(ctx, 3, wb, &d_tval))) return rc;
+  if ((rc = ensure(ctx, 4, n_series * 4, &d_np))) return rc;
+  if ((rc = ensure(ctx, 5, n_series * 4, &d_sst))) return rc;
+  if ((rc = ensure(ctx, 6, n_series * 4, &d_nt))) return rc;
+  if ((rc = ensure(ctx, 39, n_series * 8, &d_es))) return rc;
+  // 1. fused decode + Gauge windows (with `last`)
+  rc = downsample_impl(ctx, opts, d_streams, streams_bytes, d_offsets, d_lengths, n_series, start_ns, step_ns,
+                       n_windows, (double *)d_sum, (int64_t *)d_cnt, (double *)d_min, (double *)d_max,
+                       (double *)d_last, (int64_t *)d_lat, true, (uint32_t *)d_np, (int32_t *)d_sst, st);
+  if (rc) return rc;
+  // 2. one datapoint per non-empty window
+  TileParams t;
+  memset(&t, 0, sizeof(t));
+  t.sum = (const double *)d_sum;
+  t.count = (const int64_t *)d_cnt;
+  t.mn = (const double *)d_min;
+  t.mx = (const double *)d_max;
+  t.last = (const double *)d_last;
+  t.src_status = (const int32_t *)d_sst;
+  t.n_series = n_series;
+  t.n_windows = n_windows;
+  t.start = start_ns;
+  t.step = step_ns;
+  t.agg_type = agg_type;
+  t.ts_out = (int64_t *)d_tts;
+  t.val_out = (double *)d_tval;
+  t.n_out = d_n_tiles ? d_n_tiles : (uint32_t *)d_nt;
+  t.enc_start = (int64_t *)d_es;
+  CK(launch_tiles_gather(t, st));
+  ctx->launches++;
+  // 3. re-encode into the packed target buffer
+  rc = m3tsz_encode_batch_packed(ctx, opts, (const int64_t *)d_tts, (const double *)d_tval, n_series, n_windows,
+                                 t.n_out, (const int64_t *)d_es, out_unit, nullptr, nullptr, nullptr, nullptr,
+                                 0, align, d_packed, packed_capacity, d_out_offsets, d_out_len, d_status,
+                                 d_total_bytes, st);
+  if (rc) return rc;
+  CK(launch_tiles_status((const int32_t *)d_sst, d_status, n_series, st));
+  ctx->launches++;
+  return M3TSZ_OK;
+}
+
 int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *d_val, uint64_t cap,
                              const uint32_t *d_n_points, const int32_t *d_seq_status,
                              const uint64_t *d_slice_off, const uint64_t *d_replica_off,
@@ -317,7 +484,8 @@ int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *
       !d_val_out || !d_n_out || !d_status || cap == 0 || out_cap == 0 || out_cap > 0xffffffffull ||
       strategy < 0 || strategy > 3)
     return M3TSZ_ERR_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   MergeParams p;
   memset(&p, 0, sizeof(p));
   p.ts = d_ts;
@@ -350,7 +518,8 @@ int m3tsz_checksum_batch(m3tsz_ctx *ctx, const uint8_t *d_streams, uint64_t stre
   if (n_series == 0) return M3TSZ_OK;
   if (!d_streams || !d_offsets || (!d_checksums && !d_status) || (d_expected && !d_status))
     return M3TSZ_ERR_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   ChecksumParams p;
   memset(&p, 0, sizeof(p));
   p.streams = d_streams;
@@ -377,7 +546,8 @@ int m3tsz_decode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const uin
   if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
   if (n_series == 0) return M3TSZ_OK;
   if (!h_streams || !h_offsets || !h_ts || !h_val || max_points == 0) return M3TSZ_ERR_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   void *d_streams, *d_off, *d_ts, *d_val, *d_n, *d_st, *d_unit = nullptr, *d_ann = nullptr;
   int rc;
   if ((rc = ensure(ctx, 0, streams_bytes + 16, &d_streams))) return rc;
@@ -436,7 +606,8 @@ int m3tsz_decode_downsample_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts
   if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
   if (n_series == 0) return M3TSZ_OK;
   if (!h_streams || !h_offsets || !h_sum || !h_count || !h_min || !h_max) return M3TSZ_ERR_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   cudaStream_t st = ctx->stream;
   const size_t wb = (size_t)n_series * n_windows * 8;
   void *d_streams, *d_off, *d_sum, *d_cnt, *d_min, *d_max, *d_n, *d_st;
@@ -480,7 +651,8 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
   if (n_series == 0) return M3TSZ_OK;
   if (!h_ts || !h_val || !h_start || !h_packed) return M3TSZ_ERR_INVALID_ARG;
   if (!(align == 1 || align == 4 || align == 8 || align == 16 || align == 32 || align == 64)) return M3TSZ_ERR_INVALID_ARG;
-  CK(cudaSetDevice(ctx->device));
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   cudaStream_t sts[2] = {ctx->stream, ctx->stream2};
   const uint64_t ann_total = h_ann_series_off ? ann_bytes_len + 16 * h_ann_series_off[n_series] : 0;
   const uint64_t out_stride = m3tsz_encode_bound(points_stride) + ((ann_total + 15) & ~15ull);

@@ -54,8 +54,7 @@ constexpr int DEC_QUADS = DEC_RING / 4;  // + 1 mirror quad (copy of quad 0) so 
 constexpr int DEC_IN_TILE_WORDS = (DEC_QUADS + 1) * 32 * 4;
 static_assert(M3_DEC_CHK == DEC_GROUP, "ring bookkeeping runs once per output group");
 constexpr size_t DEC_WARP_SMEM_PLAIN = (size_t)DEC_IN_TILE_WORDS * 4;
-constexpr size_t DEC_WARP_SMEM_DS = (size_t)DEC_IN_TILE_WORDS * 4;
-static_assert(DEC_WARP_SMEM_PLAIN % 16 == 0 && DEC_WARP_SMEM_DS % 16 == 0, "every warp's ring must stay 16-byte aligned");
+static_assert(DEC_WARP_SMEM_PLAIN % 16 == 0, "every warp's ring must stay 16-byte aligned");
 
 constexpr uint64_t kGoNaNBits = 0x7FF8000000000001ull;  // math.NaN()
 
@@ -68,7 +67,8 @@ struct DecState {
   double int_val;
   int64_t unit_ns;
   int sig, mult, unit, scheme;
-  int emit_unit;  // time unit in force at the last datapoint produced
+  int emit_unit;   // time unit in force at the last datapoint produced
+  int first_unit;  // ... at the first datapoint produced
   int err;
   uint32_t n;
   bool is_float, done;
@@ -89,7 +89,30 @@ struct SlowSrc {
   uint64_t nbytes;
   const uint32_t *ring_lane;  // the lane's 16-byte cell of quad 0 (ring + lane * 4 words)
   uint32_t ring_safe;
+  // per-datapoint unit / annotation event table (optional; include/m3tsz_b200.h m3tsz_dp_event)
+  m3tsz_dp_event *events;
+  uint64_t events_capacity;
+  unsigned long long *event_count;
+  uint64_t series;
+  uint32_t pos0;  // bit position of the stream's first bit (relative to wbase)
 };
+
+__device__ __forceinline__ void push_event(const SlowSrc &src, uint32_t dp_index, uint32_t kind, uint32_t unit,
+                                           uint64_t bit_offset, uint32_t length) {
+  if (!src.event_count) return;
+  const unsigned long long i = atomicAdd(src.event_count, 1ull);
+  if (i < src.events_capacity) {
+    m3tsz_dp_event e;
+    e.series = src.series;
+    e.dp_index = dp_index;
+    e.kind = (uint16_t)kind;
+    e.unit = (uint16_t)unit;
+    e.bit_offset = bit_offset;
+    e.length = length;
+    e.reserved = 0;
+    src.events[i] = e;
+  }
+}
 
 __device__ __forceinline__ uint64_t gpeek64(const SlowSrc &src, uint64_t wbase, uint32_t pos) {
   const uint32_t wr = pos >> 5;
@@ -199,6 +222,7 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const SlowSrc src, int 
             s.ann_len = (uint32_t)alen;
           }
           s.ann_count++;
+          push_event(src, s.n, M3TSZ_EVENT_ANNOTATION, 0, (uint64_t)(s.pos - src.pos0), (uint32_t)alen);
           s.pos += (uint32_t)alen * 8u;
           continue;
         }
@@ -210,6 +234,7 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const SlowSrc src, int 
             unit_changed = true;
             s.scheme = scheme_kind_for_unit(tu);
           }
+          if (tu != s.unit && s.n > 0) push_event(src, s.n, M3TSZ_EVENT_TIME_UNIT, (uint32_t)tu, 0, 0);
           s.unit = tu;
           s.unit_ns = unit_nanos(tu);
           continue;
@@ -369,6 +394,7 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const SlowSrc src, int 
   }
   out_t = s.prev_time;
   s.emit_unit = s.unit;
+  if (s.n == 0) s.first_unit = s.unit;
   if (!INT_OPT || s.is_float) {
     out_v = s.prev_bits;
   } else {
@@ -388,13 +414,25 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
+__device__ __forceinline__ void cp_async16_full(uint32_t dst, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+}
 // Lane-local refill: the lane copies the 64-byte chunk at global word index gw
 // (a multiple of 16) of ITS OWN stream into quads slot_q0..slot_q0+3 of its own
 // column with four 16-byte cp.async (a warp instruction writes 32 x 16 B =
 // 4 conflict-free wavefronts; no shuffles).  Quad 0 is mirrored to quad 16.
 __device__ __forceinline__ void ring_fill(uint32_t ring_lane_addr, const uint8_t *streams, uint64_t nbytes,
                                                bool take, uint32_t gw, uint32_t slot_q0) {
-  if (take) {
+  if (take && ((uint64_t)gw * 4ull + 64ull <= nbytes)) {
+    // whole chunk inside the buffer (every chunk but the batch's last): constant-size copies
+    const uint8_t *src = streams + (uint64_t)gw * 4ull;
+    const uint32_t dst = ring_lane_addr + slot_q0 * 512u;
+    cp_async16_full(dst, src);
+    cp_async16_full(dst + 512u, src + 16);
+    cp_async16_full(dst + 1024u, src + 32);
+    cp_async16_full(dst + 1536u, src + 48);
+    if (slot_q0 == 0) cp_async16_full(ring_lane_addr + DEC_QUADS * 512u, src);
+  } else if (take) {
 #pragma unroll
     for (uint32_t k = 0; k < 4; k++) {
       const uint64_t b = ((uint64_t)gw + 4u * k) * 4ull;
@@ -407,19 +445,28 @@ __device__ __forceinline__ void ring_fill(uint32_t ring_lane_addr, const uint8_t
   }
 }
 
-struct DsAcc {  // fused-downsample per-lane accumulator (aggregation.Gauge, gauge.go:31-106)
-  int64_t cur_w, hi_w, w_start;
+// Fused-downsample per-lane accumulator: aggregation.Gauge of the open window
+// (/root/reference/src/aggregator/aggregation/gauge.go:31-106).
+struct DsAcc {
+  int64_t d;      // hot path: (time of the last datapoint) - w_end while the group's pre-check holds
+  int64_t w_end;  // exclusive end of the open window
+  int32_t cur_w, hi_w;  // open window (-1: none) / highest window initialised so far
   double sum, mn, mx;
-  int64_t cnt;
+  uint32_t cnt;      // datapoints in the open window (NaNs counted, gauge.go:85)
+  uint32_t cnt_gen;  // cnt as of the last general-path visit (cnt != cnt_gen: hot datapoints since)
+  int64_t last_t;    // MODE 2: lastAt / last (gauge.go:74-81)
+  uint64_t last_v;
 };
 
+// MODE 0: plain decode (ts, value) ; 1: fused 5-tuple-less downsample (sum, count, min, max);
+// 2: downsample + last (+ lastAt scratch).
 template <bool INT_OPT, int MODE>
-__global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCKS_DS : M3_DEC_MIN_BLOCKS)
+__global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCKS_DS : M3_DEC_MIN_BLOCKS)
     decode_kernel(const DecodeParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  constexpr size_t warp_smem = (MODE == 0) ? DEC_WARP_SMEM_PLAIN : DEC_WARP_SMEM_DS;
+  constexpr size_t warp_smem = DEC_WARP_SMEM_PLAIN;
   uint32_t *ring = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem) + warp * warp_smem);
   const uint32_t *ring_lane = ring + lane * 4;  // this lane's 16-byte cell of quad 0
   const uint32_t ring_lane_addr = smem_addr(ring_lane);
@@ -444,6 +491,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
   s.unit = 0;
   s.scheme = kSchemeNone;
   s.emit_unit = 0;
+  s.first_unit = 0;
   s.err = 0;
   s.n = 0;
   s.is_float = false;
@@ -453,7 +501,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
   s.ann_bit = 0;
   uint32_t pos0 = 0;
   if (valid) {
-    const uint64_t o0 = p.offsets[sidx], o1 = p.offsets[sidx + 1];
+    const uint64_t o0 = p.offsets[sidx];
+    const uint64_t o1 = p.lengths ? o0 + p.lengths[sidx] : p.offsets[sidx + 1];
     if (o1 < o0 || o1 > p.streams_bytes) {
       s.err = M3TSZ_ERR_INVALID_ARG;
     } else if (o1 - o0 >= (1ull << 28)) {
@@ -471,16 +520,61 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
   // previous XOR's leading / trailing zero counts, kept eagerly (float path)
   int plz = 64, ptz = 0;
 
+  const double kNaN = __longlong_as_double((long long)kGoNaNBits);
   DsAcc acc;
+  acc.d = 0;
+  acc.w_end = 0;
   acc.cur_w = -1;
   acc.hi_w = -1;
-  acc.w_start = 0;
   acc.sum = 0.0;
-  acc.mn = __longlong_as_double((long long)kGoNaNBits);
-  acc.mx = acc.mn;
+  acc.mn = kNaN;
+  acc.mx = kNaN;
   acc.cnt = 0;
+  acc.cnt_gen = 0;
+  acc.last_t = 0;
+  acc.last_v = 0;
   const int64_t range_end = p.range_start + (int64_t)p.n_windows * p.window;
   (void)range_end;
+
+  // ---- fused-downsample helpers (per lane) ----
+  auto ds_store = [&](int32_t w) {  // commit the open window's aggregate
+    const uint64_t o = (uint64_t)(uint32_t)w * p.n_series + sidx;
+    p.ds_sum[o] = acc.sum;
+    p.ds_count[o] = (int64_t)acc.cnt;
+    p.ds_min[o] = acc.mn;
+    p.ds_max[o] = acc.mx;
+    if (MODE == 2) {
+      p.ds_last[o] = __longlong_as_double((long long)acc.last_v);
+      p.ds_last_at[o] = acc.last_t;
+    }
+  };
+  auto ds_store_empty = [&](int32_t w) {  // NewGauge: sum 0, count 0, min/max NaN, last 0 (gauge.go:45-51)
+    const uint64_t o = (uint64_t)(uint32_t)w * p.n_series + sidx;
+    p.ds_sum[o] = 0.0;
+    p.ds_count[o] = 0;
+    p.ds_min[o] = kNaN;
+    p.ds_max[o] = kNaN;
+    if (MODE == 2) {
+      p.ds_last[o] = 0.0;
+      p.ds_last_at[o] = 0;
+    }
+  };
+  auto ds_reset = [&]() {
+    acc.sum = 0.0;
+    acc.cnt = 0;
+    acc.cnt_gen = 0;
+    acc.mn = kNaN;
+    acc.mx = kNaN;
+  };
+  auto ds_add = [&](uint64_t vbits) {  // Gauge.updateTotals without `last` (gauge.go:85-101)
+    const double dv = __longlong_as_double((long long)vbits);
+    acc.cnt++;
+    if (dv == dv) {
+      acc.sum = __dadd_rn(acc.sum, dv);
+      if (acc.mx != acc.mx || acc.mx < dv) acc.mx = dv;
+      if (acc.mn != acc.mn || acc.mn > dv) acc.mn = dv;
+    }
+  };
 
   // refills are DEC_FILL-word aligned: start at the stream's first word rounded down
   uint32_t filled = (s.pos >> 5) & ~(uint32_t)(DEC_FILL - 1);  // words [.., filled) requested
@@ -490,6 +584,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
   // row 0 of every group is 32-byte aligned when the arrays are and cap is a multiple of 4
   const bool out_aligned =
       MODE == 0 && (((uintptr_t)p.ts | (uintptr_t)p.val) & 31u) == 0 && (p.cap & 3u) == 0;
+  // running output pointers of this lane's series (MODE 0)
+  uint64_t *dt = nullptr, *dv = nullptr;
+  if (MODE == 0) {
+    dt = reinterpret_cast<uint64_t *>(p.ts) + sidx * p.cap;
+    dv = reinterpret_cast<uint64_t *>(p.val) + sidx * p.cap;
+  }
   // scheme/unit admit the fast path (they only change on the slow path)
   bool su_ok = false;
   // maintained flags: `live` = lane still decoding; they change on the general path only
@@ -504,7 +604,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
     // (issued many datapoints ago, so normally landed), then every lane with room
     // takes another 16-word chunk.  Lanes that nevertheless run dry fall back to
     // the slow path (reads global memory), so the thresholds only tune speed.
-    auto ring_service = [&]() {
+    {
       const bool active = live;
       const uint32_t cw = s.pos >> 5;
       int avail = (int)(filled - cw);
@@ -527,7 +627,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
               __ballot_sync(FULL_MASK, active && avail <= (rep == 0 ? DEC_ACCEPT : DEC_TRIGGER));
           if (!fmask) break;
           ring_fill(ring_lane_addr, p.streams, p.streams_bytes, (fmask >> lane) & 1u, gbase + filled,
-                         (filled >> 2) & (DEC_QUADS - 1));
+                    (filled >> 2) & (DEC_QUADS - 1));
           if ((fmask >> lane) & 1u) {
             filled += DEC_FILL;
             avail += DEC_FILL;
@@ -539,22 +639,30 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
           safe = filled;
         }
       }
-    };
+    }
 
-#pragma unroll 1
-    for (int rb = 0; rb < DEC_GROUP; rb += M3_DEC_CHK) {
-      ring_service();
-      // Hot-path conditions that cannot change while the group stays on the hot path,
-      // checked once with margins for M3_DEC_CHK datapoints of <= 80 bits each: words
-      // landed, distance to the end of the stream, not the first datapoint and no
-      // wrap of prev_time to 0 (first <=> PrevTime == 0, timestamp_iterator.go:89),
-      // float mode.
-      bool pre_ok = fast_en && (((s.pos + 80u * (M3_DEC_CHK - 1)) >> 5) + DEC_FAST_WORDS <= safe) &&
-                    (s.pos + 80u * M3_DEC_CHK <= s.end) && (s.prev_time > 0) &&
-                    ((uint64_t)s.prev_delta < (1ull << 60)) && (!INT_OPT || s.is_float);
+    // Hot-path conditions that cannot change while the group stays on the hot path,
+    // checked once with margins for M3_DEC_CHK datapoints of <= 80 bits each: words
+    // landed, distance to the end of the stream, not the first datapoint and no
+    // wrap of prev_time to 0 (first <=> PrevTime == 0, timestamp_iterator.go:89),
+    // float mode.
+    bool pre_ok = fast_en && (((s.pos + 80u * (M3_DEC_CHK - 1)) >> 5) + DEC_FAST_WORDS <= safe) &&
+                  (s.pos + 80u * M3_DEC_CHK <= s.end) && (s.prev_time > 0) &&
+                  ((uint64_t)s.prev_delta < (1ull << 60)) && (!INT_OPT || s.is_float);
+    if (MODE >= 1) {
+      // fused downsample, additionally: timestamps strictly increasing in steps of at most one
+      // window (so a datapoint is in the open window or opens the next one), the whole group
+      // inside the range, the last datapoint inside the open window, and the open window is the
+      // newest one (no committed window ahead that would have to be re-opened).
+      acc.d = (int64_t)((uint64_t)s.prev_time - (uint64_t)acc.w_end);
+      pre_ok = pre_ok && acc.cur_w >= 0 && acc.cur_w == acc.hi_w && s.prev_delta > 0 &&
+               s.prev_delta <= p.window && s.prev_time < range_end &&
+               (uint64_t)(range_end - s.prev_time) > 4ull * (uint64_t)s.prev_delta &&
+               acc.d < 0 && (0ull - (uint64_t)acc.d) <= (uint64_t)p.window;
+    }
+
 #pragma unroll
-      for (int rr = 0; rr < M3_DEC_CHK; rr++) {
-
+    for (int rr = 0; rr < M3_DEC_CHK; rr++) {
       const bool active = live;
       const uint32_t cw = s.pos >> 5;
       int64_t t = 0;
@@ -584,7 +692,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
       {
         uint32_t x = h << 1;
         uint32_t c = 1;
-        bool hot = pre_ok && (INT_OPT ? ((h >> 30) == 1u) : !(h >> 31));  // '0' zero DoD [+ '1' no update]
+        const bool hot = pre_ok && (INT_OPT ? ((h >> 30) == 1u) : !(h >> 31));  // '0' zero DoD [+ '1' no update]
         if (INT_OPT) {
           x <<= 1;
           c = 2;
@@ -594,40 +702,68 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
         const int lz = (int)((x >> 24) & 63u);
         const int nunc = (int)((x >> 18) & 63u) + 1;
         int n = cont ? (64 - plz - ptz) : nunc;
-        int tz = cont ? ptz : (64 - lz - nunc);
+        const int tz = cont ? ptz : (64 - lz - nunc);
         c += cont ? 2u : 14u;
         if (zero) {
           n = 0;
           c -= cont ? 1u : 13u;
         }
         const uint64_t field = M3_FIELD64(c);
-        const uint64_t payload = n ? (field >> (64 - n)) : 0ull;
         c += (uint32_t)n;
         if (__all_sync(FULL_MASK, hot || !active)) {
           // every live lane: unconditional update (finished lanes compute garbage
           // they never read again)
           s.pos += c;
-          s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
-          const uint64_t xr = (tz < 0) ? 0ull : (payload << tz);
-          s.prev_xor = xr;
-          s.prev_bits ^= xr;
-          lz_tz(xr, plz, ptz);
+          // xor = (top n bits of the field) << tz; nothing for the zero code or a malformed
+          // uncontained header (lz + n > 64: the reference shifts everything out)
+          const uint64_t xr = (zero || tz < 0) ? 0ull : ((field >> ((64 - n) & 63)) << (tz & 63));
           if (MODE == 0) {
+            s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
+            s.prev_xor = xr;
+            s.prev_bits ^= xr;
+            lz_tz(xr, plz, ptz);
             o_t[rr] = (uint64_t)s.prev_time;
             o_v[rr] = s.prev_bits;
             s.n += (uint32_t)active;
             continue;
+          } else {
+            // this datapoint's time relative to the end of the open window
+            acc.d = (int64_t)((uint64_t)acc.d + (uint64_t)s.prev_delta);
+            const bool adv = active && acc.d >= 0;
+            if (__any_sync(FULL_MASK, adv)) {
+              if (adv) {  // it opens the next window: commit the one it leaves
+                if (MODE == 2 && acc.cnt != acc.cnt_gen) {  // `last` of in-order datapoints = the previous one
+                  acc.last_t = (int64_t)((uint64_t)acc.d - (uint64_t)s.prev_delta + (uint64_t)acc.w_end);
+                  acc.last_v = s.prev_bits;
+                }
+                ds_store(acc.cur_w);
+                acc.cur_w++;
+                acc.hi_w = acc.cur_w;
+                acc.w_end += p.window;
+                acc.d -= p.window;
+                ds_reset();
+              }
+            }
+            s.prev_xor = xr;
+            s.prev_bits ^= xr;
+            lz_tz(xr, plz, ptz);
+            if (active) ds_add(s.prev_bits);
+            s.n += (uint32_t)active;
+            continue;
           }
-          t = s.prev_time;
-          v = s.prev_bits;
-          emitted = active;
-          goto sink;
         }
       }
 
       // ---------------- general path (any mix of cases) ----------------
       {
+        if (MODE >= 1 && pre_ok)  // leaving the hot path: prev_time was carried in acc.d
+          s.prev_time = (int64_t)((uint64_t)acc.d + (uint64_t)acc.w_end);
         pre_ok = false;  // the group's pre-check does not survive a general-path datapoint
+        if (MODE == 2 && acc.cnt != acc.cnt_gen) {  // hot datapoints since the last visit: the newest is `last`
+          acc.last_t = s.prev_time;
+          acc.last_v = s.prev_bits;
+          acc.cnt_gen = acc.cnt;
+        }
         bool ok = fast_en && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
         uint32_t c = 1;  // bits consumed before the payload
         int64_t dod = 0;
@@ -738,8 +874,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
                 const double m = __ull2double_rn(mag);
                 s.int_val = neg ? __dadd_rn(s.int_val, m) : __dsub_rn(s.int_val, m);
               }
-              const double dv = s.mult ? __ddiv_rn(s.int_val, mult_pow10(s.mult)) : s.int_val;
-              v = (uint64_t)__double_as_longlong(dv);
+              const double dvv = s.mult ? __ddiv_rn(s.int_val, mult_pow10(s.mult)) : s.int_val;
+              v = (uint64_t)__double_as_longlong(dvv);
             }
           }
         } else if (active) {  // complete grammar, from global memory
@@ -751,6 +887,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
           src.nbytes = p.streams_bytes;
           src.ring_lane = ring_lane;
           src.ring_safe = ((int)(filled - cw) >= 0) ? safe : 0u;  // ring abandoned after a skip
+          src.events = p.events;
+          src.events_capacity = p.events_capacity;
+          src.event_count = p.event_count;
+          src.series = sidx;
+          src.pos0 = pos0;
           const bool em = decode_dp_slow<INT_OPT>(tmp, src, p.default_unit, st, sv);
           s = tmp;
           t = st;
@@ -763,8 +904,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
         fast_en = live && su_ok;
       }
 
-    sink:
-      // ---------------- sink ----------------
+      // ---------------- sink (general path) ----------------
       if (MODE == 0) {
         if (emitted) {
           o_t[rr] = (uint64_t)t;
@@ -776,60 +916,48 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
           s.n++;
           // inside the open window (one unsigned compare covers both bounds; an open window
           // lies inside the range)?  Otherwise: inside the range at all?
-          bool in_win = acc.cur_w >= 0 && (uint64_t)(t - acc.w_start) < (uint64_t)p.window;
+          bool in_win = acc.cur_w >= 0 && (uint64_t)(t - (acc.w_end - p.window)) < (uint64_t)p.window;
           if (!in_win && t >= p.range_start && t < range_end) {
-            {
-              // commit the window we are leaving
-              if (acc.cur_w >= 0) {
-                const uint64_t o = (uint64_t)acc.cur_w * p.n_series + sidx;
-                p.ds_sum[o] = acc.sum;
-                p.ds_count[o] = acc.cnt;
-                p.ds_min[o] = acc.mn;
-                p.ds_max[o] = acc.mx;
+            // commit the window we are leaving
+            if (acc.cur_w >= 0) ds_store(acc.cur_w);
+            int64_t nw;
+            if (acc.cur_w >= 0 && t >= acc.w_end && t - acc.w_end < p.window)
+              nw = (int64_t)acc.cur_w + 1;
+            else
+              nw = (int64_t)((uint64_t)(t - p.range_start) / (uint64_t)p.window);
+            if (nw > (int64_t)acc.hi_w) {
+              for (int64_t w = (int64_t)acc.hi_w + 1; w < nw; w++) ds_store_empty((int32_t)w);
+              acc.hi_w = (int32_t)nw;
+              ds_reset();
+            } else {  // out-of-order timestamp: reopen a committed window
+              const uint64_t o = (uint64_t)nw * p.n_series + sidx;
+              acc.sum = p.ds_sum[o];
+              acc.cnt = (uint32_t)p.ds_count[o];
+              acc.mn = p.ds_min[o];
+              acc.mx = p.ds_max[o];
+              if (MODE == 2) {
+                acc.last_v = (uint64_t)__double_as_longlong(p.ds_last[o]);
+                acc.last_t = p.ds_last_at[o];
               }
-              int64_t nw;
-              if (acc.cur_w >= 0 && t >= acc.w_start + p.window && t - acc.w_start < 2 * p.window)
-                nw = acc.cur_w + 1;
-              else
-                nw = (int64_t)((uint64_t)(t - p.range_start) / (uint64_t)p.window);
-              if (nw > acc.hi_w) {
-                for (int64_t w = acc.hi_w + 1; w < nw; w++) {
-                  const uint64_t o = (uint64_t)w * p.n_series + sidx;
-                  p.ds_sum[o] = 0.0;
-                  p.ds_count[o] = 0;
-                  p.ds_min[o] = __longlong_as_double((long long)kGoNaNBits);
-                  p.ds_max[o] = __longlong_as_double((long long)kGoNaNBits);
-                }
-                acc.hi_w = nw;
-                acc.sum = 0.0;
-                acc.cnt = 0;
-                acc.mn = __longlong_as_double((long long)kGoNaNBits);
-                acc.mx = acc.mn;
-              } else {  // out-of-order timestamp: reopen a committed window
-                const uint64_t o = (uint64_t)nw * p.n_series + sidx;
-                acc.sum = p.ds_sum[o];
-                acc.cnt = p.ds_count[o];
-                acc.mn = p.ds_min[o];
-                acc.mx = p.ds_max[o];
-              }
-              acc.cur_w = nw;
-              acc.w_start = p.range_start + nw * p.window;
             }
+            acc.cur_w = (int32_t)nw;
+            acc.w_end = p.range_start + (nw + 1) * p.window;
             in_win = true;
           }
           if (in_win) {
-            const double dv = __longlong_as_double((long long)v);
-            acc.cnt++;
-            if (dv == dv) {  // gauge.go:88-101
-              acc.sum = __dadd_rn(acc.sum, dv);
-              if (acc.mx != acc.mx || acc.mx < dv) acc.mx = dv;
-              if (acc.mn != acc.mn || acc.mn > dv) acc.mn = dv;
+            // lastAt.IsZero() || timestamp.After(lastAt), gauge.go:74-81 (NaN values included)
+            if (MODE == 2 && (acc.cnt == 0 || t > acc.last_t)) {
+              acc.last_t = t;
+              acc.last_v = v;
             }
+            ds_add(v);
           }
+          acc.cnt_gen = acc.cnt;
         }
       }
     }
-    }
+    if (MODE >= 1 && pre_ok)  // the group stayed hot: materialise prev_time for the next pre-check
+      s.prev_time = (int64_t)((uint64_t)acc.d + (uint64_t)acc.w_end);
 
     // ---------------- store the group: each lane writes its own series ----------------
     // Every live lane emits exactly one datapoint per step until it stops, so the group's
@@ -838,8 +966,6 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
     if (MODE == 0 && valid) {
       const uint32_t lim = s.n < (uint32_t)p.cap ? s.n : (uint32_t)p.cap;
       const uint32_t my_rows = lim > group_row0 ? min(lim - group_row0, 4u) : 0u;
-      uint64_t *dt = reinterpret_cast<uint64_t *>(p.ts) + sidx * p.cap + group_row0;
-      uint64_t *dv = reinterpret_cast<uint64_t *>(p.val) + sidx * p.cap + group_row0;
       if (my_rows == 4u && out_aligned) {
         asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(dt), "l"(o_t[0]), "l"(o_t[1]), "l"(o_t[2]),
                      "l"(o_t[3])
@@ -855,27 +981,17 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
             dv[r] = o_v[r];
           }
       }
+      dt += DEC_GROUP;
+      dv += DEC_GROUP;
     }
     group_row0 += DEC_GROUP;
   }
   cp_async_wait_all();
 
   // ---------------- epilogue ----------------
-  if (MODE == 1 && valid) {
-    if (acc.cur_w >= 0) {
-      const uint64_t o = (uint64_t)acc.cur_w * p.n_series + sidx;
-      p.ds_sum[o] = acc.sum;
-      p.ds_count[o] = acc.cnt;
-      p.ds_min[o] = acc.mn;
-      p.ds_max[o] = acc.mx;
-    }
-    for (int64_t w = acc.hi_w + 1; w < (int64_t)p.n_windows; w++) {
-      const uint64_t o = (uint64_t)w * p.n_series + sidx;
-      p.ds_sum[o] = 0.0;
-      p.ds_count[o] = 0;
-      p.ds_min[o] = __longlong_as_double((long long)kGoNaNBits);
-      p.ds_max[o] = __longlong_as_double((long long)kGoNaNBits);
-    }
+  if (MODE >= 1 && valid) {
+    if (acc.cur_w >= 0) ds_store(acc.cur_w);
+    for (int64_t w = (int64_t)acc.hi_w + 1; w < (int64_t)p.n_windows; w++) ds_store_empty((int32_t)w);
   }
   if (valid) {
     if (p.n_points) p.n_points[sidx] = s.n;
@@ -883,6 +999,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
     if (MODE == 0 && st == 0 && s.n > p.cap) st = M3TSZ_ERR_CAPACITY;
     if (p.status) p.status[sidx] = st;
     if (p.unit_out) p.unit_out[sidx] = (uint8_t)(s.n ? s.emit_unit : s.unit);
+    if (p.unit_first_out) p.unit_first_out[sidx] = (uint8_t)(s.n ? s.first_unit : s.unit);
     if (p.ann_out) {
       m3tsz_annotation_ref a;
       a.bit_offset = s.ann_count ? (uint64_t)(s.ann_bit - pos0) : 0ull;
@@ -897,7 +1014,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1) ? M3_DEC_MIN_BLOCK
 
 template <bool INT_OPT, int MODE>
 static cudaError_t launch_one(const DecodeParams &p, cudaStream_t stream) {
-  constexpr size_t warp_smem = (MODE == 0) ? DEC_WARP_SMEM_PLAIN : DEC_WARP_SMEM_DS;
+  constexpr size_t warp_smem = DEC_WARP_SMEM_PLAIN;
 #ifdef M3_DEC_PAD_SMEM
   constexpr size_t smem = warp_smem * DEC_WARPS + M3_DEC_PAD_SMEM;  // diagnostic: caps resident blocks
 #else
@@ -914,11 +1031,14 @@ static cudaError_t launch_one(const DecodeParams &p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_decode(const DecodeParams &p, bool int_optimized, bool downsample,
-                          cudaStream_t stream) {
-  if (!downsample)
-    return int_optimized ? launch_one<true, 0>(p, stream) : launch_one<false, 0>(p, stream);
-  return int_optimized ? launch_one<true, 1>(p, stream) : launch_one<false, 1>(p, stream);
+// mode: 0 plain decode, 1 fused downsample (sum/count/min/max), 2 fused downsample + last
+cudaError_t launch_decode(const DecodeParams &p, bool int_optimized, int mode, cudaStream_t stream) {
+  switch (mode) {
+    case 0: return int_optimized ? launch_one<true, 0>(p, stream) : launch_one<false, 0>(p, stream);
+    case 1: return int_optimized ? launch_one<true, 1>(p, stream) : launch_one<false, 1>(p, stream);
+    case 2: return int_optimized ? launch_one<true, 2>(p, stream) : launch_one<false, 2>(p, stream);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace m3tsz

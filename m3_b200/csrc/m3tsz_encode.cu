@@ -589,7 +589,17 @@ __device__ __forceinline__ void enc_cp_async8(uint32_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <bool INT_OPT>
+// PACKED = false: one warp per 32-series batch, every series writes its own slot
+//   p.out + s * p.out_stride (fixed stride).
+// PACKED = true : persistent warps fetch batches from a counter, encode into a per-warp
+//   scratch slot set (reused batch after batch), then allocate exact space in the packed
+//   buffer with ONE atomicAdd per batch (sum of the 32 aligned lengths) and copy their
+//   streams there with coalesced 16-byte loads/stores -- the separate compaction pass
+//   (scan + gather over all bytes) and the [S][stride] slot buffer disappear; the copies
+//   of finished warps overlap the bit packing of the others.  Streams land in completion
+//   order: p.packed_off[s] / p.out_len[s] are the index entry (Offset, Size) of stream s
+//   (persist/schema/types.go:70-78).
+template <bool INT_OPT, bool PACKED>
 __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kernel(const EncodeParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
@@ -599,8 +609,20 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   uint64_t *in_tiles = reinterpret_cast<uint64_t *>(wbase);
   uint32_t *out_tile = reinterpret_cast<uint32_t *>(in_tiles + 4 * ENC_IN_TILE_DWORDS);
 
-  const uint64_t warp_s0 = ((uint64_t)blockIdx.x * ENC_WARPS + warp) * 32ull;
-  if (warp_s0 >= p.n_series) return;
+  const uint64_t n_batches = (p.n_series + 31) >> 5;
+  const uint64_t warp_slot = (uint64_t)blockIdx.x * ENC_WARPS + warp;  // PACKED: scratch slot set
+  for (uint64_t batch_iter = 0;; batch_iter++) {
+  uint64_t batch;
+  if (PACKED) {
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(p.batch_counter, 1ull);
+    batch = __shfl_sync(FULL_MASK, b, 0);
+  } else {
+    if (batch_iter) break;
+    batch = warp_slot;
+  }
+  if (batch >= n_batches) break;
+  const uint64_t warp_s0 = batch * 32ull;
   const uint64_t sidx = warp_s0 + lane;
   const bool valid = sidx < p.n_series;
 
@@ -654,7 +676,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
 
   // Lane-local flush: every lane streams the complete 16-byte groups of ITS OWN
   // column to its slot (big-endian byte order) and keeps the <= 3 leftover words.
-  uint8_t *my_out = p.out + sidx * p.out_stride;
+  uint8_t *my_out = PACKED ? p.out + (warp_slot * 32ull + (uint64_t)lane) * p.out_stride
+                           : p.out + sidx * p.out_stride;
   auto flush_out = [&]() {
     __syncwarp();
     const uint32_t kmax = __reduce_max_sync(FULL_MASK, s.k);
@@ -904,29 +927,133 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
     s.k = 0;
   }
   flush_out();
-  if (valid) {
-    if (p.out_len) p.out_len[sidx] = (total_bits + 7) >> 3;
-    if (p.status) p.status[sidx] = s.err;
+  const uint64_t my_len = (total_bits + 7) >> 3;
+  if (valid && p.out_bits) p.out_bits[sidx] = total_bits;  // incl. the end-of-stream marker, before padding
+  if (valid && p.last_value) {
+    // Encoder.LastEncoded().Value (encoder.go:305-319): the float when the encoder is in float
+    // mode, else its intVal -- the SCALED integer in int mode, and 0 without the int optimisation
+    // (isFloat is never set there)
+    p.last_value[sidx] = (INT_OPT && s.is_float) ? __longlong_as_double((long long)s.prev_bits)
+                                                 : (INT_OPT ? s.int_val : 0.0);
   }
+  if (!PACKED) {
+    if (valid) {
+      if (p.out_len) p.out_len[sidx] = my_len;
+      if (p.status) p.status[sidx] = s.err;
+    }
+  } else {
+    // ---- allocate exact space and move the batch's streams into the packed buffer ----
+    const uint64_t amask = (uint64_t)p.align - 1;
+    const uint64_t alen = valid ? ((my_len + amask) & ~amask) : 0ull;
+    uint64_t incl = alen;  // inclusive warp scan
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t o = __shfl_up_sync(FULL_MASK, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const uint64_t total = __shfl_sync(FULL_MASK, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && total) base = atomicAdd(p.packed_cursor, (unsigned long long)total);
+    base = __shfl_sync(FULL_MASK, base, 0);
+    const bool fits = base + total <= p.packed_capacity;
+    const uint64_t my_off = base + incl - alen;
+    if (valid) {
+      p.packed_off[sidx] = my_off;
+      if (p.out_len) p.out_len[sidx] = fits ? my_len : 0ull;
+      if (p.status) p.status[sidx] = (!fits && s.err == 0) ? M3TSZ_ERR_CAPACITY : s.err;
+    }
+    __syncwarp();  // the slots were written lane-locally; the copy below reads other lanes' slots
+    if (fits && total) {
+      const uint8_t *slot0 = p.out + warp_slot * 32ull * p.out_stride;
+      if (p.align >= 16) {
+        // series after series, 32 lanes x 16 bytes, eight loads in flight per lane; the flush
+        // above zero-padded every stream to a whole 16-byte group inside its slot
+        for (int j = 0; j < 32; j++) {
+          const uint64_t lj = __shfl_sync(FULL_MASK, my_len, j);
+          const uint64_t oj = __shfl_sync(FULL_MASK, my_off, j);
+          if (lj == 0) continue;
+          const uint4 *src = reinterpret_cast<const uint4 *>(slot0 + (uint64_t)j * p.out_stride);
+          uint4 *dst = reinterpret_cast<uint4 *>(p.packed + oj);
+          const uint32_t nv = (uint32_t)((lj + 15) >> 4);
+          uint32_t i = lane;
+          for (; i + 224 < nv; i += 256) {
+            uint4 r[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) r[u] = __ldcg(src + i + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; u++) __stcs(dst + i + 32 * u, r[u]);
+          }
+          for (; i < nv; i += 32) __stcs(dst + i, __ldcg(src + i));
+        }
+      } else {
+        for (int j = 0; j < 32; j++) {
+          const uint64_t lj = __shfl_sync(FULL_MASK, my_len, j);
+          const uint64_t oj = __shfl_sync(FULL_MASK, my_off, j);
+          const uint8_t *src = slot0 + (uint64_t)j * p.out_stride;
+          uint8_t *dst = p.packed + oj;
+          for (uint64_t i = lane; i < lj; i += 32) dst[i] = __ldcg(src + i);
+        }
+      }
+    }
+    __syncwarp();  // the next batch overwrites the slots
+  }
+  }  // batch loop
+}
+
+template <bool INT_OPT, bool PACKED>
+static cudaError_t launch_encode_one(const EncodeParams &p, cudaStream_t stream) {
+  constexpr size_t smem = ENC_WARP_SMEM * ENC_WARPS;
+  const uint64_t per_block = (uint64_t)ENC_WARPS * 32ull;
+  uint64_t blocks = (p.n_series + per_block - 1) / per_block;
+  if (blocks == 0) return cudaSuccess;
+  if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(encode_kernel<INT_OPT, PACKED>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (PACKED) {
+    const uint64_t resident = encode_packed_resident_blocks();
+    if (resident == 0) return cudaErrorInvalidValue;
+    if (blocks > resident) blocks = resident;
+  }
+  encode_kernel<INT_OPT, PACKED><<<(unsigned)blocks, ENC_WARPS * 32, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// Persistent grid of the packed mode: resident blocks on the current device (also the number
+// of scratch slot sets: resident blocks x ENC_WARPS x 32 slots of out_stride bytes).
+uint64_t encode_packed_resident_blocks() {
+  constexpr size_t smem = ENC_WARP_SMEM * ENC_WARPS;
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (cudaFuncSetAttribute(encode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem) != cudaSuccess)
+    return 0;
+  if (cudaFuncSetAttribute(encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem) != cudaSuccess)
+    return 0;
+  int a = 0, b = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, encode_kernel<true, true>, ENC_WARPS * 32, smem) !=
+          cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, encode_kernel<false, true>, ENC_WARPS * 32, smem) !=
+          cudaSuccess)
+    return 0;
+  per_sm = a > b ? a : b;
+  return (uint64_t)sms * (uint64_t)per_sm;
+}
+uint64_t encode_packed_scratch_slots(uint64_t n_series) {
+  const uint64_t per_block = (uint64_t)ENC_WARPS * 32ull;
+  uint64_t blocks = (n_series + per_block - 1) / per_block;
+  const uint64_t resident = encode_packed_resident_blocks();
+  if (blocks > resident) blocks = resident;
+  return blocks * per_block;
 }
 
 cudaError_t launch_encode(const EncodeParams &p, bool int_optimized, cudaStream_t stream) {
-  constexpr size_t smem = ENC_WARP_SMEM * ENC_WARPS;
-  const uint64_t per_block = (uint64_t)ENC_WARPS * 32ull;
-  const uint64_t blocks = (p.n_series + per_block - 1) / per_block;
-  if (blocks == 0) return cudaSuccess;
-  if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
-  cudaError_t e;
-  if (int_optimized) {
-    e = cudaFuncSetAttribute(encode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    encode_kernel<true><<<(unsigned)blocks, ENC_WARPS * 32, smem, stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(encode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    encode_kernel<false><<<(unsigned)blocks, ENC_WARPS * 32, smem, stream>>>(p);
+  if (p.packed) {
+    return int_optimized ? launch_encode_one<true, true>(p, stream) : launch_encode_one<false, true>(p, stream);
   }
-  return cudaGetLastError();
+  return int_optimized ? launch_encode_one<true, false>(p, stream) : launch_encode_one<false, false>(p, stream);
 }
 
 // ---------------------------------------------------------------------------

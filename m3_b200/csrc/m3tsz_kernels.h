@@ -13,6 +13,7 @@ struct DecodeParams {
   const uint8_t *streams;
   uint64_t streams_bytes;
   const uint64_t *offsets;
+  const uint64_t *lengths;  // optional [n_series]: stream s = [offsets[s], offsets[s] + lengths[s])
   uint64_t n_series;
   int default_unit;
   // plain decode outputs (series-major [n_series][cap])
@@ -26,15 +27,22 @@ struct DecodeParams {
   int64_t *ds_count;
   double *ds_min;
   double *ds_max;
+  double *ds_last;      // mode 2
+  int64_t *ds_last_at;  // mode 2 (lastAt of every window; needed to re-open a window)
   // per-series outputs
   uint32_t *n_points;
   int32_t *status;
   uint8_t *unit_out;
   m3tsz_annotation_ref *ann_out;
+  uint8_t *unit_first_out;
+  // per-datapoint unit / annotation events (optional)
+  m3tsz_dp_event *events;
+  uint64_t events_capacity;
+  unsigned long long *event_count;
 };
 
-cudaError_t launch_decode(const DecodeParams &p, bool int_optimized, bool downsample,
-                          cudaStream_t stream);
+// mode: 0 plain decode, 1 fused downsample (sum/count/min/max), 2 fused downsample + last
+cudaError_t launch_decode(const DecodeParams &p, bool int_optimized, int mode, cudaStream_t stream);
 
 struct EncodeParams {
   const int64_t *ts;
@@ -53,8 +61,19 @@ struct EncodeParams {
   uint64_t out_stride;
   uint64_t *out_len;
   int32_t *status;
+  uint64_t *out_bits;   // optional [n_series]: stream length in bits (incl. the EOS marker)
+  double *last_value;  // optional [n_series]: Encoder.LastEncoded().Value incl. the scaled-int quirk
+  // packed mode (out = per-warp scratch slot sets, see encode_kernel)
+  uint8_t *packed;
+  uint64_t packed_capacity;
+  uint64_t *packed_off;                // [n_series] start of every stream in `packed`
+  unsigned long long *packed_cursor;   // bytes allocated so far (zero on entry)
+  unsigned long long *batch_counter;   // work counter (zero on entry)
+  uint32_t align;
 };
 
+uint64_t encode_packed_resident_blocks();
+uint64_t encode_packed_scratch_slots(uint64_t n_series);  // slots of out_stride bytes the packed mode needs
 cudaError_t launch_encode(const EncodeParams &p, bool int_optimized, cudaStream_t stream);
 
 // iterator layer above the codec (m3tsz_merge.cu)
@@ -87,6 +106,43 @@ struct ChecksumParams {
   int32_t *status;           // optional: OK / CHECKSUM_MISMATCH / INVALID_ARG / STREAM_TOO_LARGE
 };
 cudaError_t launch_checksum(const ChecksumParams &p, cudaStream_t stream);
+
+// Prometheus conversion epilogue (m3tsz_query.cu)
+struct PromParams {
+  const int64_t *ts;  // [n_series][cap]
+  const double *val;
+  uint64_t cap;
+  const uint32_t *n_points;
+  uint64_t n_series;
+  int64_t resolution;
+  const uint8_t *handle_resets;  // optional [n_series]
+  double tolerance;
+  int64_t tolerance_until;
+  int64_t *ts_out;  // [n_series][out_cap] milliseconds
+  double *val_out;
+  uint64_t out_cap;
+  uint32_t *n_out;
+  int32_t *status;  // optional
+};
+cudaError_t launch_prom(const PromParams &p, cudaStream_t stream);
+
+// tile aggregation glue (m3tsz_query.cu)
+struct TileParams {
+  const double *sum;  // window-major [n_windows][n_series]
+  const int64_t *count;
+  const double *mn, *mx, *last;
+  const int32_t *src_status;  // optional
+  uint64_t n_series;
+  uint32_t n_windows;
+  int64_t start, step;
+  int agg_type;
+  int64_t *ts_out;  // [n_series][n_windows]
+  double *val_out;
+  uint32_t *n_out;
+  int64_t *enc_start;  // [n_series] encoder start of the target block
+};
+cudaError_t launch_tiles_gather(const TileParams &p, cudaStream_t stream);
+cudaError_t launch_tiles_status(const int32_t *src_status, int32_t *status, uint64_t n, cudaStream_t stream);
 
 // exclusive scan of aligned lengths + gather into a packed buffer
 cudaError_t launch_compact(const uint8_t *slots, uint64_t slot_stride, const uint64_t *len,

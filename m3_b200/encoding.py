@@ -8,33 +8,32 @@ Reference interface mirrored (paths under /root/reference/src/dbnode/encoding):
   m3tsz.NewEncoder / NewReaderIterator / NewDecoder  m3tsz/encoder.go:64-85,
   m3tsz/iterator.go:67-78, m3tsz/decoder.go:33-38
 
-The per-datapoint methods are a buffered facade: Encoder.encode() validates and
-buffers, and the bitstream is produced by one GPU launch when stream()/len()/
-discard() is called; ReaderIterator decodes its whole stream with one GPU
-launch on the first next().  Real callers should batch many series per launch
-with m3_b200.codec.BatchCodec - a cgo call or a kernel launch per datapoint
-costs more than the reference spends encoding it.
+Every method is ONE call into the C ABI's streaming handles (m3tsz_encoder_* /
+m3tsz_iter_* / *_pool_*, include/m3tsz_b200.h) - the same entry points the cgo shim of
+INTEGRATION.md binds - so these classes are the executable check of that boundary.
+The handles buffer on the host: Encoder.encode() validates and buffers, the bitstream is
+produced by one GPU launch when stream()/len()/discard()/last_encoded() is called;
+ReaderIterator decodes its whole stream with one GPU launch on the first next().  Real
+callers should batch many series per launch with m3_b200.codec.BatchCodec - a cgo call
+or a kernel launch per datapoint costs more than the reference spends encoding it
+(SURVEY.md §7).
 """
+import ctypes as C
 import struct
-from typing import List, Optional, Tuple
-
-import numpy as np
-import torch
+from typing import Optional
 
 from . import capi
-from .codec import BatchCodec
 
 _UNIT_NS = [0, 10 ** 9, 10 ** 6, 10 ** 3, 1, 60 * 10 ** 9, 3600 * 10 ** 9, 86400 * 10 ** 9,
             365 * 86400 * 10 ** 9]
 
-_codecs = {}
+_ctxs = {}
 
 
-def _codec(int_optimized, default_unit, device=0) -> BatchCodec:
-    key = (bool(int_optimized), int(default_unit), device)
-    if key not in _codecs:
-        _codecs[key] = BatchCodec(device, int_optimized, default_unit)
-    return _codecs[key]
+def _ctx(device=0) -> capi.Context:
+    if device not in _ctxs:
+        _ctxs[device] = capi.Context(device)
+    return _ctxs[device]
 
 
 # XXH64 (seed 0) == cespare/xxhash/v2 Sum64, used only for LastAnnotationChecksum()
@@ -101,226 +100,157 @@ def _trunc_div(a: int, b: int) -> int:
     return q if (a >= 0) == (b >= 0) else -q
 
 
+def _check(rc, what=""):
+    if rc != capi.OK:
+        raise capi.M3tszError(rc, what)
+
+
 class Encoder:
-    """m3tsz encoder facade (m3tsz/encoder.go).  `start_ns` is the encoder start
-    (block start), not the first datapoint's time."""
+    """m3tsz encoder (m3tsz/encoder.go) over m3tsz_encoder_*.  `start_ns` is the encoder
+    start (block start), not the first datapoint's time."""
 
     def __init__(self, start_ns: int, int_optimized: bool = True, default_unit: int = capi.UNIT_S,
-                 device: int = 0):
-        self._int_optimized = bool(int_optimized)
-        self._default_unit = int(default_unit)
-        self._device = device
-        self._codec = _codec(int_optimized, default_unit, device)
-        self._closed = False
-        self._reset(start_ns)
+                 device: int = 0, _handle=None):
+        self._ctx = _ctx(device)
+        self._opts = capi.Options(int(bool(int_optimized)), int(default_unit))
+        self._owned = _handle is None
+        if _handle is None:
+            self._h = C.c_void_p()
+            _check(capi.lib().m3tsz_encoder_create(self._ctx.handle, C.byref(self._opts), int(start_ns),
+                                                   C.byref(self._h)), "m3tsz_encoder_create")
+        else:
+            self._h = _handle
+            _check(capi.lib().m3tsz_encoder_reset(self._h, int(start_ns), 0))
 
-    def _reset(self, start_ns):
-        self._start = int(start_ns)
-        self._ts: List[int] = []
-        self._vals: List[float] = []
-        self._units: List[int] = []
-        self._anns: List[Tuple[int, bytes]] = []
-        self._unit = initial_time_unit(self._start, self._default_unit)
-        self._prev_time = self._start
-        self._prev_delta = 0
-        self._ann_checksum = _EMPTY_ANN_CHECKSUM
-        self._cached: Optional[bytes] = None
+    def __del__(self):
+        try:
+            if self._owned and self._h:
+                capi.lib().m3tsz_encoder_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     # encoding.Encoder.Encode, m3tsz/encoder.go:90-110
     def encode(self, ts_ns: int, value: float, unit: int = capi.UNIT_S, annotation: bytes = b""):
-        if self._closed:
-            raise capi.M3tszError(2, "encoder is closed")
-        # host-side validation of the timestamp step (timestamp_encoder.go:104-246), so that
-        # Encode() fails at the datapoint that the reference fails on
-        delta = ts_ns - self._prev_time
-        changed = 1 <= unit <= 8 and unit != self._unit
-        if not changed:
-            if not (1 <= unit <= 8):
-                raise capi.M3tszError(capi.ERR_UNRECOGNIZED_UNIT)
-            dod = _trunc_div(delta - self._prev_delta, _UNIT_NS[unit])
-            if unit in (capi.UNIT_S, capi.UNIT_MS) and not (-2 ** 31 <= dod < 2 ** 31):
-                raise capi.M3tszError(
-                    capi.ERR_DOD_OVERFLOW,
-                    "deltaOfDelta value %d %s overflows 32 bits" % (dod, "s" if unit == 1 else "ms"))
         annotation = bytes(annotation or b"")
-        if annotation:
-            cs = xxh64(annotation)
-            if cs != self._ann_checksum:
-                self._ann_checksum = cs
-            self._anns.append((len(self._ts), annotation))
-        self._prev_time = ts_ns
-        if changed:
-            self._unit = unit
-            self._prev_delta = 0
-        else:
-            self._prev_delta = delta
-        self._ts.append(int(ts_ns))
-        self._vals.append(float(value))
-        self._units.append(int(unit))
-        self._cached = None
+        rc = capi.lib().m3tsz_encoder_encode(self._h, int(ts_ns), float(value), int(unit),
+                                             annotation if annotation else None, len(annotation))
+        if rc == capi.ERR_DOD_OVERFLOW:
+            # the reference formats the offending value into the message (timestamp_encoder.go:219)
+            dod = int(capi.lib().m3tsz_encoder_failed_dod(self._h))
+            raise capi.M3tszError(rc, "deltaOfDelta value %d %s overflows 32 bits"
+                                  % (dod, "s" if unit == capi.UNIT_S else "ms"))
+        _check(rc)
 
     def num_encoded(self) -> int:  # :299-302
-        return len(self._ts)
+        return int(capi.lib().m3tsz_encoder_num_encoded(self._h))
 
-    def last_encoded(self):  # :305-319 (returns the datapoint as written; see DESIGN.md §6)
-        if not self._ts:
-            raise capi.M3tszError(3)
-        return self._ts[-1], self._vals[-1]
+    def last_encoded(self):  # :305-319, with the reference's scaled-int / zero quirk
+        t, v = C.c_int64(), C.c_double()
+        _check(capi.lib().m3tsz_encoder_last_encoded(self._h, C.byref(t), C.byref(v)))
+        return t.value, v.value
 
     def last_annotation_checksum(self) -> int:  # :321-327
-        if not self._ts:
-            raise capi.M3tszError(3)
-        return self._ann_checksum
+        c = C.c_uint64()
+        _check(capi.lib().m3tsz_encoder_last_annotation_checksum(self._h, C.byref(c)))
+        return c.value
 
     def empty(self) -> bool:  # :330-332
-        return not self._ts
-
-    def _encode_now(self) -> bytes:
-        if self._cached is not None:
-            return self._cached
-        n = len(self._ts)
-        if n == 0:
-            self._cached = b""
-            return self._cached
-        dev = self._codec.device
-        ts = torch.tensor([self._ts], dtype=torch.int64, device=dev)
-        vals = torch.tensor([self._vals], dtype=torch.float64, device=dev)
-        units = torch.tensor([self._units], dtype=torch.uint8, device=dev)
-        start = torch.tensor([self._start], dtype=torch.int64, device=dev)
-        ann = None
-        ann_total = 0
-        if self._anns:
-            ent = np.zeros(len(self._anns), dtype=[("dp", "<u4"), ("len", "<u4"), ("off", "<u8")])
-            blob = bytearray()
-            for i, (dp, a) in enumerate(self._anns):
-                ent[i] = (dp, len(a), len(blob))
-                blob += a
-            ann_total = len(blob)
-            ann = (torch.tensor([0, len(self._anns)], dtype=torch.int64, device=dev),
-                   torch.from_numpy(ent.view(np.uint8).reshape(-1, 16).copy()).to(dev),
-                   torch.frombuffer(bytes(blob), dtype=torch.uint8).to(dev))
-        stride = self._codec.encode_bound(n) + ((ann_total + 16 * len(self._anns) + 15) // 16) * 16
-        res = self._codec.encode(ts, vals, start, unit=capi.UNIT_S, units=units, annotations=ann,
-                                 out_stride=stride)
-        st = int(res.status[0].item())
-        if st != capi.OK:
-            raise capi.M3tszError(st, "m3tsz_encode_batch status")
-        ln = int(res.out_len[0].item())
-        self._cached = bytes(res.out[0, :ln].cpu().numpy().tobytes())
-        return self._cached
-
-    def stream(self) -> Optional[bytes]:  # Stream(): (nil, false) when empty, :282-297
-        b = self._encode_now()
-        return b if b else None
+        return bool(capi.lib().m3tsz_encoder_empty(self._h))
 
     def len(self) -> int:  # :336-354
-        return len(self._encode_now())
+        n = C.c_uint64()
+        _check(capi.lib().m3tsz_encoder_len(self._h, C.byref(n)))
+        return n.value
+
+    def _segment(self, fn, *pre):
+        n = C.c_uint64()
+        _check(capi.lib().m3tsz_encoder_len(self._h, C.byref(n)))
+        buf = C.create_string_buffer(max(1, n.value))
+        ln, tail = C.c_uint64(), C.c_uint64()
+        _check(fn(self._h, *pre, buf, n.value, C.byref(ln), C.byref(tail)))
+        self._tail_len = tail.value
+        return buf.raw[: ln.value]
+
+    def stream(self) -> Optional[bytes]:  # Stream(): (nil, false) when empty, :282-297
+        b = self._segment(capi.lib().m3tsz_encoder_stream)
+        return b if b else None
+
+    def segment(self):
+        """ts.Segment view of the stream: (head, tail) (encoder.go:394-457)."""
+        b = self._segment(capi.lib().m3tsz_encoder_stream)
+        return b[: len(b) - self._tail_len], b[len(b) - self._tail_len:]
 
     def reset(self, start_ns: int, capacity: int = 0):  # :262-264
-        self._closed = False
-        self._reset(start_ns)
+        _check(capi.lib().m3tsz_encoder_reset(self._h, int(start_ns), int(capacity)))
 
     def close(self):  # :357-370
-        self._closed = True
-        self._ts, self._vals, self._units, self._anns = [], [], [], []
-        self._cached = None
+        _check(capi.lib().m3tsz_encoder_close(self._h))
 
     def discard(self) -> bytes:  # :374-381
-        b = self._encode_now()
-        self.close()
-        return b
+        return self._segment(capi.lib().m3tsz_encoder_discard)
 
     def discard_reset(self, start_ns: int, capacity: int = 0) -> bytes:  # :385-392
-        b = self._encode_now()
-        self.reset(start_ns, capacity)
-        return b
+        return self._segment(capi.lib().m3tsz_encoder_discard_reset, int(start_ns), int(capacity))
 
 
 class ReaderIterator:
-    """m3tsz reader iterator facade (m3tsz/iterator.go:67-278)."""
+    """m3tsz reader iterator (m3tsz/iterator.go:67-278) over m3tsz_iter_*."""
 
     def __init__(self, data: Optional[bytes], int_optimized: bool = True,
-                 default_unit: int = capi.UNIT_S, device: int = 0, max_points: int = 4096):
-        self._int_optimized = bool(int_optimized)
-        self._default_unit = int(default_unit)
-        self._codec = _codec(int_optimized, default_unit, device)
-        self._max_points = max_points
+                 default_unit: int = capi.UNIT_S, device: int = 0, _handle=None):
+        self._ctx = _ctx(device)
+        self._opts = capi.Options(int(bool(int_optimized)), int(default_unit))
+        self._owned = _handle is None
+        if _handle is None:
+            self._h = C.c_void_p()
+            _check(capi.lib().m3tsz_iter_create(self._ctx.handle, C.byref(self._opts), C.byref(self._h)),
+                   "m3tsz_iter_create")
+        else:
+            self._h = _handle
         self.reset(data)
 
-    def reset(self, data: Optional[bytes]):  # :253-263
-        self._data = bytes(data) if data is not None else None
-        self._decoded = False
-        self._i = -1
-        self._n = 0
-        self._err = 0
-        self._closed = False
-        self._ts = self._vals = None
-        self._unit = 0
-        self._ann = None
+    def __del__(self):
+        try:
+            if self._owned and self._h:
+                capi.lib().m3tsz_iter_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
-    def _decode_now(self):
-        if self._decoded:
-            return
-        self._decoded = True
-        data = self._data or b""
-        dev = self._codec.device
-        padded = data + b"\0" * ((-len(data)) % 16 + 16)
-        streams = torch.frombuffer(bytearray(padded), dtype=torch.uint8).to(dev)
-        offsets = torch.tensor([0, len(data)], dtype=torch.int64, device=dev)
-        cap = self._max_points
-        while True:
-            r = self._codec.decode(streams, offsets, cap, want_annotations=True)
-            n = int(r.n_points[0].item()) & 0xFFFFFFFF
-            st = int(r.status[0].item())
-            if st == capi.ERR_CAPACITY:
-                cap = max(n, cap * 2)
-                continue
-            break
-        self._n = min(n, cap)
-        self._err = st
-        self._ts = r.ts[0, : self._n].cpu().numpy()
-        self._vals = r.values[0, : self._n].cpu().numpy()
-        self._unit = int(r.unit[0].item())
-        a = r.annotations[0].cpu().numpy().tobytes()
-        bit_off, length, count = struct.unpack("<QII", a)
-        self._ann = (bit_off, length, count)
+    def reset(self, data: Optional[bytes]):  # :253-263
+        data = bytes(data) if data is not None else b""
+        self._first_ann = None
+        self._seen_first = False
+        _check(capi.lib().m3tsz_iter_reset(self._h, data if data else None, len(data)))
 
     def next(self) -> bool:  # :81-106
-        if self._closed:
-            return False
-        self._decode_now()
-        if self._i + 1 < self._n:
-            self._i += 1
-            return True
-        self._i = self._n
-        return False
+        ok = bool(capi.lib().m3tsz_iter_next(self._h))
+        if ok and not self._seen_first:
+            self._seen_first = True
+            self._first_ann = self.current_full()[3] or None
+        return ok
+
+    def current_full(self):
+        """Current(): (ts_ns, value, unit in force at this datapoint, annotation of this datapoint)."""
+        t, v, u = C.c_int64(), C.c_double(), C.c_int32()
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(capi.lib().m3tsz_iter_current(self._h, C.byref(t), C.byref(v), C.byref(u), C.byref(p), C.byref(n)))
+        ann = C.string_at(p.value, n.value) if n.value else b""
+        return t.value, v.value, u.value, ann
 
     def current(self):  # :229-231 -> (ts_ns, value, unit)
-        return int(self._ts[self._i]), float(self._vals[self._i]), self._unit
+        return self.current_full()[:3]
 
     def first_annotation(self) -> Optional[bytes]:
-        """Bytes of the first annotation in the stream (None if there is none)."""
-        self._decode_now()
-        bit_off, length, count = self._ann
-        if not count:
-            return None
-        data = self._data
-        bits = int.from_bytes(data, "big")
-        total = len(data) * 8
-        out = bytearray()
-        for i in range(length):
-            sh = total - (bit_off + 8 * (i + 1))
-            out.append((bits >> sh) & 0xFF)
-        return bytes(out)
+        """SeriesIterator.FirstAnnotation(): the first datapoint's annotation (None if it has none)."""
+        return self._first_ann
 
     def err(self) -> int:  # :234-236
-        if self._closed:
-            return 10
-        self._decode_now()
-        return self._err if self._i >= self._n - 1 or self._n == 0 else 0
+        return int(capi.lib().m3tsz_iter_err(self._h))
 
     def close(self):  # :267-278
-        self._closed = True
+        _check(capi.lib().m3tsz_iter_close(self._h))
 
 
 class Decoder:
@@ -333,3 +263,54 @@ class Decoder:
 
     def decode(self, data: bytes) -> ReaderIterator:
         return ReaderIterator(data, self._int_optimized, self._default_unit, self._device)
+
+
+class EncoderPool:
+    """encoding.EncoderPool (encoder_pool.go:27-48) over m3tsz_encoder_pool_*: get() hands out a
+    pooled encoder (the caller reset()s it); Encoder.close() / discard() returns it."""
+
+    def __init__(self, size: int, int_optimized: bool = True, default_unit: int = capi.UNIT_S, device: int = 0):
+        self._args = (bool(int_optimized), int(default_unit), device)
+        self._ctx = _ctx(device)
+        self._opts = capi.Options(int(bool(int_optimized)), int(default_unit))
+        self._h = C.c_void_p()
+        _check(capi.lib().m3tsz_encoder_pool_create(self._ctx.handle, C.byref(self._opts), int(size),
+                                                    C.byref(self._h)))
+
+    def get(self, start_ns: int = 0) -> Encoder:
+        h = C.c_void_p()
+        _check(capi.lib().m3tsz_encoder_pool_get(self._h, C.byref(h)))
+        return Encoder(start_ns, *self._args, _handle=h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().m3tsz_encoder_pool_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class ReaderIteratorPool:
+    """encoding.ReaderIteratorPool (iterator_pool.go:27-47) over m3tsz_iter_pool_*."""
+
+    def __init__(self, size: int, int_optimized: bool = True, default_unit: int = capi.UNIT_S, device: int = 0):
+        self._args = (bool(int_optimized), int(default_unit), device)
+        self._ctx = _ctx(device)
+        self._opts = capi.Options(int(bool(int_optimized)), int(default_unit))
+        self._h = C.c_void_p()
+        _check(capi.lib().m3tsz_iter_pool_create(self._ctx.handle, C.byref(self._opts), int(size),
+                                                 C.byref(self._h)))
+
+    def get(self, data: Optional[bytes] = None) -> ReaderIterator:
+        h = C.c_void_p()
+        _check(capi.lib().m3tsz_iter_pool_get(self._h, C.byref(h)))
+        return ReaderIterator(data, *self._args, _handle=h)
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().m3tsz_iter_pool_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

@@ -190,6 +190,19 @@ uint32_t m3o_adler32(const uint8_t *data, size_t n);
 void m3o_adler32_batch(const uint8_t *streams, const uint64_t *offsets, uint64_t n_series,
                        const uint32_t *expected, uint32_t *out, int32_t *status);
 
+/* ---- query-side consumers of the decode path (m3tsz_query_oracle.c) ---- */
+/* iteratorToPromResult, src/query/storage/prom_converter.go:42-120 */
+size_t m3o_prom_convert_series(const int64_t *ts, const double *vals, size_t n, int64_t resolution_ns,
+                               int handle_resets, double value_decrease_tolerance,
+                               int64_t tolerance_until_ns, int64_t *ts_ms_out, double *val_out,
+                               size_t out_cap);
+/* Gauge.ValueOf (gauge.go:144-165); agg_type = aggregation.Type id (1 Last, 2 Min, 3 Max, 4 Mean, 6 Count, 7 Sum) */
+double m3o_gauge_value_of(int agg_type, double sum, int64_t count, double min, double max, double last);
+/* decode -> Gauge per Step window -> one datapoint per non-empty window at the window end */
+size_t m3o_aggregate_tiles_series(const int64_t *ts, const double *vals, size_t n, int64_t start_ns,
+                                  int64_t step_ns, size_t n_windows, int agg_type, int64_t *ts_out,
+                                  double *val_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -325,6 +325,83 @@ def main():
     }
     g["precision_value"] = {"src": "encoding/m3tsz/roundtrip_test.go:94-106", "value": 187.80131100000006}
 
+    # ---- aggregation.Gauge tables: src/aggregator/aggregation/gauge_test.go ----
+    # time.Now() in the Go tests is strictly increasing between calls: times are given as offsets.
+    g["gauge"] = {
+        "src": "aggregator/aggregation/gauge_test.go:35-57 (default), :59-105 (UpdatePrevious prefix), "
+               ":117-170 (custom types), :173-195 (last, out of order)",
+        "cases": [
+            {"name": "1..100", "src_line": "gauge_test.go:35-48,121-147",
+             "times": list(range(100)), "values": [float(i) for i in range(1, 101)],
+             "last": 100.0, "count": 100, "mean": 50.5, "max": 100.0, "min": 1.0, "sum": 5050.0},
+            {"name": "empty", "src_line": "gauge_test.go:49-57,149-170",
+             "times": [], "values": [],
+             "last": 0.0, "count": 0, "mean": 0.0, "max": "NaN", "min": "NaN", "sum": 0.0},
+            {"name": "1,2,3", "src_line": "gauge_test.go:64-75",
+             "times": [0, 1, 2], "values": [1.0, 2.0, 3.0],
+             "last": 3.0, "count": 3, "mean": 2.0, "max": 3.0, "min": 1.0, "sum": 6.0},
+            {"name": "last out of order", "src_line": "gauge_test.go:173-195",
+             # timeMid = now+60s; pre = mid-1s; prepre = mid-1s; after = mid+1s
+             "times": [60, 59, 61, 59], "values": [42.0, 41.0, 43.0, 40.0],
+             "last": 43.0, "out_of_order": 2},  # the test asserts only Last() and the counter
+        ],
+    }
+
+    # ---- Prometheus conversion epilogue: src/query/storage/prom_converter_test.go ----
+    HOUR, MIN = 3600 * SEC, 60 * SEC
+    T0 = 1600000000 // 3600 * 3600 * SEC  # xtime.Now().Truncate(time.Hour): any hour-aligned instant
+
+    def dps(*pairs):
+        return [[T0 + off, v] for off, v in pairs]
+
+    def samples(*pairs):
+        return [[(T0 + off) // MS, v] for off, v in pairs]
+
+    g["prom_counter_normalization"] = {
+        "src": "query/storage/prom_converter_test.go:319-440 (resolutionThreshold = 5m default, options.go:30; "
+               "handleResets = isCounter && maxResolution >= threshold, prom_converter.go:74-82)",
+        "resolution_threshold_ns": 5 * MIN,
+        "cases": [
+            {"name": "low resolution gauge", "is_counter": False, "max_resolution_ns": HOUR,
+             "given": dps((0, 1), (HOUR, 2)), "want": samples((0, 1), (HOUR, 2))},
+            {"name": "high resolution gauge", "is_counter": False, "max_resolution_ns": MIN,
+             "given": dps((0, 1), (MIN, 2)), "want": samples((0, 1), (MIN, 2))},
+            {"name": "low resolution counter, no datapoints", "is_counter": True, "max_resolution_ns": HOUR,
+             "given": [], "want": []},
+            {"name": "low resolution counter, one datapoint", "is_counter": True, "max_resolution_ns": HOUR,
+             "given": dps((0, 1)), "want": samples((0, 1))},
+            {"name": "high resolution counter with no resets", "is_counter": True, "max_resolution_ns": MIN,
+             "given": dps((0, 1), (MIN, 2), (2 * MIN, 2), (3 * MIN, 3)),
+             "want": samples((0, 1), (MIN, 2), (2 * MIN, 2), (3 * MIN, 3))},
+            {"name": "high resolution counter with resets", "is_counter": True, "max_resolution_ns": MIN,
+             "given": dps((0, 10), (MIN, 3), (2 * MIN, 5), (3 * MIN, 8)),
+             "want": samples((0, 10), (MIN, 3), (2 * MIN, 5), (3 * MIN, 8))},
+            {"name": "low resolution counter with no resets", "is_counter": True, "max_resolution_ns": HOUR,
+             "given": dps((0, 1), (MIN, 2), (HOUR, 2), (HOUR + MIN, 3)),
+             "want": samples((MIN, 2), (HOUR + MIN, 3))},
+            {"name": "low resolution counter with resets", "is_counter": True, "max_resolution_ns": HOUR,
+             "given": dps((0, 10), (MIN, 3), (HOUR, 5), (HOUR + MIN, 8)),
+             "want": samples((MIN, 13), (HOUR + MIN, 18))},
+        ],
+    }
+    a, b = 187.80131100000006, 187.801311
+    g["prom_value_decrease_tolerance"] = {
+        "src": "query/storage/prom_converter_test.go:444-500 (datapoint i at now + i minutes)",
+        "now_ns": T0, "step_ns": MIN,
+        "cases": [
+            {"name": "no tolerance", "given": [a, b, a, b, 200, 199.99], "tolerance": 0, "until_ns": 0,
+             "want": [a, b, a, b, 200, 199.99]},
+            {"name": "low tolerance", "given": [a, b, a, b, 200, 199.99], "tolerance": 0.00000001,
+             "until_ns": T0 + HOUR, "want": [a, a, a, a, 200, 199.99]},
+            {"name": "high tolerance", "given": [a, b, a, b, 200, 199.99], "tolerance": 0.0001,
+             "until_ns": T0 + HOUR, "want": [a, a, a, a, 200, 200]},
+            {"name": "tolerance expired", "given": [200, 199.99, 200, 199.99, 200, 199.99], "tolerance": 0.0001,
+             "until_ns": T0, "want": [200, 199.99, 200, 199.99, 200, 199.99]},
+            {"name": "tolerance expires in the middle", "given": [200, 199.99, 200, 199.99, 200, 199.99],
+             "tolerance": 0.0001, "until_ns": T0 + 3 * MIN, "want": [200, 200, 200, 199.99, 200, 199.99]},
+        ],
+    }
+
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1)

@@ -108,6 +108,12 @@ def lib():
                                        vp, C.c_size_t, vp, vp, C.c_int]),
         "m3o_downsample_series": (None, [vp, vp, C.c_size_t, C.c_int64, C.c_int64, C.c_size_t, vp, vp,
                                          vp, vp, vp]),
+        "m3o_prom_convert_series": (C.c_size_t, [vp, vp, C.c_size_t, C.c_int64, C.c_int, C.c_double, C.c_int64,
+                                                 vp, vp, C.c_size_t]),
+        "m3o_gauge_value_of": (C.c_double, [C.c_int, C.c_double, C.c_int64, C.c_double, C.c_double,
+                                            C.c_double]),
+        "m3o_aggregate_tiles_series": (C.c_size_t, [vp, vp, C.c_size_t, C.c_int64, C.c_int64, C.c_size_t,
+                                                    C.c_int, vp, vp]),
         "m3o_series_merge_batch": (None, [vp, vp, C.c_uint64, vp, vp, vp, vp, vp, C.c_uint64, C.c_int64,
                                           C.c_int64, C.c_int, vp, vp, C.c_uint64, vp, vp]),
         "m3o_adler32": (C.c_uint32, [C.c_char_p, C.c_size_t]),
@@ -346,6 +352,35 @@ def downsample_series(ts, vals, range_start_ns, window_ns, n_windows):
     lib().m3o_downsample_series(_ptr(ts), _ptr(vals), len(ts), int(range_start_ns), int(window_ns),
                                 n_windows, _ptr(s), _ptr(c), _ptr(mn), _ptr(mx), _ptr(last))
     return s, c, mn, mx, last
+
+
+AGG_LAST, AGG_MIN, AGG_MAX, AGG_MEAN, AGG_COUNT, AGG_SUM = 1, 2, 3, 4, 6, 7  # aggregation.Type ids
+
+
+def prom_convert_series(ts, vals, resolution_ns, handle_resets, tolerance=0.0, until_ns=0):
+    """iteratorToPromResult over one decoded series -> (ts_ms int64[], values float64[])."""
+    ts = np.ascontiguousarray(ts, dtype=np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    cap = len(ts) + 1
+    to = np.zeros(cap, dtype=np.int64)
+    vo = np.zeros(cap, dtype=np.float64)
+    n = lib().m3o_prom_convert_series(_ptr(ts), _ptr(vals), len(ts), int(resolution_ns), int(bool(handle_resets)),
+                                      float(tolerance), int(until_ns), _ptr(to), _ptr(vo), cap)
+    return to[:n].copy(), vo[:n].copy()
+
+
+def gauge_value_of(agg_type, s, c, mn, mx, last):
+    return float(lib().m3o_gauge_value_of(int(agg_type), float(s), int(c), float(mn), float(mx), float(last)))
+
+
+def aggregate_tiles_series(ts, vals, start_ns, step_ns, n_windows, agg_type):
+    ts = np.ascontiguousarray(ts, dtype=np.int64)
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    to = np.zeros(max(1, n_windows), dtype=np.int64)
+    vo = np.zeros(max(1, n_windows), dtype=np.float64)
+    n = lib().m3o_aggregate_tiles_series(_ptr(ts), _ptr(vals), len(ts), int(start_ns), int(step_ns),
+                                         int(n_windows), int(agg_type), _ptr(to), _ptr(vo))
+    return to[:n].copy(), vo[:n].copy()
 
 
 def convert_to_int_float(v, cur_max_mult):

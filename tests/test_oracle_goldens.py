@@ -500,3 +500,60 @@ def test_downsample_oracle_gauge_semantics():
     assert s[0] == 2.0 and mn[0] == -2.0 and mx[0] == 3.0 and last[0] == -2.0
     assert s[1] == 5.0 and s[2] == 0.0 and math.isnan(mn[2]) and math.isnan(mx[2])
     assert s[3] == 15.0 and last[3] == 8.0
+
+
+# ------------------------------------------------------------------ Gauge tables (pins the downsample oracle)
+def test_downsample_oracle_pinned_by_gauge_test_tables():
+    """aggregator/aggregation/gauge_test.go tables, through m3o_downsample_series (one window
+    = one Gauge) and m3o_gauge_value_of (Gauge.ValueOf)."""
+    for case in G["gauge"]["cases"]:
+        ts = np.array(case["times"], dtype=np.int64) * SEC + 1000 * SEC
+        vals = np.array(case["values"], dtype=np.float64)
+        s, c, mn, mx, last = O.downsample_series(ts, vals, 0, 10_000 * SEC, 1)
+        assert last[0] == case["last"], case["name"]
+        assert O.gauge_value_of(O.AGG_LAST, s[0], c[0], mn[0], mx[0], last[0]) == case["last"]
+        if "count" not in case:
+            continue
+        assert c[0] == case["count"] and s[0] == case["sum"], case["name"]
+        assert O.gauge_value_of(O.AGG_COUNT, s[0], c[0], mn[0], mx[0], last[0]) == float(case["count"])
+        assert O.gauge_value_of(O.AGG_SUM, s[0], c[0], mn[0], mx[0], last[0]) == case["sum"]
+        assert O.gauge_value_of(O.AGG_MEAN, s[0], c[0], mn[0], mx[0], last[0]) == case["mean"]
+        for key, arr, agg in (("min", mn, O.AGG_MIN), ("max", mx, O.AGG_MAX)):
+            got = O.gauge_value_of(agg, s[0], c[0], mn[0], mx[0], last[0])
+            if case[key] == "NaN":
+                assert math.isnan(arr[0]) and math.isnan(got)
+            else:
+                assert arr[0] == case[key] and got == case[key]
+        # SumSq / Stdev / unsupported types report 0 without HasExpensiveAggregations (gauge_test.go:43)
+        assert O.gauge_value_of(8, s[0], c[0], mn[0], mx[0], last[0]) == 0.0
+
+
+# ------------------------------------------------------------------ Prometheus epilogue tables
+def test_prom_convert_oracle_counter_normalization():
+    T = G["prom_counter_normalization"]
+    for case in T["cases"]:
+        res = case["max_resolution_ns"]
+        handle = case["is_counter"] and res >= T["resolution_threshold_ns"]
+        ts = [d[0] for d in case["given"]]
+        vals = [float(d[1]) for d in case["given"]]
+        to, vo = O.prom_convert_series(ts, vals, res, handle)
+        assert [[int(a), float(b)] for a, b in zip(to, vo)] == [[w[0], float(w[1])] for w in case["want"]], case["name"]
+
+
+def test_prom_convert_oracle_value_decrease_tolerance():
+    T = G["prom_value_decrease_tolerance"]
+    for case in T["cases"]:
+        n = len(case["given"])
+        ts = [T["now_ns"] + i * T["step_ns"] for i in range(n)]
+        to, vo = O.prom_convert_series(ts, case["given"], 0, False, case["tolerance"], case["until_ns"])
+        assert list(to) == [t // 1_000_000 for t in ts], case["name"]
+        assert list(vo) == [float(v) for v in case["want"]], case["name"]
+
+
+def test_aggregate_tiles_oracle_shape():
+    ts = np.array([0, 60, 120, 299, 300, 900, 901], dtype=np.int64) * SEC
+    vals = np.array([1.0, float("nan"), 3.0, -2.0, 5.0, 7.0, 8.0])
+    to, vo = O.aggregate_tiles_series(ts, vals, 0, 300 * SEC, 4, O.AGG_LAST)
+    assert list(to) == [300 * SEC, 600 * SEC, 1200 * SEC] and list(vo) == [-2.0, 5.0, 8.0]
+    to, vo = O.aggregate_tiles_series(ts, vals, 0, 300 * SEC, 4, O.AGG_MEAN)
+    assert list(vo) == [0.5, 5.0, 7.5]
