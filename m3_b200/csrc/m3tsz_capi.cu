@@ -339,6 +339,16 @@ int m3tsz_encode_batch_packed(m3tsz_ctx *ctx, const m3tsz_options *opts, const i
   p.packed_cursor = reinterpret_cast<unsigned long long *>(d_total_bytes);
   p.batch_counter = reinterpret_cast<unsigned long long *>(ctr);
   p.align = align;
+  {
+    // phase spread = one batch period (about half a microsecond per datapoint and warp on a B200,
+    // DESIGN.md §4.7), only when every warp slot gets several batches
+    static const long ns_per_dp = [] {
+      const char *e = getenv("M3TSZ_ENC_STAGGER_NS_PER_DP");
+      return e ? atol(e) : 500L;
+    }();
+    const uint64_t n_batches = (n_series + 31) / 32;
+    if (ns_per_dp > 0 && n_batches >= 3 * (slots / 32)) p.stagger_ns = points_stride * (uint64_t)ns_per_dp;
+  }
   CK(launch_encode(p, opts->int_optimized != 0, st));
   ctx->launches++;
   return M3TSZ_OK;

@@ -714,9 +714,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
           // every live lane: unconditional update (finished lanes compute garbage
           // they never read again)
           s.pos += c;
-          // xor = (top n bits of the field) << tz; nothing for the zero code or a malformed
-          // uncontained header (lz + n > 64: the reference shifts everything out)
-          const uint64_t xr = (zero || tz < 0) ? 0ull : ((field >> ((64 - n) & 63)) << (tz & 63));
+          // xor = (top n bits of the field) << tz; nothing for the zero code, an empty contained
+          // window (previous XOR zero) or a malformed uncontained header (lz + n > 64: the
+          // reference shifts everything out)
+          const uint64_t xr = (n == 0 || tz < 0) ? 0ull : ((field >> (64 - n)) << tz);
           if (MODE == 0) {
             s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
             s.prev_xor = xr;

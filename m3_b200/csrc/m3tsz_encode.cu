@@ -611,6 +611,21 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
 
   const uint64_t n_batches = (p.n_series + 31) >> 5;
   const uint64_t warp_slot = (uint64_t)blockIdx.x * ENC_WARPS + warp;  // PACKED: scratch slot set
+  if (PACKED && p.stagger_ns) {
+    // Batches of equal length keep the persistent warps in lockstep: everyone packs bits (ALU
+    // bound, DRAM half idle), then everyone copies (DRAM bound, ALU idle).  Spreading the warps'
+    // phases over one batch period lets the copies of some overlap the bit packing of the others.
+    const uint32_t h = (uint32_t)warp_slot * 2654435761u;  // golden-ratio hash: phases mix within an SM
+    const uint64_t delay = ((uint64_t)(h >> 8) * p.stagger_ns) >> 24;
+    uint64_t t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 >= delay) break;
+      const uint64_t rem = delay - (t1 - t0);
+      __nanosleep((unsigned)(rem > 20000 ? 20000 : rem));
+    }
+  }
   for (uint64_t batch_iter = 0;; batch_iter++) {
   uint64_t batch;
   if (PACKED) {

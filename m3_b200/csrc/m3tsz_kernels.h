@@ -70,6 +70,7 @@ struct EncodeParams {
   unsigned long long *packed_cursor;   // bytes allocated so far (zero on entry)
   unsigned long long *batch_counter;   // work counter (zero on entry)
   uint32_t align;
+  uint64_t stagger_ns;  // start-up phase spread of the persistent warps (0 = none)
 };
 
 uint64_t encode_packed_resident_blocks();

@@ -465,3 +465,140 @@ def test_aggregate_tiles_byte_identical(codecs, int_opt, agg):
         assert nt[s] == len(tts), s
         exp = O.encode_series(tts, tvals, START, O.UNIT_S, int_opt) if len(tts) else b""
         assert packed[g_off[s]: g_off[s] + g_len[s]].tobytes() == exp, (s, agg)
+
+
+# ------------------------------------------------------------------ boundary: streaming handles + pools
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_streaming_handles_vs_oracle(int_opt):
+    """m3tsz_encoder_* / m3tsz_iter_* (through the Python mirror of the Go interfaces) against the
+    oracle's Encoder / Iterator: bytes, accessors incl. the LastEncoded scaled-int quirk
+    (encoder.go:305-319), per-datapoint unit + annotation out of Current()."""
+    from m3_b200 import capi
+    from m3_b200.encoding import Encoder, ReaderIterator
+    rng = np.random.default_rng(77)
+    units = [O.UNIT_S, O.UNIT_MS, O.UNIT_US, O.UNIT_NS]
+    for trial in range(6):
+        e, o = Encoder(START, int_opt), O.Encoder(START, int_opt)
+        assert e.empty() and e.stream() is None and e.len() == 0 and e.num_encoded() == 0
+        with pytest.raises(capi.M3tszError) as ei:
+            e.last_encoded()
+        assert ei.value.status == 3  # errNoEncodedDatapoints
+        t, v, unit = START, 50.0, O.UNIT_S
+        for i in range(150):
+            if trial % 2 and rng.random() < 0.05:
+                unit = units[int(rng.integers(0, 4))]
+            t += int(rng.integers(1, 50)) * SEC
+            v += float(rng.normal())
+            val = [round(v, 2), float(round(v)), v, round(v, 1)][trial % 4]
+            ann = bytes(rng.integers(0, 256, size=int(rng.integers(1, 30)), dtype=np.uint8)) \
+                if rng.random() < 0.06 else b""
+            e.encode(t, val, unit, ann)
+            assert o.encode(t, val, unit, ann) == 0
+            if i in (0, 1, 7, 60, 149):  # accessors mid-stream force a launch each time
+                assert e.stream() == o.stream() and e.len() == o.len()
+                ot, ov, oerr = o.last_encoded()
+                assert oerr == 0 and e.last_encoded() == (ot, ov), (trial, i)
+                assert e.last_annotation_checksum() == o.last_annotation_checksum()[0]
+                assert e.num_encoded() == o.num_encoded() and not e.empty()
+        head, tail = e.segment()
+        raw, pos = o.raw()
+        assert head == raw[:-1] and len(tail) in (2, 3) and head + tail == o.stream()
+        data = e.stream()
+        it = ReaderIterator(data, int_opt)
+        oit = O.Iterator(data, int_opt)
+        n = 0
+        while oit.next():
+            assert it.next()
+            assert it.current_full() == oit.current(), (trial, n)
+            n += 1
+        assert not it.next() and it.err() == 0 and n == 150
+        # truncated stream: the error becomes visible with the Next() that fails
+        cut = data[: len(data) // 2]
+        it.reset(cut)
+        oit = O.Iterator(cut, int_opt)
+        while oit.next():
+            assert it.next() and it.err() == 0
+            assert it.current() == oit.current()[:3]
+        if not int_opt:  # int mode: DESIGN.md §6.1 (the reference may run on past a failed read)
+            assert not it.next() and it.err() == oit.err() != 0
+        it.close()
+        assert it.err() == 10 and not it.next()
+        seg = e.discard()
+        assert seg == data
+        with pytest.raises(capi.M3tszError) as ei:
+            e.encode(t + SEC, 1.0, O.UNIT_S)
+        assert ei.value.status == 2  # errEncoderClosed
+        e.reset(START + 7200 * SEC)
+        e.encode(START + 7201 * SEC, 1.5, O.UNIT_S)
+        assert e.num_encoded() == 1
+
+
+def test_last_encoded_quirk_values():
+    from m3_b200.encoding import Encoder
+    e = Encoder(START, True)
+    e.encode(START + SEC, 12.5, O.UNIT_S)  # int mode with multiplier 1: intVal = 125
+    assert e.last_encoded() == (START + SEC, 125.0)
+    e.encode(START + 2 * SEC, 0.123456789012, O.UNIT_S)  # float mode: the value itself
+    assert e.last_encoded() == (START + 2 * SEC, 0.123456789012)
+    f = Encoder(START, False)
+    f.encode(START + SEC, 12.5, O.UNIT_S)  # no int optimisation: isFloat never set -> intVal 0
+    assert f.last_encoded() == (START + SEC, 0.0)
+
+
+def test_pools():
+    from m3_b200.encoding import EncoderPool, ReaderIteratorPool
+    pool = EncoderPool(2)
+    a, b, c = pool.get(START), pool.get(START), pool.get(START)  # the third is allocated on demand
+    for k, e in enumerate((a, b, c)):
+        e.encode(START + SEC, float(k), O.UNIT_S)
+    streams = [e.discard() for e in (a, b, c)]  # Discard closes: back to the pool
+    d = pool.get(START)
+    assert d.empty() and d.num_encoded() == 0
+    d.encode(START + SEC, 2.0, O.UNIT_S)
+    assert d.stream() == streams[2]
+    ip = ReaderIteratorPool(1)
+    it = ip.get(streams[1])
+    assert it.next() and it.current() == (START + SEC, 1.0, O.UNIT_S) and not it.next() and it.err() == 0
+    it.close()
+    it2 = ip.get(streams[0])
+    assert it2.next() and it2.current()[1] == 0.0
+
+
+# ------------------------------------------------------------------ row N2: fileset ingestion
+def test_fileset_ingest_and_tool(codecs, tmp_path, capsys):
+    from m3_b200 import fileset as F
+    from m3_b200.tools import read_data_files
+    rng = np.random.default_rng(3)
+    S, P = 400, 60
+    streams, _ = _annotated_streams(rng, S, P, True)
+    ids = [b"id-%04d" % int(i) for i in rng.permutation(S)]
+    blob = b"".join(streams)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in streams])])[:-1]
+    F.write_fileset(str(tmp_path), "ns", 3, START, 7200 * SEC, ids, blob, off, [len(s) for s in streams])
+    fs = F.read_fileset(str(tmp_path), "ns", 3, START)
+    res, ck = F.decode_fileset(codecs[True], fs, P)
+    torch.cuda.synchronize()
+    assert (ck.cpu().numpy() == 0).all() and (res.status.cpu().numpy() == 0).all()
+    by_id = dict(zip(ids, streams))
+    gts, gv = res.ts.cpu().numpy(), res.values.cpu().numpy()
+    for k in range(0, S, 13):
+        ots, ovals, err, _ = oracle_decode(by_id[fs.ids[k]], True)
+        assert (gts[k, :P] == ots).all() and (gv[k, :P].view(np.uint64) == ovals.view(np.uint64)).all()
+    # a flipped data byte is caught by the DEVICE checksum against the index entry
+    bad = F.FilesetData(fs.info, fs.ids, fs.tags, fs.offsets, fs.sizes, fs.data_checksums, np.array(fs.data))
+    bad.data[int(fs.offsets[5]) + 3] ^= 1
+    _, ck = F.decode_fileset(codecs[True], bad, P)
+    torch.cuda.synchronize()
+    ckn = ck.cpu().numpy()
+    assert ckn[5] == 15 and (np.delete(ckn, 5) == 0).all()  # M3TSZ_ERR_CHECKSUM_MISMATCH
+    # the tool: same report as the reference's read_data_files --benchmark datapoints
+    rc = read_data_files.main(["-p", str(tmp_path), "-n", "ns", "-s", "3", "-b", str(START), "-B", "datapoints"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "%d series read" % S in out and "%d datapoints decoded" % (S * P) in out
+    rc = read_data_files.main(["-p", str(tmp_path / "gen"), "-n", "g", "-s", "0", "--generate", "3000", "--points",
+                               "50", "-B", "datapoints"])
+    out = capsys.readouterr().out
+    assert rc == 0 and "150000 datapoints decoded" in out
+    rc = read_data_files.main(["-p", str(tmp_path), "-n", "ns", "-s", "3", "-b", str(START), "-f", "id-0007"])
+    out = capsys.readouterr().out
+    assert rc == 0 and out.count("{id: id-0007") == P
