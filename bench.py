@@ -3,22 +3,25 @@
 
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
 prints ONE JSON line on rank 0.  One "step" = one pass of the hot path over one
-batch: batch ENCODE of S series x P points (lane-per-series sm_100a kernel),
-stream compaction, and batch DECODE of the resulting bitstreams.  The batch is
-1M series x 1440 points per GPU -- the shape BASELINE.json's north-star target is
-quoted on (configs[2-4]; configs[4] = 8M series over 8 GPUs = this at N=8); with
-N GPUs every rank holds its own 1M-series shard (weak scaling, no data-path
-collective: series are independent).  `--series 100000` runs configs[1].
+batch: batch ENCODE of S series x P points straight into one packed buffer
+(lane-per-series sm_100a kernel; no slots, no compaction pass) and batch DECODE of
+the resulting bitstreams.  The batch is 1M series x 1440 points per GPU -- the shape
+BASELINE.json's north-star target is quoted on (configs[2-4]; configs[4] = 8M series
+over 8 GPUs = this at N=8); with N GPUs every rank holds its own 1M-series shard
+(weak scaling, no data-path collective: series are independent).  `--series 100000`
+runs configs[1].
 
   value   = S*P*N / step time, inputs and outputs resident in HBM (CUDA events)
-  e2e     = the same step through the C ABI's *_host entry points with pinned
-            HOST buffers (H2D of inputs and D2H of results inside the timed region)
-  roofline= the decode kernel: algorithmic bytes (compressed bytes + CSR offsets
-            in, 16 B/dp out) / its average duration inside the timed region
-  cpu_baseline = the CPU oracle (plain-C restatement of the reference's Go codec;
-            no Go toolchain in this image) on all host cores, bounded sample
+  e2e     = the SAME batch through the C ABI's *_host entry points from pinned HOST
+            buffers, chunk by chunk (H2D of the inputs and D2H of the results inside
+            the timed region; the encode and the decode leg run from two host threads so
+            both PCIe directions stay busy)
+  roofline= the decode kernel: algorithmic bytes (compressed bytes + index entries in,
+            16 B/dp out) / its average duration inside the timed region
+  cpu_baseline = the CPU oracle (plain-C restatement of the reference's Go codec; no Go
+            toolchain in this image) on the host cores this process may use, bounded sample
 
-`--impl reference` times that CPU oracle as the reference arm.
+`--impl reference` times that CPU oracle as the reference arm on the full batch.
 """
 import argparse
 import json
@@ -40,20 +43,112 @@ L2_BYTES = 126 * 1024 * 1024
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--series", type=int, default=1_000_000, help="series per GPU")
-    ap.add_argument("--e2e-series", type=int, default=100_000,
-                    help="series of the batch pushed through the host-buffer API per e2e step")
+    ap.add_argument("--e2e-series", type=int, default=0,
+                    help="series pushed through the host-buffer API per e2e step (0 = the whole batch, "
+                         "reduced only if pinned host memory is short)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="e2e steps (0 = min(steps, 20))")
     ap.add_argument("--points", type=int, default=1440)
     ap.add_argument("--int-optimized", type=int, default=1)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget (GPU arm)")
+    ap.add_argument("--ref-seconds", type=float, default=1200.0,
+                    help="reference arm: shrink the per-step sample only if the full batch would exceed this")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
-                    help="headline step only (no downsample / merge / fixtures / all-gather side measurements)")
+                    help="headline step only (no downsample / merge / tiles / fixtures / all-gather side measurements)")
     return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- host facts
+def usable_cores():
+    """Host threads this process can really use: the CPU affinity mask capped by the cgroup
+    CPU quota (os.cpu_count() reports the machine, not the lease)."""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    cores = aff if quota is None else max(1, min(aff, int(quota + 0.5)))
+    return cores, {"os_cpu_count": os.cpu_count(), "sched_affinity": aff,
+                   "cgroup_cpu_quota": quota, "used": cores}
+
+
+def available_host_bytes():
+    avail = None
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                avail = int(ln.split()[1]) * 1024
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v != "max":
+                lim = int(v)
+                use = 0
+                try:
+                    use = int(open(path.replace("memory.max", "memory.current")
+                                   .replace("memory.limit_in_bytes", "memory.usage_in_bytes")).read())
+                except Exception:
+                    pass
+                avail = min(avail, lim - use) if avail is not None else lim - use
+            break
+        except Exception:
+            continue
+    return avail if avail is not None else 64 << 30
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this rank's threads (and so its first-touch pinned allocations) to the NUMA node
+    its GPU hangs off; several ranks staging through one socket is what bent the N=8 e2e curve."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id  # torch >= 2.3
+    except Exception:
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id",
+                                  "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
+            bdf = out
+        except Exception:
+            return None
+    try:
+        if isinstance(bdf, int):
+            return None
+        bdf = bdf.lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+    return None
 
 
 def measured_peak_gbs():
@@ -66,13 +161,26 @@ def measured_peak_gbs():
 
 
 def recorded_traffic(workload):
-    """dram bytes per decode launch from the committed ncu --set full capture, if any."""
+    """dram bytes per decode launch from the committed ncu --set full capture of this workload
+    (profiles/traffic.json names the capture file); a citation, not a per-run measurement."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         return t.get(workload)
     except Exception:
         return None
+
+
+def make_config(S, P, int_opt, bytes_per_dp):
+    return {"workload": "batch of %d series x %d points per GPU (the north-star target shape "
+                        "1M x 1440 = configs[2-4] size; configs[4] = 8M over 8 GPUs), Gaussian "
+                        "random walk (x0=100, N(0,1) steps), 60 s cadence, unit=Second; step = "
+                        "encode (packed output) + decode" % (S, P),
+            "series_per_gpu": S, "points": P, "int_optimized": bool(int_opt),
+            "compressed_bytes_per_dp": round(bytes_per_dp, 4),
+            "l2": "inputs %.2f GB and outputs %.2f GB per step >> 126 MB L2, no flush needed"
+                  % (S * P * 16 / 1e9, S * P * (16 + bytes_per_dp) / 1e9),
+            "parallelism": "series sharded per GPU, no data-path collective"}
 
 
 class ClockSampler:
@@ -130,61 +238,117 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU oracle arm
-def cpu_oracle_throughput(n_series, n_points, int_opt, budget_s, steps=1, warmup=0):
-    """Times the CPU oracle (encode + decode of a Gaussian-walk sample) on all host
-    cores.  Returns (dp/s over the timed steps, dict describing the run)."""
-    import numpy as np
-    import torch
+class CpuOracleRunner:
+    """Encode + decode of Gaussian-walk chunks with the CPU oracle on `cores` threads (one thread
+    per disjoint series range, like the reference's one-goroutine-per-series fan-out).  Work
+    buffers belong to the runner and are reused; inputs are generated before the timed region."""
 
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import oracle_lib as O
-    from m3_b200 import synth
+    def __init__(self, n_points, int_opt, cores):
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        self.np, self.O = np, O
+        self.P, self.int_opt, self.cores = n_points, int_opt, cores
+        self.bufs = None
 
-    cores = os.cpu_count() or 1
-    probe_s = max(cores * 4, 64)
-    ts, vals, start = synth.gaussian_walk(probe_s, n_points, "cpu", seed=99)
-    ts_np, vals_np, st = ts.numpy(), vals.numpy(), int(start[0])
+    def make_chunks(self, n_series, chunk, seed):
+        from m3_b200 import synth
+        chunks = []
+        for c0 in range(0, n_series, chunk):
+            n = min(chunk, n_series - c0)
+            ts, vals, start = synth.gaussian_walk(n, self.P, "cpu", seed=seed + c0)
+            chunks.append((ts.numpy(), vals.numpy(), int(start[0])))
+        return chunks
 
-    state = {}
+    def _ensure(self, S):
+        np = self.np
+        if self.bufs is None or self.bufs["S"] < S:
+            stride = 64 + 20 * self.P
+            self.bufs = {"S": S,
+                         "enc": (np.zeros((S, stride), dtype=np.uint8), np.zeros(S, dtype=np.uint64),
+                                 np.zeros(S, dtype=np.int32)),
+                         "dec": (np.zeros((S, self.P), dtype=np.int64), np.zeros((S, self.P), dtype=np.float64),
+                                 np.zeros(S, dtype=np.uint32), np.zeros(S, dtype=np.int32)),
+                         "blob": np.zeros(S * (8 * self.P + 64), dtype=np.uint8)}
+        return self.bufs
 
-    def run(ts_np, vals_np):
+    def run_chunk(self, ts_np, vals_np, st):
+        np, O = self.np, self.O
         S = ts_np.shape[0]
-        if state.get("S") != S:  # preallocate + touch every output once (not timed)
-            stride = 64 + 20 * n_points
-            state.update(S=S, enc=(np.zeros((S, stride), dtype=np.uint8), np.zeros(S, dtype=np.uint64),
-                                   np.zeros(S, dtype=np.int32)),
-                         dec=(np.zeros((S, n_points), dtype=np.int64), np.zeros((S, n_points), dtype=np.float64),
-                              np.zeros(S, dtype=np.uint32), np.zeros(S, dtype=np.int32)))
+        b = self._ensure(S)
+        enc = tuple(x[:S] for x in b["enc"])
+        dec = tuple(x[:S] for x in b["dec"])
         t0 = time.perf_counter()
-        out, ln, status = O.encode_batch(ts_np, vals_np, st, 1, int_opt, n_threads=cores, bufs=state["enc"])
+        out, ln, status = O.encode_batch(ts_np, vals_np, st, 1, self.int_opt, n_threads=self.cores, bufs=enc)
         t1 = time.perf_counter()
+        # hand the streams to the decoder as one CSR buffer (not timed: the reference's iterators
+        # read the encoders' own buffers)
         off = np.zeros(S + 1, dtype=np.uint64)
         off[1:] = np.cumsum(ln)
-        blob = np.concatenate([out[i, : ln[i]] for i in range(S)])
+        total = int(off[-1])
+        blob = b["blob"][:total]
+        pos = 0
+        for i in range(S):
+            n = int(ln[i])
+            blob[pos:pos + n] = out[i, :n]
+            pos += n
         t2 = time.perf_counter()
-        O.decode_batch(blob, off, n_points, int_opt, n_threads=cores, bufs=state["dec"])
+        O.decode_batch(blob, off, self.P, self.int_opt, n_threads=self.cores, bufs=dec)
         t3 = time.perf_counter()
-        return (t1 - t0), (t3 - t2)
+        return (t1 - t0), (t3 - t2), total
 
-    run(ts_np, vals_np)  # warm the library / page in
-    te, td = run(ts_np, vals_np)
+    def run_step(self, chunks):
+        te = td = 0.0
+        nbytes = 0
+        for ts_np, vals_np, st in chunks:
+            a, b, n = self.run_chunk(ts_np, vals_np, st)
+            te += a
+            td += b
+            nbytes += n
+        return te, td, nbytes
+
+
+def cpu_oracle_throughput(n_series, n_points, int_opt, budget_s, steps=1, warmup=0, full=False):
+    """Times the CPU oracle on the host cores this process may use.  full=False: a bounded sample
+    sized to `budget_s`; full=True: the whole n_series batch per step, shrunk only if
+    (steps + warmup) steps would exceed budget_s.  Returns (dp/s, info)."""
+    cores, core_info = usable_cores()
+    runner = CpuOracleRunner(n_points, int_opt, cores)
+    probe_s = max(cores * 8, 128)
+    probe = runner.make_chunks(probe_s, probe_s, seed=99)
+    runner.run_step(probe)  # warm the library / page in
+    te, td, _ = runner.run_step(probe)
     per_series = (te + td) / probe_s
     total_steps = max(1, steps + warmup)
-    S = int(max(probe_s, min(n_series, budget_s / total_steps / max(per_series, 1e-9))))
-    S = max(cores, (S // cores) * cores)
-    ts, vals, start = synth.gaussian_walk(S, n_points, "cpu", seed=100)
-    ts_np, vals_np = ts.numpy(), vals.numpy()
+    fit = int(budget_s / total_steps / max(per_series, 1e-9))
+    if full:
+        S = n_series if fit >= n_series else max(probe_s, fit)
+        # host memory: inputs 16 B/dp for the whole batch + one chunk of work buffers
+        mem = available_host_bytes()
+        max_by_mem = int(0.5 * mem / (n_points * 16))
+        if S > max_by_mem:
+            S = max(probe_s, max_by_mem)
+    else:
+        S = int(max(probe_s, min(n_series, fit)))
+    S = max(cores, (S // cores) * cores) if S < n_series else S
+    chunk = min(S, 100_000)
+    chunks = runner.make_chunks(S, chunk, seed=100)
     for _ in range(warmup):
-        run(ts_np, vals_np)
+        runner.run_step(chunks)
     tot_e = tot_d = 0.0
+    nbytes = 0
     for _ in range(steps):
-        te, td = run(ts_np, vals_np)
+        te, td, nbytes = runner.run_step(chunks)
         tot_e += te
         tot_d += td
     dp = S * n_points * steps
     info = {
-        "cores": cores, "sample": "%d series x %d points per step (Gaussian walk, intOptimized=%s), "
-        "encode then decode, %d threads" % (S, n_points, bool(int_opt), cores),
+        "cores": cores, "core_info": core_info, "series_per_step": S, "full_batch": S == n_series,
+        "compressed_bytes_per_dp": nbytes / float(S * n_points),
+        "sample": "%d series x %d points per step%s (Gaussian walk, intOptimized=%s), encode then decode, "
+                  "%d threads (sched_getaffinity %s, cgroup quota %s, os.cpu_count %s)"
+                  % (S, n_points, " = the whole batch" if S == n_series else " (bounded sample)", bool(int_opt),
+                     cores, core_info["sched_affinity"], core_info["cgroup_cpu_quota"], core_info["os_cpu_count"]),
         "encode_dps": dp / tot_e, "decode_dps": dp / tot_d, "ms_per_step": (tot_e + tot_d) * 1e3 / steps,
         "kind": "port",
         "note": "C restatement of the reference algorithm (Go toolchain unavailable); published Go "
@@ -200,8 +364,7 @@ def fixture_set_throughput(codec, dev, time_fn, n_streams=200_000):
     launch.  The zero padding after each stream's end-of-stream marker is never parsed."""
     import base64
     import torch
-    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden",
-                                    "m3tsz_goldens.json")))
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "m3tsz_goldens.json")))
     raw = [base64.b64decode(x) for x in g["fixtures_b64"]["streams"]]
     pts = g["fixtures_b64"]["expected_points"]
     padded = [r + b"\0" * ((-len(r)) % 64) for r in raw]
@@ -225,19 +388,19 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, info = cpu_oracle_throughput(args.series, args.points, args.int_optimized,
-                                        budget_s=60.0, steps=args.steps, warmup=args.warmup)
+    value, info = cpu_oracle_throughput(args.series, args.points, args.int_optimized, budget_s=args.ref_seconds,
+                                        steps=args.steps, warmup=args.warmup, full=True)
+    cfg = make_config(args.series, args.points, args.int_optimized, info["compressed_bytes_per_dp"])
+    if not info["full_batch"]:
+        cfg["reference_sample"] = "bounded: %d of %d series per step" % (info["series_per_step"], args.series)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64/f64",
-        "data": "synthetic",
-        "config": {"workload": "CPU oracle encode+decode, bounded sample of %d-series x %d-point "
-                               "Gaussian-walk batch" % (args.series, args.points),
-                   "int_optimized": bool(args.int_optimized)},
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64/f64 (integer bit manipulation; float64 values)", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"], "encode_dps": info["encode_dps"],
-                         "decode_dps": info["decode_dps"], "note": info["note"]},
+                         "decode_dps": info["decode_dps"], "note": info["note"], "core_info": info["core_info"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -245,12 +408,163 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- GPU arm
+def run_e2e(args, codec, ts, vals, start, P, int_opt, rank, world, dev, barrier, dist):
+    """The whole batch through m3tsz_encode_batch_host / m3tsz_decode_batch_host from pinned host
+    memory, chunk by chunk.  Inputs: one pinned buffer per chunk (distinct data, H2D every step);
+    outputs: reusable pinned staging per leg (D2H every step, overwritten by the next chunk).  The
+    two legs run from two host threads (two contexts): encode of chunk c+1 overlaps decode of
+    chunk c, so the H2D-heavy and the D2H-heavy leg share the full-duplex link."""
+    import torch
+    from m3_b200.codec import BatchCodec
+    S = ts.shape[0]
+    chunk = min(S, 100_000)
+    want = args.e2e_series or S
+    per_series_pinned = P * 16
+    budget = 0.4 * available_host_bytes() / max(1, world) - 3 * chunk * P * 16
+    Se = int(max(chunk, min(want, S, budget // per_series_pinned)))
+    Se = (Se // chunk) * chunk if Se >= chunk else Se
+    n_chunks = (Se + chunk - 1) // chunk
+    bounds = [(c * chunk, min(Se, (c + 1) * chunk)) for c in range(n_chunks)]
+    h_in = []
+    for c0, c1 in bounds:  # distinct pinned inputs per chunk
+        h_in.append((ts[c0:c1].cpu().pin_memory(), vals[c0:c1].cpu().pin_memory(), start[c0:c1].cpu().pin_memory()))
+    e_cap = chunk * (P * 9 + 128)
+    # two sets of encode outputs (the decode leg reads set c%2 while the encode leg fills the other)
+    enc_out = [dict(packed=torch.empty(e_cap, dtype=torch.uint8).pin_memory(),
+                    off=torch.empty(chunk + 1, dtype=torch.int64).pin_memory(),
+                    ln=torch.empty(chunk, dtype=torch.int64).pin_memory(),
+                    st=torch.empty(chunk, dtype=torch.int32).pin_memory()) for _ in range(2)]
+    h_dts = torch.empty((chunk, P), dtype=torch.int64).pin_memory()
+    h_dvals = torch.empty((chunk, P), dtype=torch.float64).pin_memory()
+    h_n = torch.empty(chunk, dtype=torch.int32).pin_memory()
+    h_dst = torch.empty(chunk, dtype=torch.int32).pin_memory()
+    dec_codec = BatchCodec(dev.index, int_optimized=int_opt)  # second context: its own streams + scratch
+    state = {"bytes": 0, "err": None}
+
+    def host_step(check=False):
+        filled = [threading.Semaphore(0) for _ in range(n_chunks)]
+        freed = [threading.Semaphore(0) for _ in range(n_chunks)]
+        nbytes = [0] * n_chunks
+
+        def enc_leg():
+            try:
+                for c, (c0, c1) in enumerate(bounds):
+                    if c >= 2:
+                        freed[c - 2].acquire()
+                    o = enc_out[c % 2]
+                    n = c1 - c0
+                    codec.encode_host(h_in[c][0], h_in[c][1], h_in[c][2], 1, o["packed"], o["off"][: n + 1],
+                                      o["ln"][:n], o["st"][:n], align=64)
+                    nbytes[c] = int(o["off"][n])
+                    filled[c].release()
+            except Exception as e:  # pragma: no cover
+                state["err"] = e
+                for f in filled:
+                    f.release()
+
+        th = threading.Thread(target=enc_leg)
+        th.start()
+        for c, (c0, c1) in enumerate(bounds):
+            filled[c].acquire()
+            if state["err"] is not None:
+                break
+            o = enc_out[c % 2]
+            n = c1 - c0
+            dec_codec.decode_host(o["packed"][: nbytes[c]], o["off"][: n + 1], P, h_dts[:n], h_dvals[:n], h_n[:n],
+                                  h_dst[:n])
+            if check:
+                assert torch.equal(h_dts[:n], h_in[c][0]) and int((h_dst[:n] != 0).sum()) == 0
+            freed[c].release()
+        th.join()
+        if state["err"] is not None:
+            raise state["err"]
+        state["bytes"] = sum(nbytes)
+
+    host_step(check=True)
+    for _ in range(max(0, min(args.warmup, 2) - 1)):
+        host_step()
+    barrier()
+    l0 = codec.launch_count() + dec_codec.launch_count()
+    e_steps = args.e2e_steps or max(1, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        host_step()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e_launch = codec.launch_count() + dec_codec.launch_count() - l0
+    tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e_s = float(tt[0]) / e_steps
+    nb = state["bytes"]
+    h2d = Se * P * 16 + Se * 8 + nb + (Se + n_chunks) * 8
+    d2h = nb + (Se + n_chunks) * 8 + Se * 12 + Se * P * 16 + Se * 8
+    return {"value": Se * P * world / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": e_s * 1e3, "steps": e_steps, "launches_per_step": e_launch / e_steps,
+            "series_per_step": Se, "chunks_per_step": n_chunks, "whole_batch": Se == S,
+            "pcie_gbs_each_way": max(h2d, d2h) / e_s / 1e9,
+            "api": "m3tsz_encode_batch_host + m3tsz_decode_batch_host over %d-series chunks (pinned host "
+                   "inputs, reusable pinned result staging; encode leg and decode leg on two host threads / "
+                   "two contexts)" % chunk}
+
+
+def run_fetch_e2e(args, codec, ts, vals, start, P, rank, world, dev, barrier, dist):
+    """Fetch path with host buffers (RF=3): compressed replica streams up, merged series down."""
+    import numpy as np
+    import torch
+    Sf = min(ts.shape[0], 100_000)
+    enc = codec.encode(ts[:Sf], vals[:Sf], start[:Sf], unit=1)
+    cpacked, coff = codec.compact(enc, align=64)
+    torch.cuda.synchronize()
+    off = coff.cpu().numpy()
+    ln = enc.out_len.cpu().numpy()
+    blob = cpacked[: int(off[-1])].cpu().numpy()
+    del enc, cpacked, coff
+    # host CSR of 3 replicas per series: the same stream three times (replicas agree on a healthy cluster)
+    al = (ln + 63) // 64 * 64
+    seq_off = np.zeros(3 * Sf + 1, dtype=np.int64)
+    seq_off[1:] = np.cumsum(np.repeat(al, 3))
+    total = int(seq_off[-1])
+    h_streams = torch.zeros(total + 64, dtype=torch.uint8).pin_memory()
+    hs = h_streams.numpy()
+    for s in range(Sf):
+        seg = blob[off[s]: off[s] + ln[s]]
+        for r in range(3):
+            o = int(seq_off[3 * s + r])
+            hs[o: o + ln[s]] = seg
+    h_off = torch.from_numpy(seq_off).pin_memory()
+    ar = torch.arange(3 * Sf + 1, dtype=torch.int64)
+    h_slice, h_rep, h_ser = ar.clone(), ar.clone(), torch.arange(0, 3 * Sf + 1, 3, dtype=torch.int64)
+    h_ts = torch.empty((Sf, P), dtype=torch.int64).pin_memory()
+    h_val = torch.empty((Sf, P), dtype=torch.float64).pin_memory()
+    h_n = torch.empty(Sf, dtype=torch.int32).pin_memory()
+    h_st = torch.empty(Sf, dtype=torch.int32).pin_memory()
+
+    def step():
+        codec.fetch_host(h_streams[:total], h_off, h_slice, h_rep, h_ser, P, P, h_ts, h_val, h_n, h_st)
+
+    step()
+    assert int((h_st != 0).sum()) == 0 and bool((h_n == P).all())
+    assert torch.equal(h_ts, ts[:Sf].cpu())
+    barrier()
+    n_steps = 5
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        step()
+    t1 = time.perf_counter()
+    tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    s = float(tt[0]) / n_steps
+    return {"replicas": 3, "series": Sf, "input_dps": 3 * Sf * P * world / s, "output_dps": Sf * P * world / s,
+            "ms_per_step": s * 1e3, "h2d_bytes_per_step": total + (3 * Sf + 1) * 8,
+            "d2h_bytes_per_step": Sf * P * 16 + Sf * 8,
+            "api": "m3tsz_fetch_batch_host (H2D compressed replicas -> decode -> series merge -> D2H merged)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-
-    from m3_b200 import synth
-    from m3_b200.codec import BatchCodec, DecodeResult, EncodeResult
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -258,53 +572,49 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the codec has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    from m3_b200 import synth
+    from m3_b200.codec import BatchCodec, DecodeResult, PackedResult
+
     S, P = args.series, args.points
     int_opt = bool(args.int_optimized)
     codec = BatchCodec(local_rank, int_optimized=int_opt)
     ts, vals, start = synth.gaussian_walk(S, P, dev, seed=1000 + rank)
-    stride = codec.encode_bound(P)
-    enc = EncodeResult(out=torch.empty((S, stride), dtype=torch.uint8, device=dev),
-                       out_len=torch.empty(S, dtype=torch.int64, device=dev),
-                       status=torch.empty(S, dtype=torch.int32, device=dev))
-    codec.encode(ts, vals, start, unit=1, out=enc)
-    total = int(enc.out_len.sum().item())
-    cap_bytes = total + 64 * S + 64
-    packed = torch.empty(cap_bytes, dtype=torch.uint8, device=dev)
-    offsets = torch.empty(S + 1, dtype=torch.int64, device=dev)
+    cap_bytes = S * (P * 8 + 256)  # Gaussian walk: ~7.3 B/dp; a short series simply reports M3TSZ_ERR_CAPACITY
+    pk = PackedResult(packed=torch.empty(cap_bytes, dtype=torch.uint8, device=dev),
+                      offsets=torch.empty(S, dtype=torch.int64, device=dev),
+                      out_len=torch.empty(S, dtype=torch.int64, device=dev),
+                      status=torch.empty(S, dtype=torch.int32, device=dev),
+                      total=torch.zeros(1, dtype=torch.int64, device=dev))
     dec = DecodeResult(ts=torch.empty((S, P), dtype=torch.int64, device=dev),
                        values=torch.empty((S, P), dtype=torch.float64, device=dev),
                        n_points=torch.empty(S, dtype=torch.int32, device=dev),
                        status=torch.empty(S, dtype=torch.int32, device=dev),
                        unit=torch.empty(S, dtype=torch.uint8, device=dev), annotations=None)
-    import ctypes as C
-    from m3_b200 import capi
-
-    def compact():
-        rc = capi.lib().m3tsz_compact_streams(
-            codec.ctx.handle, C.c_void_p(enc.out.data_ptr()), stride, C.c_void_p(enc.out_len.data_ptr()),
-            S, 64, C.c_void_p(packed.data_ptr()), cap_bytes, C.c_void_p(offsets.data_ptr()),
-            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-        codec.ctx.check(rc, "compact")
-
     dec_events = []
 
+    def encode():
+        codec.encode_packed(ts, vals, start, unit=1, align=64, out=pk)
+
+    def decode():
+        codec.decode(pk.packed, pk.offsets, P, out=dec, lengths=pk.out_len)
+
     def step(record=False):
-        codec.encode(ts, vals, start, unit=1, out=enc)
-        compact()
+        encode()
         if record:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            codec.decode(packed, offsets, P, out=dec)
+            decode()
             e1.record()
             dec_events.append((e0, e1))
         else:
-            codec.decode(packed, offsets, P, out=dec)
+            decode()
 
     def barrier():
         torch.cuda.synchronize()
@@ -314,13 +624,13 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    # sanity: the timed path round-trips (float mode exactly; int mode up to the
-    # reference's own near-integer rounding)
-    assert int((enc.status != 0).sum()) == 0 and int((dec.status != 0).sum()) == 0
+    # sanity: the timed path round-trips (float mode exactly; int mode up to the reference's own
+    # near-integer rounding -- the parity tests compare those series with the oracle bit for bit)
+    assert int((pk.status != 0).sum()) == 0 and int((dec.status != 0).sum()) == 0
     assert torch.equal(dec.ts, ts)
     mism = int((dec.values.view(torch.int64) != vals.view(torch.int64)).sum())
     assert mism <= S * P * 1e-6, mism
-    compressed_bytes = int(enc.out_len.sum().item())
+    compressed_bytes = int(pk.out_len.sum().item())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -358,24 +668,54 @@ def run_ours(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / n
 
-    enc_ms = time_fn(lambda: codec.encode(ts, vals, start, unit=1, out=enc))
+    enc_ms = time_fn(encode)
     extras = not args.no_extras
-    ds_ms, n_win, merge_ms, Sm, fixtures, cks = None, 0, None, 0, None, None
+    side = {}
     if extras:
-        fixtures = fixture_set_throughput(codec, dev, time_fn)
+        s0 = int(start[0].item())
+        n_win = (P * 60 + 299) // 300
+        side["fixture_set"] = fixture_set_throughput(codec, dev, time_fn)
         # segment checksums (row N2): Adler-32 of every stream of the packed batch
-        ck, ck_st = codec.segment_checksums(packed, offsets, lengths=enc.out_len)
+        off1 = torch.cat([pk.offsets, pk.offsets[-1:]])
+        ck, ck_st = codec.segment_checksums(pk.packed, off1, lengths=pk.out_len)
         assert int((ck_st != 0).sum()) == 0
-        ck_ms = time_fn(lambda: codec.segment_checksums(packed, offsets, lengths=enc.out_len))
-        cks = {"streams": S, "bytes": compressed_bytes, "ms": ck_ms,
-               "algorithmic_gbs": compressed_bytes / (ck_ms * 1e-3) / 1e9}
-        del ck, ck_st
-        ds = codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC, (P * 60 + 299) // 300)
-        ds_ms = time_fn(lambda: codec.decode_downsample(packed, offsets, int(start[0].item()), 300 * SEC,
-                                                        (P * 60 + 299) // 300, out=ds))
-        n_win = ds.sum.shape[0]
-        del ds
-
+        ck_ms = time_fn(lambda: codec.segment_checksums(pk.packed, off1, lengths=pk.out_len))
+        side["segment_checksum"] = {"streams": S, "bytes": compressed_bytes, "ms": ck_ms,
+                                    "algorithmic_gbs": compressed_bytes / (ck_ms * 1e-3) / 1e9}
+        del ck, ck_st, off1
+        # fused decode + 5-min Gauge downsample (config 4) on the full batch needs CSR offsets:
+        # re-pack the batch once in series order (not timed)
+        full_slots = None
+        if S <= 1_000_000:
+            torch.cuda.empty_cache()
+            full_slots = codec.encode(ts, vals, start, unit=1)
+            fpacked, foff = codec.compact(full_slots, align=64)
+            del full_slots
+            ds = codec.decode_downsample(fpacked, foff, s0, 300 * SEC, n_win)
+            assert int((ds.status != 0).sum()) == 0 and bool((ds.count == 5).all())
+            ds_ms = time_fn(lambda: codec.decode_downsample(fpacked, foff, s0, 300 * SEC, n_win, out=ds))
+            side["decode_downsample"] = {
+                "windows": n_win, "ms": ds_ms, "series": S,
+                "algorithmic_gbs": (compressed_bytes + n_win * S * 32) / (ds_ms * 1e-3) / 1e9,
+                "frac_of_hbm": (compressed_bytes + n_win * S * 32) / (ds_ms * 1e-3) / 1e9 / measured_peak_gbs()[0],
+                "read_gbs": compressed_bytes / (ds_ms * 1e-3) / 1e9, "dps": S * P / (ds_ms * 1e-3)}
+            del ds
+            dsl = codec.decode_downsample(fpacked, foff, s0, 300 * SEC, n_win, want_last=True)
+            dsl_ms = time_fn(lambda: codec.decode_downsample(fpacked, foff, s0, 300 * SEC, n_win, out=dsl,
+                                                             want_last=True))
+            side["decode_downsample_last"] = {"ms": dsl_ms, "algorithmic_gbs":
+                                              (compressed_bytes + n_win * S * 48) / (dsl_ms * 1e-3) / 1e9}
+            del dsl
+            # tile aggregation (row N3): decode -> Gauge per 5 min -> re-encode, packed
+            tiles, n_tiles = codec.aggregate_tiles(fpacked, foff, s0, 300 * SEC, n_win)
+            assert int((tiles.status != 0).sum()) == 0 and bool((n_tiles == n_win).all())
+            tile_ms = time_fn(lambda: codec.aggregate_tiles(fpacked, foff, s0, 300 * SEC, n_win, out=tiles), n=3)
+            tile_bytes = int(tiles.total.item())
+            side["aggregate_tiles"] = {"ms": tile_ms, "source_dps": S * P / (tile_ms * 1e-3), "step_s": 300,
+                                       "agg": "last", "out_bytes": tile_bytes,
+                                       "algorithmic_gbs": (compressed_bytes + tile_bytes) / (tile_ms * 1e-3) / 1e9}
+            del tiles, n_tiles, fpacked, foff
+            torch.cuda.empty_cache()
         # series merge (row N1): RF=3 fetch shape -- every 3 consecutive decoded streams are the
         # replicas of one series (same timestamps => 3 inputs collapse to 1 output per timestamp)
         Sm = (min(S, 300_000) // 3) * 3
@@ -388,79 +728,40 @@ def run_ours(args):
         assert int((m_out[3] != 0).sum()) == 0 and bool((m_out[2] == P).all())
         del m_out
         merge_ms = time_fn(mg, n=3)
+        side["series_merge"] = {"replicas": 3, "series": Sm // 3, "ms": merge_ms,
+                                "input_dps": Sm * P / (merge_ms * 1e-3),
+                                "algorithmic_gbs": (Sm * P * 16 + (Sm // 3) * P * 16) / (merge_ms * 1e-3) / 1e9}
+        # Prometheus epilogue (row N4) over the decoded batch: ns -> ms, plain and counter-normalised
+        Sp = min(S, 300_000)
+        pr = lambda: codec.prom_convert(dec.ts[:Sp], dec.values[:Sp], dec.n_points[:Sp])
+        pr()
+        prom_ms = time_fn(pr, n=3)
+        hr = torch.ones(Sp, dtype=torch.uint8, device=dev)
+        prr = lambda: codec.prom_convert(dec.ts[:Sp], dec.values[:Sp], dec.n_points[:Sp], 300 * SEC, hr)
+        prr()
+        prom_r_ms = time_fn(prr, n=3)
+        side["prom_convert"] = {"series": Sp, "ms": prom_ms, "dps": Sp * P / (prom_ms * 1e-3),
+                                "algorithmic_gbs": Sp * P * 32 / (prom_ms * 1e-3) / 1e9,
+                                "counter_normalised_ms": prom_r_ms}
+        del hr
+        torch.cuda.empty_cache()
 
     # ---- fetch-side all-gather (only when a query spans shards) ----
     allgather = None
     if world > 1 and extras:
-        from m3_b200.sharded import all_gather_blocks
-        sub = min(S, max(1, (8 << 30) // (world * P * 16)))  # bound the gathered block to ~8 GiB
-        blk_t, blk_v = dec.ts[:sub].contiguous(), dec.values[:sub].contiguous()
-        all_gather_blocks(blk_t, sub * world)
-        barrier()
-        a = torch.cuda.Event(enable_timing=True)
-        b = torch.cuda.Event(enable_timing=True)
-        a.record()
-        g_t = all_gather_blocks(blk_t, sub * world)
-        g_v = all_gather_blocks(blk_v, sub * world)
-        b.record()
-        barrier()
-        ag = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        dist.all_reduce(ag, op=dist.ReduceOp.MAX)
-        recv = (world - 1) * sub * P * 16
-        allgather = {"series_per_rank": sub, "ms": float(ag[0]), "bytes_received_per_gpu": recv,
-                     "gbs_per_gpu": recv / (float(ag[0]) * 1e-3) / 1e9,
-                     "nvlink_peer_peak_gbs": 770.0, "frac": recv / (float(ag[0]) * 1e-3) / 1e9 / 770.0}
-        del g_t, g_v
+        from m3_b200.sharded import fetch_allgather_decoded
+        allgather = fetch_allgather_decoded(codec, pk, P, dist, dev, barrier)
 
-    # ---- e2e: the same step through the *_host C ABI with pinned host buffers ----
-    e2e = None
+    # ---- e2e: the same batch through the *_host C ABI with pinned host buffers ----
+    e2e = fetch = None
     if not args.no_e2e:
-        # the host API is exercised on the first Se series of the batch (pinning the
-        # whole 1M-series batch = ~80 GB of host memory would dominate the run time);
-        # its throughput is PCIe-bound and does not depend on the batch size.
-        Se = min(S, args.e2e_series)
-        e_cap = int(enc.out_len[:Se].sum().item()) + 64 * Se + 64
-        h_ts = ts[:Se].cpu().pin_memory()
-        h_vals = vals[:Se].cpu().pin_memory()
-        h_start = start[:Se].cpu().pin_memory()
-        h_packed = torch.empty(e_cap, dtype=torch.uint8).pin_memory()
-        h_off = torch.empty(Se + 1, dtype=torch.int64).pin_memory()
-        h_len = torch.empty(Se, dtype=torch.int64).pin_memory()
-        h_st = torch.empty(Se, dtype=torch.int32).pin_memory()
-        h_dts = torch.empty((Se, P), dtype=torch.int64).pin_memory()
-        h_dvals = torch.empty((Se, P), dtype=torch.float64).pin_memory()
-        h_n = torch.empty(Se, dtype=torch.int32).pin_memory()
-
-        def host_step():
-            codec.encode_host(h_ts, h_vals, h_start, 1, h_packed, h_off, h_len, h_st, align=64)
-            nbytes = int(h_off[-1])
-            codec.decode_host(h_packed[:nbytes], h_off, P, h_dts, h_dvals, h_n, h_st)
-            return nbytes
-
-        for _ in range(max(1, min(args.warmup, 2))):
-            nb = host_step()
-        assert torch.equal(h_dts, h_ts)
-        barrier()
-        l0 = codec.launch_count()
-        t0 = time.perf_counter()
-        e_steps = max(1, min(args.steps, 5))
-        for _ in range(e_steps):
-            nb = host_step()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        e_launch = codec.launch_count() - l0
-        tt = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e_s = float(tt[0]) / e_steps
-        h2d = Se * P * 16 + Se * 8 + nb + (Se + 1) * 8
-        d2h = nb + (Se + 1) * 8 + Se * 12 + Se * P * 16 + Se * 8
-        e2e = {"value": Se * P * world / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e_s * 1e3, "steps": e_steps,
-               "launches_per_step": e_launch / e_steps, "series_per_step": Se,
-               "api": "m3tsz_encode_batch_host + m3tsz_decode_batch_host (pinned host buffers, "
-                      "chunked two-stream H2D/kernel/D2H pipeline)"}
-        del h_ts, h_vals, h_dts, h_dvals, h_packed
+        if extras:
+            fetch = run_fetch_e2e(args, codec, ts, vals, start, P, rank, world, dev, barrier, dist)
+        del dec
+        torch.cuda.empty_cache()
+        e2e = run_e2e(args, codec, ts, vals, start, P, int_opt, rank, world, dev, barrier, dist)
+        if numa:
+            e2e["numa_binding"] = numa
 
     if rank != 0:
         if world > 1:
@@ -470,13 +771,14 @@ def run_ours(args):
 
     # ---- roofline of the decode kernel ----
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = compressed_bytes + (S + 1) * 8 + S * P * 16 + S * 9  # in: streams + offsets; out: ts, val, n/status/unit
+    alg_bytes = compressed_bytes + S * 16 + S * P * 16 + S * 9  # in: streams + (offset, size); out: ts, val, n/status/unit
     achieved = alg_bytes / (dec_ms_max * 1e-3) / 1e9
     workload = "%dx%d" % (S, P)
+    traffic = recorded_traffic(workload)
     roofline = {"bound": "hbm", "kernel": "m3tsz::decode_kernel<%s,0>" % ("true" if int_opt else "false"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(workload), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms_max,
+                "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture, committed)",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms_max,
                 "bytes_per_dp": alg_bytes / (S * P)}
 
     cpu = None
@@ -484,36 +786,19 @@ def run_ours(args):
         cv, info = cpu_oracle_throughput(S, P, int_opt, budget_s=args.cpu_seconds)
         cpu = {"value": cv, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                "sample": info["sample"], "encode_dps": info["encode_dps"], "decode_dps": info["decode_dps"],
-               "note": info["note"]}
+               "note": info["note"], "core_info": info["core_info"]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64/f64 (integer bit manipulation; float64 values)",
-        "data": "synthetic",
-        "config": {"workload": "batch of %d series x %d points per GPU (the north-star target shape "
-                               "1M x 1440 = configs[2-4] size; configs[4] = 8M over 8 GPUs), Gaussian "
-                               "random walk (x0=100, N(0,1) steps), 60 s cadence, unit=Second; step = "
-                               "encode + compact + decode" % (S, P),
-                   "series_per_gpu": S, "points": P, "int_optimized": int_opt,
-                   "compressed_bytes_per_dp": compressed_bytes / (S * P),
-                   "l2": "inputs %.2f GB and outputs %.2f GB per step >> 126 MB L2, no flush needed"
-                         % (S * P * 16 / 1e9, (compressed_bytes + S * P * 16) / 1e9),
-                   "parallelism": "series sharded per GPU, no data-path collective"},
+        "data": "synthetic", "config": make_config(S, P, int_opt, compressed_bytes / (S * P)),
         "encode_dps": S * P / (enc_ms * 1e-3), "decode_dps": S * P / (dec_ms_max * 1e-3),
-        "decode_downsample_dps": (S * P / (ds_ms * 1e-3)) if extras else None,
-        "decode_downsample": {"windows": n_win, "ms": ds_ms,
-                              "algorithmic_gbs": (compressed_bytes + n_win * S * 32) / (ds_ms * 1e-3) / 1e9}
-        if extras else None,
-        "series_merge": {"replicas": 3, "series": Sm // 3, "ms": merge_ms,
-                         "input_dps": Sm * P / (merge_ms * 1e-3),
-                         "algorithmic_gbs": (Sm * P * 16 + (Sm // 3) * P * 16) / (merge_ms * 1e-3) / 1e9}
-        if extras else None,
-        "fixture_set": fixtures, "segment_checksum": cks,
         "encode_ms": enc_ms, "decode_ms": dec_ms_max,
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_fetch": fetch, "gpu_launches": launches,
         "clocks": clocks, "fetch_allgather": allgather,
     }
+    line.update(side)
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -389,6 +389,23 @@ int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *
                              uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Fetch with HOST buffers: decode + series merge in one call, so that only the
+ * COMPRESSED replica streams go up over PCIe and only the MERGED series come back
+ * (the decoded replicas, 16 B per datapoint and replica, never leave the device).
+ * Same structure arguments as m3tsz_merge_series_batch, over the streams
+ * h_offsets[q] .. h_offsets[q+1] of sequence q (sequences of one series must be
+ * consecutive: the call works through chunks of whole series on two CUDA streams,
+ * H2D / decode / merge / D2H overlapped).  max_points = decode capacity per
+ * sequence; outputs [n_series][out_cap] + h_n_out + h_status as m3tsz_merge_series_batch.
+ * ---------------------------------------------------------------------- */
+int m3tsz_fetch_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *h_streams,
+                           uint64_t streams_bytes, const uint64_t *h_offsets, uint64_t n_seq,
+                           const uint64_t *h_slice_off, const uint64_t *h_replica_off,
+                           const uint64_t *h_series_off, uint64_t n_series, uint64_t max_points,
+                           int64_t start_ns, int64_t end_ns, int32_t strategy, int64_t *h_ts_out,
+                           double *h_val_out, uint64_t out_cap, uint32_t *h_n_out, int32_t *h_status);
+
+/* ------------------------------------------------------------------------
  * Prometheus conversion epilogue: iteratorToPromResult,
  * src/query/storage/prom_converter.go:42-120, over decoded / merged series that are
  * already in HBM -- the last per-datapoint host loop of a fetch:
@@ -515,6 +532,32 @@ void m3tsz_encoder_pool_destroy(m3tsz_encoder_pool *pool);
 int m3tsz_iter_pool_create(m3tsz_ctx *ctx, const m3tsz_options *opts, uint64_t size, m3tsz_iter_pool **out);
 int m3tsz_iter_pool_get(m3tsz_iter_pool *pool, m3tsz_iter **out);
 void m3tsz_iter_pool_destroy(m3tsz_iter_pool *pool);
+
+/* ------------------------------------------------------------------------
+ * Fetch-side exchange (BASELINE config 5): series shard trivially, so
+ * encode / decode need no collective; only a query that spans shards needs every
+ * shard's DECODED blocks on every GPU.  m3tsz_allgather_decoded decodes the first
+ * gather_series streams of the local shard chunk by chunk and all-gathers chunk k-1
+ * over NCCL / NVLink while chunk k is decoded (ring of two staging buffers, one fused
+ * NCCL kernel per chunk).  Every rank passes the same gather_series / max_points /
+ * chunk_series.  Outputs (on every rank):
+ *   d_ts_all / d_val_all : [n_ranks][gather_series][max_points], rank r's series s at
+ *                          ((r * gather_series + s) * max_points)
+ *   d_n_points_all / d_status_all : [n_ranks][gather_series]
+ * nccl_comm is an ncclComm_t of n_ranks ranks (the caller's, or one made with
+ * m3tsz_nccl_comm_create from an id broadcast out of band).  NCCL is resolved at run
+ * time (dlopen of the libnccl.so.2 the process has loaded); without it the calls
+ * return M3TSZ_ERR_NO_DEVICE.  d_lengths may be NULL (CSR offsets).  Asynchronous:
+ * `stream` continues after the pipeline has finished.
+ * ---------------------------------------------------------------------- */
+int m3tsz_nccl_unique_id(uint8_t *out128);
+int m3tsz_nccl_comm_create(m3tsz_ctx *ctx, const uint8_t *unique_id128, int n_ranks, int rank, void **comm);
+int m3tsz_nccl_comm_destroy(void *comm);
+int m3tsz_allgather_decoded(m3tsz_ctx *ctx, const m3tsz_options *opts, void *nccl_comm, int n_ranks,
+                            const uint8_t *d_streams, uint64_t streams_bytes, const uint64_t *d_offsets,
+                            const uint64_t *d_lengths, uint64_t n_series, uint64_t gather_series,
+                            uint64_t max_points, uint64_t chunk_series, int64_t *d_ts_all, double *d_val_all,
+                            uint32_t *d_n_points_all, int32_t *d_status_all, void *stream);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,8 @@ EXPORTED_SYMBOLS = [
     "m3tsz_decode_downsample_batch_host", "m3tsz_merge_series_batch", "m3tsz_checksum_batch",
     "m3tsz_decode_batch_ex", "m3tsz_decode_downsample_last_batch", "m3tsz_encode_bound_units",
     "m3tsz_encode_batch_packed", "m3tsz_prom_convert_batch", "m3tsz_aggregate_tiles_batch",
-    "m3tsz_encode_batch_ex",
+    "m3tsz_encode_batch_ex", "m3tsz_fetch_batch_host", "m3tsz_nccl_unique_id", "m3tsz_nccl_comm_create",
+    "m3tsz_nccl_comm_destroy", "m3tsz_allgather_decoded",
     "m3tsz_encoder_create", "m3tsz_encoder_destroy", "m3tsz_encoder_reset", "m3tsz_encoder_encode",
     "m3tsz_encoder_num_encoded", "m3tsz_encoder_failed_dod", "m3tsz_encoder_last_encoded", "m3tsz_encoder_last_annotation_checksum",
     "m3tsz_encoder_empty", "m3tsz_encoder_len", "m3tsz_encoder_stream", "m3tsz_encoder_close",
@@ -173,6 +174,18 @@ def lib():
     for f in ("m3tsz_encoder_pool_destroy", "m3tsz_iter_pool_destroy"):
         getattr(L, f).restype = None
         getattr(L, f).argtypes = [vp]
+    L.m3tsz_nccl_unique_id.restype = C.c_int
+    L.m3tsz_nccl_unique_id.argtypes = [vp]
+    L.m3tsz_nccl_comm_create.restype = C.c_int
+    L.m3tsz_nccl_comm_create.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.m3tsz_nccl_comm_destroy.restype = C.c_int
+    L.m3tsz_nccl_comm_destroy.argtypes = [vp]
+    L.m3tsz_allgather_decoded.restype = C.c_int
+    L.m3tsz_allgather_decoded.argtypes = [vp, po, vp, C.c_int, vp, u64, vp, vp, u64, u64, u64, u64, vp, vp, vp,
+                                          vp, vp]
+    L.m3tsz_fetch_batch_host.restype = C.c_int
+    L.m3tsz_fetch_batch_host.argtypes = [vp, po, vp, u64, vp, u64, vp, vp, vp, u64, u64, i64, i64, i32, vp, vp,
+                                         u64, vp, vp]
     L.m3tsz_prom_convert_batch.restype = C.c_int
     L.m3tsz_prom_convert_batch.argtypes = [vp, vp, vp, u64, vp, u64, i64, vp, C.c_double, i64, vp, vp, u64,
                                            vp, vp, vp]

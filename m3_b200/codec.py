@@ -354,5 +354,17 @@ class BatchCodec:
             _ptr(h_min), _ptr(h_max), _ptr(h_n_points), _ptr(h_status))
         self.ctx.check(rc, "m3tsz_decode_downsample_batch_host")
 
+    def fetch_host(self, h_streams, h_offsets, h_slice_off, h_replica_off, h_series_off, max_points, out_cap,
+                   h_ts_out, h_val_out, h_n_out, h_status, start_ns=0, end_ns=0, strategy=0):
+        """Host tensors in and out: compressed replica streams up, merged series down."""
+        n_seq = h_offsets.numel() - 1
+        S = h_series_off.numel() - 1
+        rc = capi.lib().m3tsz_fetch_batch_host(
+            self.ctx.handle, C.byref(self.opts), _ptr(h_streams), h_streams.numel(), _ptr(h_offsets), n_seq,
+            _ptr(h_slice_off), _ptr(h_replica_off), _ptr(h_series_off), S, int(max_points), int(start_ns),
+            int(end_ns), int(strategy), _ptr(h_ts_out), _ptr(h_val_out), int(out_cap), _ptr(h_n_out),
+            _ptr(h_status))
+        self.ctx.check(rc, "m3tsz_fetch_batch_host")
+
     def launch_count(self):
         return self.ctx.launch_count()

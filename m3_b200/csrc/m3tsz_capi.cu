@@ -340,11 +340,12 @@ int m3tsz_encode_batch_packed(m3tsz_ctx *ctx, const m3tsz_options *opts, const i
   p.batch_counter = reinterpret_cast<unsigned long long *>(ctr);
   p.align = align;
   {
-    // phase spread = one batch period (about half a microsecond per datapoint and warp on a B200,
-    // DESIGN.md §4.7), only when every warp slot gets several batches
+    // optional start-up phase spread of the persistent warps (tuning knob; measured on a B200 at
+    // 1M x 1440: 0 / 250 / 500 / 800 ns per datapoint -> 13.0 / 13.2 / 13.4 / 13.6 ms, so it is off:
+    // the copy phase costs warp residency, not DRAM contention -- profiles/r02_encode_history.md)
     static const long ns_per_dp = [] {
       const char *e = getenv("M3TSZ_ENC_STAGGER_NS_PER_DP");
-      return e ? atol(e) : 500L;
+      return e ? atol(e) : 0L;
     }();
     const uint64_t n_batches = (n_series + 31) / 32;
     if (ns_per_dp > 0 && n_batches >= 3 * (slots / 32)) p.stagger_ns = points_stride * (uint64_t)ns_per_dp;
@@ -548,7 +549,7 @@ int m3tsz_checksum_batch(m3tsz_ctx *ctx, const uint8_t *d_streams, uint64_t stre
 // --------------------------------------------------------------------------
 // host-buffer variants
 // --------------------------------------------------------------------------
-int m3tsz_decode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *h_streams,
+static int m3tsz_decode_batch_host_impl(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *h_streams,
                             uint64_t streams_bytes, const uint64_t *h_offsets, uint64_t n_series,
                             int64_t *h_ts, double *h_val, uint64_t max_points,
                             uint32_t *h_n_points, int32_t *h_status, uint8_t *h_unit,
@@ -606,7 +607,21 @@ int m3tsz_decode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const uin
   return M3TSZ_OK;
 }
 
-int m3tsz_decode_downsample_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts,
+int m3tsz_decode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *h_streams,
+                            uint64_t streams_bytes, const uint64_t *h_offsets, uint64_t n_series,
+                            int64_t *h_ts, double *h_val, uint64_t max_points,
+                            uint32_t *h_n_points, int32_t *h_status, uint8_t *h_unit,
+                            m3tsz_annotation_ref *h_ann) {
+  const int rc = m3tsz_decode_batch_host_impl(ctx, opts, h_streams, streams_bytes, h_offsets, n_series, h_ts, h_val, max_points, h_n_points, h_status, h_unit, h_ann);
+  if (ctx && ctx->stream) {  // never return with copies from / into the caller's buffers in flight
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream2);
+  }
+  return rc;
+}
+
+static int m3tsz_decode_downsample_batch_host_impl(m3tsz_ctx *ctx, const m3tsz_options *opts,
                                        const uint8_t *h_streams, uint64_t streams_bytes,
                                        const uint64_t *h_offsets, uint64_t n_series,
                                        int64_t range_start_ns, int64_t window_ns,
@@ -647,7 +662,23 @@ int m3tsz_decode_downsample_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts
   return M3TSZ_OK;
 }
 
-int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *h_ts,
+int m3tsz_decode_downsample_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts,
+                                       const uint8_t *h_streams, uint64_t streams_bytes,
+                                       const uint64_t *h_offsets, uint64_t n_series,
+                                       int64_t range_start_ns, int64_t window_ns,
+                                       uint32_t n_windows, double *h_sum, int64_t *h_count,
+                                       double *h_min, double *h_max, uint32_t *h_n_points,
+                                       int32_t *h_status) {
+  const int rc = m3tsz_decode_downsample_batch_host_impl(ctx, opts, h_streams, streams_bytes, h_offsets, n_series, range_start_ns, window_ns, n_windows, h_sum, h_count, h_min, h_max, h_n_points, h_status);
+  if (ctx && ctx->stream) {  // never return with copies from / into the caller's buffers in flight
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream2);
+  }
+  return rc;
+}
+
+static int m3tsz_encode_batch_host_impl(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *h_ts,
                             const double *h_val, uint64_t n_series, uint64_t points_stride,
                             const uint32_t *h_n_points, const int64_t *h_start, int32_t unit,
                             const uint8_t *h_units, const uint64_t *h_ann_series_off,
@@ -665,7 +696,7 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
   if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   cudaStream_t sts[2] = {ctx->stream, ctx->stream2};
   const uint64_t ann_total = h_ann_series_off ? ann_bytes_len + 16 * h_ann_series_off[n_series] : 0;
-  const uint64_t out_stride = m3tsz_encode_bound(points_stride) + ((ann_total + 15) & ~15ull);
+  const uint64_t out_stride = m3tsz_encode_bound_units(points_stride, h_units != nullptr) + ((ann_total + 15) & ~15ull);
   const uint64_t ch = pick_chunk(n_series, points_stride * 16 + points_stride * 8);
   const size_t row_bytes = (size_t)points_stride * 8;
   int rc;
@@ -699,6 +730,8 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
     bool busy;
   } ln[2];
   const size_t tmp_bytes = compact_scan_tmp_bytes(ch);
+  // every start is rounded up to `align`: budget the aligned worst case per stream
+  const uint64_t packed_stride = (out_stride + align - 1) & ~(uint64_t)(align - 1);
   for (int i = 0; i < 2; i++) {
     const int b = 16 + i * 10;
     ln[i].units = nullptr;
@@ -709,12 +742,13 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
     if ((rc = ensure(ctx, b + 3, ch * out_stride, &ln[i].out))) return rc;
     if ((rc = ensure(ctx, b + 4, ch * 8, &ln[i].len))) return rc;
     if ((rc = ensure(ctx, b + 5, ch * 4, &ln[i].st))) return rc;
-    if ((rc = ensure(ctx, b + 6, ch * out_stride + 16, &ln[i].packed))) return rc;
+    if ((rc = ensure(ctx, b + 6, ch * packed_stride + 64, &ln[i].packed))) return rc;
     if ((rc = ensure(ctx, b + 7, (ch + 1) * 8, &ln[i].off))) return rc;
     if ((rc = ensure(ctx, b + 8, tmp_bytes, &ln[i].tmp))) return rc;
-    if ((rc = ensure_stage(ctx, i, (ch + 1) * 8))) return rc;
+    if ((rc = ensure_stage(ctx, i, (ch + 1) * 8 + 8))) return rc;
   }
   CK(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(int32_t), sts[0]));
+  CK(cudaStreamSynchronize(sts[0]));  // the flags are zero before either lane's kernels can set them
 
   auto issue = [&](int i, uint64_t c0) -> int {
     Lane &L = ln[i];
@@ -734,10 +768,11 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
                                (uint8_t *)L.out, out_stride, (uint64_t *)L.len, (int32_t *)L.st, st);
     if (r) return r;
     CK(launch_compact((const uint8_t *)L.out, out_stride, (const uint64_t *)L.len, n, align,
-                      (uint8_t *)L.packed, ch * out_stride + 16, (uint64_t *)L.off, L.tmp, tmp_bytes,
+                      (uint8_t *)L.packed, ch * packed_stride + 64, (uint64_t *)L.off, L.tmp, tmp_bytes,
                       ctx->d_flag + i, st));
     ctx->launches += 3;
     CK(cudaMemcpyAsync(ctx->h_stage[i], L.off, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((uint8_t *)ctx->h_stage[i] + (ch + 1) * 8, ctx->d_flag + i, 4, cudaMemcpyDeviceToHost, st));
     if (h_out_len) CK(cudaMemcpyAsync(h_out_len + c0, L.len, n * 8, cudaMemcpyDeviceToHost, st));
     if (h_status) CK(cudaMemcpyAsync(h_status + c0, L.st, n * 4, cudaMemcpyDeviceToHost, st));
     return M3TSZ_OK;
@@ -751,7 +786,9 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
     const uint64_t n = L.c1 - L.c0;
     const uint64_t *co = (const uint64_t *)ctx->h_stage[i];
     const uint64_t total = co[n];
-    if (host_base + total > packed_capacity) return M3TSZ_ERR_CAPACITY;
+    int32_t overflow = 0;
+    memcpy(&overflow, (const uint8_t *)ctx->h_stage[i] + (ch + 1) * 8, 4);
+    if (overflow || host_base + total > packed_capacity) return M3TSZ_ERR_CAPACITY;
     if (total)
       CK(cudaMemcpyAsync(h_packed + host_base, L.packed, total, cudaMemcpyDeviceToHost, sts[i]));
     for (uint64_t j = 0; j <= n; j++) h_offsets[L.c0 + j] = host_base + co[j];
@@ -773,6 +810,143 @@ int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int
   CK(cudaStreamSynchronize(sts[0]));
   CK(cudaStreamSynchronize(sts[1]));
   // CSR convention: offsets[n] is the end of the last stream; un-pad the final alignment
+  return M3TSZ_OK;
+}
+
+int m3tsz_encode_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *h_ts,
+                            const double *h_val, uint64_t n_series, uint64_t points_stride,
+                            const uint32_t *h_n_points, const int64_t *h_start, int32_t unit,
+                            const uint8_t *h_units, const uint64_t *h_ann_series_off,
+                            const m3tsz_annotation_entry *h_ann_entries,
+                            const uint8_t *h_ann_bytes, uint64_t ann_bytes_len, uint32_t align,
+                            uint8_t *h_packed, uint64_t packed_capacity, uint64_t *h_offsets,
+                            uint64_t *h_out_len, int32_t *h_status) {
+  const int rc = m3tsz_encode_batch_host_impl(ctx, opts, h_ts, h_val, n_series, points_stride, h_n_points, h_start, unit, h_units, h_ann_series_off, h_ann_entries, h_ann_bytes, ann_bytes_len, align, h_packed, packed_capacity, h_offsets, h_out_len, h_status);
+  if (ctx && ctx->stream) {  // never return with copies from / into the caller's buffers in flight
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream2);
+  }
+  return rc;
+}
+
+
+// --------------------------------------------------------------------------
+// Fetch path with host buffers: only compressed bytes go up, only the merged result
+// comes back (the decoded replicas never cross PCIe).
+int m3tsz_fetch_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8_t *h_streams,
+                           uint64_t streams_bytes, const uint64_t *h_offsets, uint64_t n_seq,
+                           const uint64_t *h_slice_off, const uint64_t *h_replica_off,
+                           const uint64_t *h_series_off, uint64_t n_series, uint64_t max_points,
+                           int64_t start_ns, int64_t end_ns, int32_t strategy, int64_t *h_ts_out,
+                           double *h_val_out, uint64_t out_cap, uint32_t *h_n_out, int32_t *h_status) {
+  if (!ctx || !valid_opts(opts)) return M3TSZ_ERR_INVALID_ARG;
+  if (n_series == 0) return M3TSZ_OK;
+  if (!h_streams || !h_offsets || !h_slice_off || !h_replica_off || !h_series_off || !h_ts_out || !h_val_out ||
+      !h_n_out || !h_status || max_points == 0 || out_cap == 0 || n_seq == 0 || strategy < 0 || strategy > 3)
+    return M3TSZ_ERR_INVALID_ARG;
+  const uint64_t n_rep = h_series_off[n_series], n_slice = h_replica_off[n_rep];
+  if (h_slice_off[n_slice] != n_seq || h_series_off[0] != 0 || h_replica_off[0] != 0 || h_slice_off[0] != 0)
+    return M3TSZ_ERR_INVALID_ARG;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
+  cudaStream_t sts[2] = {ctx->stream, ctx->stream2};
+  // series per chunk: ~8 chunks, whole sequences of whole series
+  uint64_t ch = (n_series + 7) / 8;
+  {
+    const uint64_t per_series = (streams_bytes + (n_seq * max_points * 16)) / n_series + out_cap * 16;
+    uint64_t min_ch = (32ull << 20) / (per_series ? per_series : 1);
+    if (min_ch < 1024) min_ch = 1024;
+    if (ch < min_ch) ch = min_ch;
+    if (ch > n_series) ch = n_series;
+  }
+  // the largest chunk in sequences / slices / replicas
+  uint64_t max_q = 0, max_k = 0, max_r = 0;
+  for (uint64_t s0 = 0; s0 < n_series; s0 += ch) {
+    const uint64_t s1 = s0 + ch < n_series ? s0 + ch : n_series;
+    const uint64_t r0 = h_series_off[s0], r1 = h_series_off[s1];
+    if (r1 < r0 || r1 > n_rep) return M3TSZ_ERR_INVALID_ARG;
+    const uint64_t k0 = h_replica_off[r0], k1 = h_replica_off[r1];
+    if (k1 < k0 || k1 > n_slice) return M3TSZ_ERR_INVALID_ARG;
+    const uint64_t q0 = h_slice_off[k0], q1 = h_slice_off[k1];
+    if (q1 < q0 || q1 > n_seq) return M3TSZ_ERR_INVALID_ARG;
+    if (q1 - q0 > max_q) max_q = q1 - q0;
+    if (k1 - k0 > max_k) max_k = k1 - k0;
+    if (r1 - r0 > max_r) max_r = r1 - r0;
+  }
+  void *d_streams, *d_off;
+  int rc;
+  if ((rc = ensure(ctx, 0, streams_bytes + 16, &d_streams))) return rc;
+  if ((rc = ensure(ctx, 1, (n_seq + 1) * 8, &d_off))) return rc;
+  struct Lane {
+    void *ts, *val, *n, *st, *meta, *ots, *oval, *on, *ost;
+  } ln[2];
+  const size_t meta_words = (max_k + 1) + (max_r + 1) + (ch + 1);
+  for (int i = 0; i < 2; i++) {
+    const int b = 16 + i * 10;
+    if ((rc = ensure(ctx, b + 0, max_q * max_points * 8, &ln[i].ts))) return rc;
+    if ((rc = ensure(ctx, b + 1, max_q * max_points * 8, &ln[i].val))) return rc;
+    if ((rc = ensure(ctx, b + 2, max_q * 4, &ln[i].n))) return rc;
+    if ((rc = ensure(ctx, b + 3, max_q * 4, &ln[i].st))) return rc;
+    if ((rc = ensure(ctx, b + 4, meta_words * 8, &ln[i].meta))) return rc;
+    if ((rc = ensure(ctx, b + 5, ch * out_cap * 8, &ln[i].ots))) return rc;
+    if ((rc = ensure(ctx, b + 6, ch * out_cap * 8, &ln[i].oval))) return rc;
+    if ((rc = ensure(ctx, b + 7, ch * 4, &ln[i].on))) return rc;
+    if ((rc = ensure(ctx, b + 8, ch * 4, &ln[i].ost))) return rc;
+    if ((rc = ensure_stage(ctx, i, meta_words * 8))) return rc;
+  }
+  auto fail = [&](int code) {  // never return with copies into the caller's buffers in flight
+    cudaStreamSynchronize(sts[0]);
+    cudaStreamSynchronize(sts[1]);
+    return code;
+  };
+  CK(cudaMemcpyAsync(d_off, h_offsets, (n_seq + 1) * 8, cudaMemcpyHostToDevice, sts[0]));
+  CK(cudaEventRecord(ctx->ev, sts[0]));
+  CK(cudaStreamWaitEvent(sts[1], ctx->ev, 0));
+  int k = 0;
+  for (uint64_t s0 = 0; s0 < n_series; s0 += ch, k++) {
+    const int i = k & 1;
+    cudaStream_t st = sts[i];
+    Lane &L = ln[i];
+    const uint64_t s1 = s0 + ch < n_series ? s0 + ch : n_series, ns = s1 - s0;
+    const uint64_t r0 = h_series_off[s0], r1 = h_series_off[s1];
+    const uint64_t k0 = h_replica_off[r0], k1 = h_replica_off[r1];
+    const uint64_t q0 = h_slice_off[k0], q1 = h_slice_off[k1], nq = q1 - q0;
+    const uint64_t b0 = h_offsets[q0], b1 = h_offsets[q1];
+    if (b1 < b0 || b1 > streams_bytes) return fail(M3TSZ_ERR_INVALID_ARG);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return fail(M3TSZ_ERR_CUDA);  // lane buffers + staging are free again
+    // iterator structure of the chunk, rebased to the chunk's first sequence / slice / replica
+    uint64_t *m = (uint64_t *)ctx->h_stage[i];
+    uint64_t *m_slice = m, *m_rep = m + (max_k + 1), *m_ser = m_rep + (max_r + 1);
+    for (uint64_t j = k0; j <= k1; j++) m_slice[j - k0] = h_slice_off[j] - q0;
+    for (uint64_t j = r0; j <= r1; j++) m_rep[j - r0] = h_replica_off[j] - k0;
+    for (uint64_t j = s0; j <= s1; j++) m_ser[j - s0] = h_series_off[j] - r0;
+    if (cudaMemcpyAsync(L.meta, m, meta_words * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      return fail(M3TSZ_ERR_CUDA);
+    if (b1 > b0 && cudaMemcpyAsync((uint8_t *)d_streams + b0, h_streams + b0, b1 - b0, cudaMemcpyHostToDevice, st) !=
+                       cudaSuccess)
+      return fail(M3TSZ_ERR_CUDA);
+    if (nq) {
+      rc = m3tsz_decode_batch(ctx, opts, (const uint8_t *)d_streams, streams_bytes, (const uint64_t *)d_off + q0, nq,
+                              (int64_t *)L.ts, (double *)L.val, max_points, (uint32_t *)L.n, (int32_t *)L.st,
+                              nullptr, nullptr, st);
+      if (rc) return fail(rc);
+    }
+    const uint64_t *dm = (const uint64_t *)L.meta;
+    rc = m3tsz_merge_series_batch(ctx, (const int64_t *)L.ts, (const double *)L.val, max_points,
+                                  (const uint32_t *)L.n, (const int32_t *)L.st, dm, dm + (max_k + 1),
+                                  dm + (max_k + 1) + (max_r + 1), ns, start_ns, end_ns, strategy, (int64_t *)L.ots,
+                                  (double *)L.oval, out_cap, (uint32_t *)L.on, (int32_t *)L.ost, st);
+    if (rc) return fail(rc);
+    if (cudaMemcpyAsync(h_ts_out + s0 * out_cap, L.ots, ns * out_cap * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(h_val_out + s0 * out_cap, L.oval, ns * out_cap * 8, cudaMemcpyDeviceToHost, st) !=
+            cudaSuccess ||
+        cudaMemcpyAsync(h_n_out + s0, L.on, ns * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(h_status + s0, L.ost, ns * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      return fail(M3TSZ_ERR_CUDA);
+  }
+  if (cudaStreamSynchronize(sts[0]) != cudaSuccess || cudaStreamSynchronize(sts[1]) != cudaSuccess)
+    return set_cuda_error(ctx, cudaGetLastError(), "m3tsz_fetch_batch_host");
   return M3TSZ_OK;
 }
 

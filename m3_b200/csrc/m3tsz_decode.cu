@@ -31,7 +31,7 @@ namespace m3tsz {
 #define M3_DEC_SAFE_MIN 12  // fewer landed words ahead than this: confirm the copy in flight
 #endif
 #ifndef M3_DEC_MIN_BLOCKS
-#define M3_DEC_MIN_BLOCKS 5
+#define M3_DEC_MIN_BLOCKS 4  // 4 x 4 warps with ~110 registers beat 5 blocks squeezed into 96 (profiles/r02_decode_history.md)
 #endif
 #ifndef M3_DEC_MIN_BLOCKS_DS
 #define M3_DEC_MIN_BLOCKS_DS 4  // fused-downsample kernel (5 blocks fit its shared memory but spill registers)
@@ -89,28 +89,31 @@ struct SlowSrc {
   uint64_t nbytes;
   const uint32_t *ring_lane;  // the lane's 16-byte cell of quad 0 (ring + lane * 4 words)
   uint32_t ring_safe;
-  // per-datapoint unit / annotation event table (optional; include/m3tsz_b200.h m3tsz_dp_event)
+};
+
+// per-datapoint unit / annotation event table (optional; include/m3tsz_b200.h m3tsz_dp_event)
+struct EventSink {
   m3tsz_dp_event *events;
-  uint64_t events_capacity;
-  unsigned long long *event_count;
+  uint64_t capacity;
+  unsigned long long *count;
   uint64_t series;
   uint32_t pos0;  // bit position of the stream's first bit (relative to wbase)
 };
 
-__device__ __forceinline__ void push_event(const SlowSrc &src, uint32_t dp_index, uint32_t kind, uint32_t unit,
+__device__ __forceinline__ void push_event(const EventSink &ev, uint32_t dp_index, uint32_t kind, uint32_t unit,
                                            uint64_t bit_offset, uint32_t length) {
-  if (!src.event_count) return;
-  const unsigned long long i = atomicAdd(src.event_count, 1ull);
-  if (i < src.events_capacity) {
+  if (!ev.count) return;
+  const unsigned long long i = atomicAdd(ev.count, 1ull);
+  if (i < ev.capacity) {
     m3tsz_dp_event e;
-    e.series = src.series;
+    e.series = ev.series;
     e.dp_index = dp_index;
     e.kind = (uint16_t)kind;
     e.unit = (uint16_t)unit;
     e.bit_offset = bit_offset;
     e.length = length;
     e.reserved = 0;
-    src.events[i] = e;
+    ev.events[i] = e;
   }
 }
 
@@ -151,7 +154,8 @@ __device__ __forceinline__ uint64_t gpeek64(const SlowSrc &src, uint64_t wbase, 
 // without error); false on end-of-stream (s.done) or error (s.err).
 template <bool INT_OPT>
 __device__ __noinline__ bool decode_dp_slow(DecState &s, const SlowSrc src, int default_unit,
-                                            int64_t &out_t, uint64_t &out_v) {
+                                            int64_t &out_t, uint64_t &out_v, const EventSink *evp) {
+  const EventSink &ev = *evp;
   // ---- ReadTimestamp, timestamp_iterator.go:80-113 ----
   const bool first = (s.prev_time == 0);
   int64_t nt = 0;
@@ -222,7 +226,7 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const SlowSrc src, int 
             s.ann_len = (uint32_t)alen;
           }
           s.ann_count++;
-          push_event(src, s.n, M3TSZ_EVENT_ANNOTATION, 0, (uint64_t)(s.pos - src.pos0), (uint32_t)alen);
+          push_event(ev, s.n, M3TSZ_EVENT_ANNOTATION, 0, (uint64_t)(s.pos - ev.pos0), (uint32_t)alen);
           s.pos += (uint32_t)alen * 8u;
           continue;
         }
@@ -234,7 +238,7 @@ __device__ __noinline__ bool decode_dp_slow(DecState &s, const SlowSrc src, int 
             unit_changed = true;
             s.scheme = scheme_kind_for_unit(tu);
           }
-          if (tu != s.unit && s.n > 0) push_event(src, s.n, M3TSZ_EVENT_TIME_UNIT, (uint32_t)tu, 0, 0);
+          if (tu != s.unit && s.n > 0) push_event(ev, s.n, M3TSZ_EVENT_TIME_UNIT, (uint32_t)tu, 0, 0);
           s.unit = tu;
           s.unit_ns = unit_nanos(tu);
           continue;
@@ -414,8 +418,18 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
+#ifndef M3_DEC_CPASYNC_CG
+#define M3_DEC_CPASYNC_CG 0  // 1: cp.async.cg (L2 only) for whole-chunk refills
+#endif
+#ifndef M3_DEC_L2_PREFETCH
+#define M3_DEC_L2_PREFETCH 0  // 1: pull the chunk after the one being copied into L2
+#endif
 __device__ __forceinline__ void cp_async16_full(uint32_t dst, const void *src) {
+#if M3_DEC_CPASYNC_CG
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+#else
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 // Lane-local refill: the lane copies the 64-byte chunk at global word index gw
 // (a multiple of 16) of ITS OWN stream into quads slot_q0..slot_q0+3 of its own
@@ -432,6 +446,13 @@ __device__ __forceinline__ void ring_fill(uint32_t ring_lane_addr, const uint8_t
     cp_async16_full(dst + 1024u, src + 32);
     cp_async16_full(dst + 1536u, src + 48);
     if (slot_q0 == 0) cp_async16_full(ring_lane_addr + DEC_QUADS * 512u, src);
+#if M3_DEC_L2_PREFETCH
+    // the refill after this one then finds its chunk in L2 instead of waiting on a DRAM row
+    if ((uint64_t)gw * 4ull + 128ull <= nbytes) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 64));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 96));
+    }
+#endif
   } else if (take) {
 #pragma unroll
     for (uint32_t k = 0; k < 4; k++) {
@@ -451,6 +472,12 @@ struct DsAcc {
   int64_t d;      // hot path: (time of the last datapoint) - w_end while the group's pre-check holds
   int64_t w_end;  // exclusive end of the open window
   int32_t cur_w, hi_w;  // open window (-1: none) / highest window initialised so far
+  uint64_t o;     // element index of the open window in the window-major outputs: cur_w * n_series + sidx
+  bool in_open;   // the last datapoint produced lies in the open window (false after an ignored one)
+  // sum as gauge.go:92; min / max start at +inf / -inf instead of NaN: with `v < mn` / `v > mx`
+  // that takes the same decisions as gauge.go:93-99 on every sequence of values (a NaN value never
+  // compares true, signed zeros keep the first one seen), and "no value seen" is the one state
+  // mn == +inf && mx == -inf, written out as NaN / NaN
   double sum, mn, mx;
   uint32_t cnt;      // datapoints in the open window (NaNs counted, gauge.go:85)
   uint32_t cnt_gen;  // cnt as of the last general-path visit (cnt != cnt_gen: hot datapoints since)
@@ -526,9 +553,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
   acc.w_end = 0;
   acc.cur_w = -1;
   acc.hi_w = -1;
+  acc.o = 0;
+  acc.in_open = false;
   acc.sum = 0.0;
-  acc.mn = kNaN;
-  acc.mx = kNaN;
+  acc.mn = __longlong_as_double(0x7ff0000000000000ll);
+  acc.mx = __longlong_as_double((long long)0xfff0000000000000ull);
   acc.cnt = 0;
   acc.cnt_gen = 0;
   acc.last_t = 0;
@@ -537,12 +566,15 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
   (void)range_end;
 
   // ---- fused-downsample helpers (per lane) ----
-  auto ds_store = [&](int32_t w) {  // commit the open window's aggregate
-    const uint64_t o = (uint64_t)(uint32_t)w * p.n_series + sidx;
+  const double kPosInf = __longlong_as_double(0x7ff0000000000000ll);
+  const double kNegInf = __longlong_as_double((long long)0xfff0000000000000ull);
+  auto ds_store = [&]() {  // commit the open window's aggregate
+    const uint64_t o = acc.o;
+    const bool none = acc.mn == kPosInf && acc.mx == kNegInf;  // no non-NaN value in the window
     p.ds_sum[o] = acc.sum;
     p.ds_count[o] = (int64_t)acc.cnt;
-    p.ds_min[o] = acc.mn;
-    p.ds_max[o] = acc.mx;
+    p.ds_min[o] = none ? kNaN : acc.mn;
+    p.ds_max[o] = none ? kNaN : acc.mx;
     if (MODE == 2) {
       p.ds_last[o] = __longlong_as_double((long long)acc.last_v);
       p.ds_last_at[o] = acc.last_t;
@@ -563,17 +595,15 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
     acc.sum = 0.0;
     acc.cnt = 0;
     acc.cnt_gen = 0;
-    acc.mn = kNaN;
-    acc.mx = kNaN;
+    acc.mn = kPosInf;
+    acc.mx = kNegInf;
   };
   auto ds_add = [&](uint64_t vbits) {  // Gauge.updateTotals without `last` (gauge.go:85-101)
     const double dv = __longlong_as_double((long long)vbits);
     acc.cnt++;
-    if (dv == dv) {
-      acc.sum = __dadd_rn(acc.sum, dv);
-      if (acc.mx != acc.mx || acc.mx < dv) acc.mx = dv;
-      if (acc.mn != acc.mn || acc.mn > dv) acc.mn = dv;
-    }
+    if (dv == dv) acc.sum = __dadd_rn(acc.sum, dv);
+    if (dv > acc.mx) acc.mx = dv;
+    if (dv < acc.mn) acc.mn = dv;
   };
 
   // refills are DEC_FILL-word aligned: start at the stream's first word rounded down
@@ -651,14 +681,14 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
                   ((uint64_t)s.prev_delta < (1ull << 60)) && (!INT_OPT || s.is_float);
     if (MODE >= 1) {
       // fused downsample, additionally: timestamps strictly increasing in steps of at most one
-      // window (so a datapoint is in the open window or opens the next one), the whole group
-      // inside the range, the last datapoint inside the open window, and the open window is the
-      // newest one (no committed window ahead that would have to be re-opened).
+      // window (so a datapoint is in the open window or opens the next one), the last datapoint
+      // inside the open window, the open window is the newest one (no committed window ahead that
+      // would have to be re-opened), and at least four more windows before the end of the range
+      // (four datapoints advance at most four windows).  Only the last compare is per group: the
+      // rest is a flag maintained where it can change (general path, window advance).
       acc.d = (int64_t)((uint64_t)s.prev_time - (uint64_t)acc.w_end);
-      pre_ok = pre_ok && acc.cur_w >= 0 && acc.cur_w == acc.hi_w && s.prev_delta > 0 &&
-               s.prev_delta <= p.window && s.prev_time < range_end &&
-               (uint64_t)(range_end - s.prev_time) > 4ull * (uint64_t)s.prev_delta &&
-               acc.d < 0 && (0ull - (uint64_t)acc.d) <= (uint64_t)p.window;
+      pre_ok = pre_ok && acc.in_open && acc.cur_w == acc.hi_w && s.prev_delta > 0 && s.prev_delta <= p.window &&
+               (uint32_t)acc.cur_w + (uint32_t)M3_DEC_CHK < p.n_windows;
     }
 
 #pragma unroll
@@ -737,9 +767,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
                   acc.last_t = (int64_t)((uint64_t)acc.d - (uint64_t)s.prev_delta + (uint64_t)acc.w_end);
                   acc.last_v = s.prev_bits;
                 }
-                ds_store(acc.cur_w);
+                ds_store();
                 acc.cur_w++;
                 acc.hi_w = acc.cur_w;
+                acc.o += p.n_series;
                 acc.w_end += p.window;
                 acc.d -= p.window;
                 ds_reset();
@@ -748,7 +779,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
             s.prev_xor = xr;
             s.prev_bits ^= xr;
             lz_tz(xr, plz, ptz);
-            if (active) ds_add(s.prev_bits);
+            // finished lanes committed their window when they stopped: what they add here is never read
+            ds_add(s.prev_bits);
             s.n += (uint32_t)active;
             continue;
           }
@@ -888,12 +920,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
           src.nbytes = p.streams_bytes;
           src.ring_lane = ring_lane;
           src.ring_safe = ((int)(filled - cw) >= 0) ? safe : 0u;  // ring abandoned after a skip
-          src.events = p.events;
-          src.events_capacity = p.events_capacity;
-          src.event_count = p.event_count;
-          src.series = sidx;
-          src.pos0 = pos0;
-          const bool em = decode_dp_slow<INT_OPT>(tmp, src, p.default_unit, st, sv);
+          EventSink evs;
+          evs.events = p.events;
+          evs.capacity = p.events_capacity;
+          evs.count = p.event_count;
+          evs.series = sidx;
+          evs.pos0 = pos0;
+          const bool em = decode_dp_slow<INT_OPT>(tmp, src, p.default_unit, st, sv, &evs);
           s = tmp;
           t = st;
           v = sv;
@@ -918,24 +951,30 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
           // inside the open window (one unsigned compare covers both bounds; an open window
           // lies inside the range)?  Otherwise: inside the range at all?
           bool in_win = acc.cur_w >= 0 && (uint64_t)(t - (acc.w_end - p.window)) < (uint64_t)p.window;
-          if (!in_win && t >= p.range_start && t < range_end) {
+          const bool in_range = t >= p.range_start && t < range_end;
+          if (!in_win && in_range) {
             // commit the window we are leaving
-            if (acc.cur_w >= 0) ds_store(acc.cur_w);
+            if (acc.cur_w >= 0) ds_store();
             int64_t nw;
             if (acc.cur_w >= 0 && t >= acc.w_end && t - acc.w_end < p.window)
               nw = (int64_t)acc.cur_w + 1;
             else
               nw = (int64_t)((uint64_t)(t - p.range_start) / (uint64_t)p.window);
+            acc.o = (uint64_t)nw * p.n_series + sidx;
             if (nw > (int64_t)acc.hi_w) {
               for (int64_t w = (int64_t)acc.hi_w + 1; w < nw; w++) ds_store_empty((int32_t)w);
               acc.hi_w = (int32_t)nw;
               ds_reset();
             } else {  // out-of-order timestamp: reopen a committed window
-              const uint64_t o = (uint64_t)nw * p.n_series + sidx;
+              const uint64_t o = acc.o;
               acc.sum = p.ds_sum[o];
               acc.cnt = (uint32_t)p.ds_count[o];
               acc.mn = p.ds_min[o];
               acc.mx = p.ds_max[o];
+              if (acc.mn != acc.mn) {  // stored as NaN / NaN: no value yet
+                acc.mn = kPosInf;
+                acc.mx = kNegInf;
+              }
               if (MODE == 2) {
                 acc.last_v = (uint64_t)__double_as_longlong(p.ds_last[o]);
                 acc.last_t = p.ds_last_at[o];
@@ -945,6 +984,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
             acc.w_end = p.range_start + (nw + 1) * p.window;
             in_win = true;
           }
+          acc.in_open = in_win;
           if (in_win) {
             // lastAt.IsZero() || timestamp.After(lastAt), gauge.go:74-81 (NaN values included)
             if (MODE == 2 && (acc.cnt == 0 || t > acc.last_t)) {
@@ -954,6 +994,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
             ds_add(v);
           }
           acc.cnt_gen = acc.cnt;
+        }
+        if (!live && acc.cur_w >= 0) {
+          // this lane is done: commit its open window now, so that the hot path may run its
+          // (unconditional) accumulation on finished lanes without harm
+          ds_store();
+          acc.cur_w = -1;
+          acc.in_open = false;
         }
       }
     }
@@ -991,7 +1038,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
 
   // ---------------- epilogue ----------------
   if (MODE >= 1 && valid) {
-    if (acc.cur_w >= 0) ds_store(acc.cur_w);
+    if (acc.cur_w >= 0) ds_store();
     for (int64_t w = (int64_t)acc.hi_w + 1; w < (int64_t)p.n_windows; w++) ds_store_empty((int32_t)w);
   }
   if (valid) {

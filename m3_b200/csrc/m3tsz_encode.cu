@@ -981,7 +981,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
     if (fits && total) {
       const uint8_t *slot0 = p.out + warp_slot * 32ull * p.out_stride;
       if (p.align >= 16) {
-        // series after series, 32 lanes x 16 bytes, eight loads in flight per lane; the flush
+        // series after series, 32 lanes x 16 bytes, sixteen loads in flight per lane; the flush
         // above zero-padded every stream to a whole 16-byte group inside its slot
         for (int j = 0; j < 32; j++) {
           const uint64_t lj = __shfl_sync(FULL_MASK, my_len, j);
@@ -991,12 +991,19 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
           uint4 *dst = reinterpret_cast<uint4 *>(p.packed + oj);
           const uint32_t nv = (uint32_t)((lj + 15) >> 4);
           uint32_t i = lane;
-          for (; i + 224 < nv; i += 256) {
-            uint4 r[8];
+          for (; i + 480 < nv; i += 512) {  // 16 loads in flight per lane: 8 KB per warp
+            uint4 r[16];
 #pragma unroll
-            for (int u = 0; u < 8; u++) r[u] = __ldcg(src + i + 32 * u);
+            for (int u = 0; u < 16; u++) r[u] = __ldcg(src + i + 32 * u);
 #pragma unroll
-            for (int u = 0; u < 8; u++) __stcs(dst + i + 32 * u, r[u]);
+            for (int u = 0; u < 16; u++) __stcs(dst + i + 32 * u, r[u]);
+          }
+          for (; i + 96 < nv; i += 128) {
+            uint4 r[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) r[u] = __ldcg(src + i + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) __stcs(dst + i + 32 * u, r[u]);
           }
           for (; i < nv; i += 32) __stcs(dst + i, __ldcg(src + i));
         }
