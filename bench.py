@@ -3,9 +3,11 @@
 
 Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`
 prints ONE JSON line on rank 0.  One "step" = one pass of the hot path over one
-batch: batch ENCODE of S series x P points straight into one packed buffer
-(lane-per-series sm_100a kernel; no slots, no compaction pass) and batch DECODE of
-the resulting bitstreams.  The batch is 1M series x 1440 points per GPU -- the shape
+batch: batch ENCODE of S series x P points (lane-per-series sm_100a kernel; every
+series into its own segment, like the reference's encoders own their buffers) and batch
+DECODE of those segments addressed by (offset, size) -- no compaction pass in between.
+Packing into ONE buffer for a fileset is the persist step; its cost (encode with packed
+output) is reported next to it as `encode_packed` / `step_packed`.  The batch is 1M series x 1440 points per GPU -- the shape
 BASELINE.json's north-star target is quoted on (configs[2-4]; configs[4] = 8M series
 over 8 GPUs = this at N=8); with N GPUs every rank holds its own 1M-series shard
 (weak scaling, no data-path collective: series are independent).  `--series 100000`
@@ -175,7 +177,7 @@ def make_config(S, P, int_opt, bytes_per_dp):
     return {"workload": "batch of %d series x %d points per GPU (the north-star target shape "
                         "1M x 1440 = configs[2-4] size; configs[4] = 8M over 8 GPUs), Gaussian "
                         "random walk (x0=100, N(0,1) steps), 60 s cadence, unit=Second; step = "
-                        "encode (packed output) + decode" % (S, P),
+                        "encode (per-series segments) + decode" % (S, P),
             "series_per_gpu": S, "points": P, "int_optimized": bool(int_opt),
             "compressed_bytes_per_dp": round(bytes_per_dp, 4),
             "l2": "inputs %.2f GB and outputs %.2f GB per step >> 126 MB L2, no flush needed"
@@ -585,12 +587,15 @@ def run_ours(args):
     int_opt = bool(args.int_optimized)
     codec = BatchCodec(local_rank, int_optimized=int_opt)
     ts, vals, start = synth.gaussian_walk(S, P, dev, seed=1000 + rank)
-    cap_bytes = S * (P * 8 + 256)  # Gaussian walk: ~7.3 B/dp; a short series simply reports M3TSZ_ERR_CAPACITY
-    pk = PackedResult(packed=torch.empty(cap_bytes, dtype=torch.uint8, device=dev),
-                      offsets=torch.empty(S, dtype=torch.int64, device=dev),
-                      out_len=torch.empty(S, dtype=torch.int64, device=dev),
-                      status=torch.empty(S, dtype=torch.int32, device=dev),
-                      total=torch.zeros(1, dtype=torch.int64, device=dev))
+    # per-series segments sized for the data: 9 B per datapoint (Gaussian walk: ~7.3); a series that
+    # needs more reports M3TSZ_ERR_CAPACITY and would be re-encoded with m3tsz_encode_bound (20 B/dp)
+    stride = ((64 + 9 * P) + 63) // 64 * 64
+    from m3_b200.codec import EncodeResult
+    enc = EncodeResult(out=torch.empty((S, stride), dtype=torch.uint8, device=dev),
+                       out_len=torch.empty(S, dtype=torch.int64, device=dev),
+                       status=torch.empty(S, dtype=torch.int32, device=dev))
+    seg_off = torch.arange(S, dtype=torch.int64, device=dev) * stride
+    seg_flat = enc.out.view(-1)
     dec = DecodeResult(ts=torch.empty((S, P), dtype=torch.int64, device=dev),
                        values=torch.empty((S, P), dtype=torch.float64, device=dev),
                        n_points=torch.empty(S, dtype=torch.int32, device=dev),
@@ -599,10 +604,10 @@ def run_ours(args):
     dec_events = []
 
     def encode():
-        codec.encode_packed(ts, vals, start, unit=1, align=64, out=pk)
+        codec.encode(ts, vals, start, unit=1, out=enc)
 
     def decode():
-        codec.decode(pk.packed, pk.offsets, P, out=dec, lengths=pk.out_len)
+        codec.decode(seg_flat, seg_off, P, out=dec, lengths=enc.out_len)
 
     def step(record=False):
         encode()
@@ -626,11 +631,11 @@ def run_ours(args):
     barrier()
     # sanity: the timed path round-trips (float mode exactly; int mode up to the reference's own
     # near-integer rounding -- the parity tests compare those series with the oracle bit for bit)
-    assert int((pk.status != 0).sum()) == 0 and int((dec.status != 0).sum()) == 0
+    assert int((enc.status != 0).sum()) == 0 and int((dec.status != 0).sum()) == 0
     assert torch.equal(dec.ts, ts)
     mism = int((dec.values.view(torch.int64) != vals.view(torch.int64)).sum())
     assert mism <= S * P * 1e-6, mism
-    compressed_bytes = int(pk.out_len.sum().item())
+    compressed_bytes = int(enc.out_len.sum().item())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -669,6 +674,20 @@ def run_ours(args):
         return a.elapsed_time(b) / n
 
     enc_ms = time_fn(encode)
+    # the persist variant: encode straight into one packed buffer (fileset data-file layout)
+    del enc, seg_flat, seg_off
+    torch.cuda.empty_cache()
+    cap_bytes = compressed_bytes + 64 * S + 4096
+    pk = PackedResult(packed=torch.empty(cap_bytes, dtype=torch.uint8, device=dev),
+                      offsets=torch.empty(S, dtype=torch.int64, device=dev),
+                      out_len=torch.empty(S, dtype=torch.int64, device=dev),
+                      status=torch.empty(S, dtype=torch.int32, device=dev),
+                      total=torch.zeros(1, dtype=torch.int64, device=dev))
+    encp = lambda: codec.encode_packed(ts, vals, start, unit=1, align=64, out=pk)
+    encp()
+    assert int((pk.status != 0).sum()) == 0 and int(pk.out_len.sum().item()) == compressed_bytes
+    encp_ms = time_fn(encp)
+    decp_ms = time_fn(lambda: codec.decode(pk.packed, pk.offsets, P, out=dec, lengths=pk.out_len))
     extras = not args.no_extras
     side = {}
     if extras:
@@ -676,13 +695,12 @@ def run_ours(args):
         n_win = (P * 60 + 299) // 300
         side["fixture_set"] = fixture_set_throughput(codec, dev, time_fn)
         # segment checksums (row N2): Adler-32 of every stream of the packed batch
-        off1 = torch.cat([pk.offsets, pk.offsets[-1:]])
-        ck, ck_st = codec.segment_checksums(pk.packed, off1, lengths=pk.out_len)
+            ck, ck_st = codec.segment_checksums(pk.packed, pk.offsets, lengths=pk.out_len)
         assert int((ck_st != 0).sum()) == 0
-        ck_ms = time_fn(lambda: codec.segment_checksums(pk.packed, off1, lengths=pk.out_len))
+        ck_ms = time_fn(lambda: codec.segment_checksums(pk.packed, pk.offsets, lengths=pk.out_len))
         side["segment_checksum"] = {"streams": S, "bytes": compressed_bytes, "ms": ck_ms,
                                     "algorithmic_gbs": compressed_bytes / (ck_ms * 1e-3) / 1e9}
-        del ck, ck_st, off1
+        del ck, ck_st
         # fused decode + 5-min Gauge downsample (config 4) on the full batch needs CSR offsets:
         # re-pack the batch once in series order (not timed)
         full_slots = None
@@ -795,6 +813,9 @@ def run_ours(args):
         "data": "synthetic", "config": make_config(S, P, int_opt, compressed_bytes / (S * P)),
         "encode_dps": S * P / (enc_ms * 1e-3), "decode_dps": S * P / (dec_ms_max * 1e-3),
         "encode_ms": enc_ms, "decode_ms": dec_ms_max,
+        "encode_packed": {"ms": encp_ms, "dps": S * P / (encp_ms * 1e-3), "decode_from_packed_ms": decp_ms,
+                          "step_packed_ms": encp_ms + decp_ms,
+                          "note": "encode with one packed output buffer (m3tsz_encode_batch_packed) + decode of it"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_fetch": fetch, "gpu_launches": launches,
         "clocks": clocks, "fetch_allgather": allgather,
     }

@@ -352,8 +352,9 @@ int m3tsz_decode_downsample_batch_host(m3tsz_ctx *ctx, const m3tsz_options *opts
  *   digest.Checksum               src/dbnode/digest/digest.go:36-38
  *   check                         src/dbnode/persist/fs/read.go:395-397, seek.go:370-373
  * Computes the Adler-32 of every stream [d_offsets[s], d_offsets[s+1]) -- or
- * [d_offsets[s], d_offsets[s] + d_lengths[s]) when d_lengths is given (padded
- * starts) -- into d_checksums (optional) and, when d_expected (the index entries'
+ * [d_offsets[s], d_offsets[s] + d_lengths[s]) when d_lengths is given (index-entry
+ * (Offset, Size) addressing: any placement and order, d_offsets then needs only
+ * n_series entries) -- into d_checksums (optional) and, when d_expected (the index entries'
  * DataChecksum) is given, sets d_status[s] to M3TSZ_ERR_CHECKSUM_MISMATCH where
  * it differs.  One of d_checksums / d_status is required.
  * ---------------------------------------------------------------------- */

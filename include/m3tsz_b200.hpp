@@ -9,8 +9,9 @@
 //   m3tsz::ReaderIterator <- encoding.ReaderIterator (m3tsz/iterator.go)
 //   m3tsz::Decoder        <- encoding.Decoder        (m3tsz/decoder.go)
 //   m3tsz::BatchCodec     <- the batch sites
-// Per-datapoint methods are a buffered facade: the bitstream is produced /
-// consumed by one GPU launch.  There is no CPU codec behind this header.
+// Encoder / ReaderIterator are RAII wrappers of the C streaming handles (m3tsz_encoder_*,
+// m3tsz_iter_*): the bitstream is produced / consumed by one GPU launch when it is needed.
+// There is no CPU codec behind this header.
 #pragma once
 
 #include <cstdint>
@@ -105,160 +106,117 @@ class BatchCodec {
   m3tsz_options opts_{};
 };
 
-// encoding.Encoder facade (m3tsz/encoder.go:64-457)
+// encoding.Encoder (m3tsz/encoder.go:64-457): RAII over the C streaming handle; every method is
+// one m3tsz_encoder_* call (the same entry points the cgo shim of INTEGRATION.md binds).
 class Encoder {
  public:
-  Encoder(BatchCodec &codec, int64_t start_nanos) : codec_(codec) { Reset(start_nanos); }
-
-  // Encode (encoder.go:90-110): validates what the reference validates eagerly
-  // (closed encoder, unrecognised unit, s/ms delta-of-delta int32 overflow).
-  void Encode(Datapoint dp, int unit, const std::string &annotation = std::string()) {
-    if (closed_) throw Error(M3TSZ_ERR_ENCODER_CLOSED, "");
-    const bool changed = unit >= 1 && unit <= 8 && unit != unit_;
-    const int64_t delta = dp.timestamp_nanos - prev_time_;
-    if (!changed) {
-      if (unit < 1 || unit > 8) throw Error(M3TSZ_ERR_UNRECOGNIZED_UNIT, "");
-      static const int64_t kNs[9] = {0, 1000000000LL, 1000000LL, 1000LL, 1LL, 60000000000LL,
-                                     3600000000000LL, 86400000000000LL, 31536000000000000LL};
-      const int64_t dod = (delta - prev_delta_) / kNs[unit];
-      if (unit <= 2 && dod != (int64_t)(int32_t)dod)
-        throw Error(M3TSZ_ERR_DOD_OVERFLOW, "deltaOfDelta value " + std::to_string(dod) +
-                                                (unit == 1 ? " s" : " ms") + " overflows 32 bits");
-    }
-    if (!annotation.empty()) {
-      m3tsz_annotation_entry e;
-      e.dp_index = (uint32_t)ts_.size();
-      e.length = (uint32_t)annotation.size();
-      e.byte_offset = ann_bytes_.size();
-      ann_entries_.push_back(e);
-      ann_bytes_.insert(ann_bytes_.end(), annotation.begin(), annotation.end());
-    }
-    prev_time_ = dp.timestamp_nanos;
-    if (changed) {
-      unit_ = unit;
-      prev_delta_ = 0;
-    } else {
-      prev_delta_ = delta;
-    }
-    ts_.push_back(dp.timestamp_nanos);
-    vals_.push_back(dp.value);
-    units_.push_back((uint8_t)unit);
-    dirty_ = true;
+  Encoder(BatchCodec &codec, int64_t start_nanos) {
+    int rc = m3tsz_encoder_create(codec.ctx(), &codec.options(), start_nanos, &h_);
+    if (rc != M3TSZ_OK) throw Error(rc, "m3tsz_encoder_create");
   }
-  int NumEncoded() const { return (int)ts_.size(); }   // :299-302
-  bool Empty() const { return ts_.empty(); }           // :330-332
-  Datapoint LastEncoded() const {                      // :305-319 (datapoint as written)
-    if (ts_.empty()) throw Error(M3TSZ_ERR_NO_DATAPOINTS, "");
-    return Datapoint{ts_.back(), vals_.back()};
+  ~Encoder() { m3tsz_encoder_destroy(h_); }
+  Encoder(const Encoder &) = delete;
+  Encoder &operator=(const Encoder &) = delete;
+
+  void Encode(Datapoint dp, int unit, const std::string &annotation = std::string()) {  // :90-110
+    int rc = m3tsz_encoder_encode(h_, dp.timestamp_nanos, dp.value, unit,
+                                  reinterpret_cast<const uint8_t *>(annotation.data()), annotation.size());
+    if (rc == M3TSZ_ERR_DOD_OVERFLOW)
+      throw Error(rc, "deltaOfDelta value " + std::to_string(m3tsz_encoder_failed_dod(h_)) +
+                          (unit == M3TSZ_UNIT_SECOND ? " s" : " ms") + " overflows 32 bits");
+    if (rc != M3TSZ_OK) throw Error(rc, "");
+  }
+  int NumEncoded() const { return (int)m3tsz_encoder_num_encoded(h_); }  // :299-302
+  bool Empty() const { return m3tsz_encoder_empty(h_) != 0; }            // :330-332
+  Datapoint LastEncoded() {  // :305-319, incl. the scaled-int / zero quirk
+    Datapoint dp{0, 0.0};
+    int rc = m3tsz_encoder_last_encoded(h_, &dp.timestamp_nanos, &dp.value);
+    if (rc != M3TSZ_OK) throw Error(rc, "");
+    return dp;
+  }
+  uint64_t LastAnnotationChecksum() const {  // :321-327
+    uint64_t c = 0;
+    int rc = m3tsz_encoder_last_annotation_checksum(h_, &c);
+    if (rc != M3TSZ_OK) throw Error(rc, "");
+    return c;
+  }
+  size_t Len() {  // :336-354
+    uint64_t n = 0;
+    int rc = m3tsz_encoder_len(h_, &n);
+    if (rc != M3TSZ_OK) throw Error(rc, "");
+    return (size_t)n;
   }
   // Stream(): head||tail bytes of the segment; empty vector == (nil, false)  (:282-297)
   const std::vector<uint8_t> &Stream() {
-    if (dirty_) {
-      std::vector<uint64_t> off;
-      std::vector<int32_t> st;
-      if (ts_.empty()) {
-        bytes_.clear();
-      } else {
-        const uint64_t aoff[2] = {0, ann_entries_.size()};
-        codec_.EncodeBatch(ts_.data(), vals_.data(), 1, ts_.size(), nullptr, &start_, M3TSZ_UNIT_SECOND,
-                           bytes_, off, st, units_.data(), ann_entries_.empty() ? nullptr : aoff,
-                           ann_entries_.data(), ann_bytes_.data(), ann_bytes_.size());
-        if (st[0] != M3TSZ_OK) throw Error(st[0], "encode");
-      }
-      dirty_ = false;
-    }
+    bytes_.resize(Len());
+    uint64_t n = 0;
+    int rc = m3tsz_encoder_stream(h_, bytes_.data(), bytes_.size(), &n, &tail_len_);
+    if (rc != M3TSZ_OK) throw Error(rc, "");
+    bytes_.resize(n);
     return bytes_;
   }
-  size_t Len() { return Stream().size(); }             // :336-354
-  void Reset(int64_t start_nanos) {                    // :262-279
-    start_ = start_nanos;
-    ts_.clear();
-    vals_.clear();
-    units_.clear();
-    ann_entries_.clear();
-    ann_bytes_.clear();
-    bytes_.clear();
-    dirty_ = false;
-    closed_ = false;
-    prev_time_ = start_nanos;
-    prev_delta_ = 0;
-    const int du = codec_.options().default_time_unit;
-    static const int64_t kNs[9] = {0, 1000000000LL, 1000000LL, 1000LL, 1LL, 60000000000LL,
-                                   3600000000000LL, 86400000000000LL, 31536000000000000LL};
-    unit_ = (du >= 1 && du <= 8 && start_nanos % kNs[du] == 0) ? du : 0;  // initialTimeUnit
+  size_t TailLen() const { return (size_t)tail_len_; }  // ts.Segment tail of the last Stream()
+  void Reset(int64_t start_nanos, uint64_t capacity = 0) {  // :262-279
+    int rc = m3tsz_encoder_reset(h_, start_nanos, capacity);
+    if (rc != M3TSZ_OK) throw Error(rc, "");
   }
-  void Close() { closed_ = true; }                     // :357-370
-  std::vector<uint8_t> Discard() {                     // :374-381
+  void Close() { m3tsz_encoder_close(h_); }  // :357-370
+  std::vector<uint8_t> Discard() {            // :374-381
     std::vector<uint8_t> b = Stream();
     Close();
     return b;
   }
+  std::vector<uint8_t> DiscardReset(int64_t start_nanos, uint64_t capacity = 0) {  // :385-392
+    std::vector<uint8_t> b = Stream();
+    Reset(start_nanos, capacity);
+    return b;
+  }
 
  private:
-  BatchCodec &codec_;
-  int64_t start_ = 0, prev_time_ = 0, prev_delta_ = 0;
-  int unit_ = 0;
-  bool dirty_ = false, closed_ = false;
-  std::vector<int64_t> ts_;
-  std::vector<double> vals_;
-  std::vector<uint8_t> units_, ann_bytes_, bytes_;
-  std::vector<m3tsz_annotation_entry> ann_entries_;
+  m3tsz_encoder *h_ = nullptr;
+  std::vector<uint8_t> bytes_;
+  uint64_t tail_len_ = 0;
 };
 
-// encoding.ReaderIterator facade (m3tsz/iterator.go:67-278)
+// encoding.ReaderIterator (m3tsz/iterator.go:67-278) over m3tsz_iter_*
 class ReaderIterator {
  public:
-  ReaderIterator(BatchCodec &codec, const uint8_t *data, size_t len) : codec_(codec) { Reset(data, len); }
-  void Reset(const uint8_t *data, size_t len) {        // :253-263
-    data_.assign(data, data + len);
-    decoded_ = false;
-    closed_ = false;
-    i_ = -1;
-    n_ = 0;
-    err_ = 0;
+  ReaderIterator(BatchCodec &codec, const uint8_t *data, size_t len) {
+    int rc = m3tsz_iter_create(codec.ctx(), &codec.options(), &h_);
+    if (rc != M3TSZ_OK) throw Error(rc, "m3tsz_iter_create");
+    Reset(data, len);
   }
-  bool Next() {                                        // :81-106
-    if (closed_) return false;
-    if (!decoded_) DecodeAll();
-    if (i_ + 1 < n_) {
-      i_++;
-      return true;
-    }
-    i_ = n_;
-    return false;
+  ~ReaderIterator() { m3tsz_iter_destroy(h_); }
+  ReaderIterator(ReaderIterator &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+  ReaderIterator(const ReaderIterator &) = delete;
+  ReaderIterator &operator=(const ReaderIterator &) = delete;
+
+  void Reset(const uint8_t *data, size_t len) {  // :253-263
+    int rc = m3tsz_iter_reset(h_, data, len);
+    if (rc != M3TSZ_OK) throw Error(rc, "");
   }
-  Datapoint Current() const { return Datapoint{ts_[i_], vals_[i_]}; }  // :229-231
-  int CurrentUnit() const { return unit_; }
-  int Err() const { return closed_ ? M3TSZ_ERR_ITER_CLOSED : ((i_ >= n_ - 1 || n_ == 0) ? err_ : 0); }
-  void Close() { closed_ = true; }                     // :267-278
+  bool Next() { return m3tsz_iter_next(h_) != 0; }  // :81-106
+  Datapoint Current() const {                       // :229-231
+    Datapoint dp{0, 0.0};
+    m3tsz_iter_current(h_, &dp.timestamp_nanos, &dp.value, nullptr, nullptr, nullptr);
+    return dp;
+  }
+  int CurrentUnit() const {  // the unit in force at the current datapoint
+    int32_t u = 0;
+    m3tsz_iter_current(h_, nullptr, nullptr, &u, nullptr, nullptr);
+    return u;
+  }
+  std::string CurrentAnnotation() const {  // annotation of the current datapoint ("" = none)
+    const uint8_t *p = nullptr;
+    uint64_t n = 0;
+    m3tsz_iter_current(h_, nullptr, nullptr, nullptr, &p, &n);
+    return n ? std::string(reinterpret_cast<const char *>(p), n) : std::string();
+  }
+  int Err() const { return m3tsz_iter_err(h_); }  // :234-236
+  void Close() { m3tsz_iter_close(h_); }          // :267-278
 
  private:
-  void DecodeAll() {
-    decoded_ = true;
-    uint64_t cap = 2048;
-    std::vector<uint32_t> n;
-    std::vector<int32_t> st;
-    std::vector<uint8_t> unit;
-    const uint64_t off[2] = {0, data_.size()};
-    for (;;) {
-      codec_.DecodeBatch(data_.data(), data_.size(), off, 1, cap, ts_, vals_, n, st, &unit);
-      if (st[0] == M3TSZ_ERR_CAPACITY) {
-        cap = n[0];
-        continue;
-      }
-      break;
-    }
-    n_ = (int64_t)(n[0] < cap ? n[0] : cap);
-    err_ = st[0];
-    unit_ = unit[0];
-  }
-  BatchCodec &codec_;
-  std::vector<uint8_t> data_;
-  std::vector<int64_t> ts_;
-  std::vector<double> vals_;
-  int64_t i_ = -1, n_ = 0;
-  int err_ = 0, unit_ = 0;
-  bool decoded_ = false, closed_ = false;
+  m3tsz_iter *h_ = nullptr;
 };
 
 // encoding.Decoder (m3tsz/decoder.go:27-44)

@@ -311,11 +311,11 @@ class BatchCodec:
 
     def segment_checksums(self, streams, offsets, lengths=None, expected=None):
         """Adler-32 of every stream (ts.Segment.CalculateChecksum, src/dbnode/ts/segment.go:60-76)
-        over the decoder's CSR layout; `lengths` (int64 [S]) gives exact sizes when the starts are
-        padded; `expected` (int32/uint32 [S], the index entries' DataChecksum) turns differences
+        over the decoder's CSR layout; with `lengths` (int64 [S]) stream s = offsets[s] .. +lengths[s]
+        (any placement, `offsets` may then have S entries); `expected` (int32/uint32 [S], the index entries' DataChecksum) turns differences
         into status M3TSZ_ERR_CHECKSUM_MISMATCH.  Returns (checksums int32-viewed-as-uint32 [S],
         status int32 [S])."""
-        S = offsets.numel() - 1
+        S = offsets.numel() - 1 if lengths is None else lengths.numel()
         dev = self.device
         out = torch.empty(S, dtype=torch.int32, device=dev)
         status = torch.empty(S, dtype=torch.int32, device=dev)

@@ -30,11 +30,9 @@ __global__ void __launch_bounds__(CK_WARPS * 32) checksum_kernel(const ChecksumP
   const uint64_t s = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (s >= p.n_series) return;
   const uint64_t o0 = p.offsets[s];
-  uint64_t o1 = p.offsets[s + 1];
-  if (p.lengths) {  // index entry Size: the next start may be padded
-    const uint64_t l = p.lengths[s];
-    o1 = (l <= o1 - o0 && o1 >= o0) ? o0 + l : ~0ull;  // a size past the next start is an argument error
-  }
+  // index-entry addressing (Offset, Size): the streams may sit anywhere in the buffer, in any
+  // order (the packed encoder places them in completion order); CSR otherwise
+  const uint64_t o1 = p.lengths ? o0 + p.lengths[s] : p.offsets[s + 1];
   if (o1 < o0 || o1 > p.streams_bytes || o1 - o0 >= (1ull << 28)) {
     if (lane == 0) {
       if (p.out) p.out[s] = 0;

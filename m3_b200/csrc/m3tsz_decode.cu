@@ -34,7 +34,7 @@ namespace m3tsz {
 #define M3_DEC_MIN_BLOCKS 4  // 4 x 4 warps with ~110 registers beat 5 blocks squeezed into 96 (profiles/r02_decode_history.md)
 #endif
 #ifndef M3_DEC_MIN_BLOCKS_DS
-#define M3_DEC_MIN_BLOCKS_DS 4  // fused-downsample kernel (5 blocks fit its shared memory but spill registers)
+#define M3_DEC_MIN_BLOCKS_DS 5  // fused-downsample kernels: 5 x 4 warps at 96 registers (7.94 vs 8.25 ms at 4 blocks)
 #endif
 #ifndef M3_DEC_WARPS
 #define M3_DEC_WARPS 4
@@ -543,6 +543,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
       pos0 = s.pos;
     }
   }
+  if (MODE >= 1 && valid && s.err != 0) {  // rejected before its first datapoint: publish now (see the sink)
+    if (p.n_points) p.n_points[sidx] = 0;
+    if (p.status) p.status[sidx] = s.err;
+  }
   const uint32_t gbase = (uint32_t)s.wbase;  // streams_bytes < 16 GiB (checked by the host)
   // previous XOR's leading / trailing zero counts, kept eagerly (float path)
   int plz = 64, ptz = 0;
@@ -686,7 +690,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
       // would have to be re-opened), and at least four more windows before the end of the range
       // (four datapoints advance at most four windows).  Only the last compare is per group: the
       // rest is a flag maintained where it can change (general path, window advance).
-      acc.d = (int64_t)((uint64_t)s.prev_time - (uint64_t)acc.w_end);
+      // (a finished lane keeps d < 0 and delta == 0: the hot path's advance test needs no `active`)
+      acc.d = live ? (int64_t)((uint64_t)s.prev_time - (uint64_t)acc.w_end) : -1ll;
       pre_ok = pre_ok && acc.in_open && acc.cur_w == acc.hi_w && s.prev_delta > 0 && s.prev_delta <= p.window &&
                (uint32_t)acc.cur_w + (uint32_t)M3_DEC_CHK < p.n_windows;
     }
@@ -760,7 +765,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
           } else {
             // this datapoint's time relative to the end of the open window
             acc.d = (int64_t)((uint64_t)acc.d + (uint64_t)s.prev_delta);
-            const bool adv = active && acc.d >= 0;
+            const bool adv = (int32_t)((uint64_t)acc.d >> 32) >= 0;  // sign of the high word
             if (__any_sync(FULL_MASK, adv)) {
               if (adv) {  // it opens the next window: commit the one it leaves
                 if (MODE == 2 && acc.cnt != acc.cnt_gen) {  // `last` of in-order datapoints = the previous one
@@ -781,7 +786,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
             lz_tz(xr, plz, ptz);
             // finished lanes committed their window when they stopped: what they add here is never read
             ds_add(s.prev_bits);
-            s.n += (uint32_t)active;
+            s.n++;  // finished lanes published n_points / status when they stopped
             continue;
           }
         }
@@ -995,12 +1000,16 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
           }
           acc.cnt_gen = acc.cnt;
         }
-        if (!live && acc.cur_w >= 0) {
-          // this lane is done: commit its open window now, so that the hot path may run its
-          // (unconditional) accumulation on finished lanes without harm
-          ds_store();
+        if (!live && active) {
+          // this lane is done: commit its open window and publish its counters now, so that the
+          // hot path may run its unconditional updates on finished lanes without harm
+          if (acc.cur_w >= 0) ds_store();
           acc.cur_w = -1;
           acc.in_open = false;
+          acc.d = -1;
+          s.prev_delta = 0;
+          if (p.n_points) p.n_points[sidx] = s.n;
+          if (p.status) p.status[sidx] = s.err;
         }
       }
     }
@@ -1042,10 +1051,12 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
     for (int64_t w = (int64_t)acc.hi_w + 1; w < (int64_t)p.n_windows; w++) ds_store_empty((int32_t)w);
   }
   if (valid) {
-    if (p.n_points) p.n_points[sidx] = s.n;
     int st = s.err;
-    if (MODE == 0 && st == 0 && s.n > p.cap) st = M3TSZ_ERR_CAPACITY;
-    if (p.status) p.status[sidx] = st;
+    if (MODE == 0) {
+      if (p.n_points) p.n_points[sidx] = s.n;
+      if (st == 0 && s.n > p.cap) st = M3TSZ_ERR_CAPACITY;
+      if (p.status) p.status[sidx] = st;
+    }
     if (p.unit_out) p.unit_out[sidx] = (uint8_t)(s.n ? s.emit_unit : s.unit);
     if (p.unit_first_out) p.unit_first_out[sidx] = (uint8_t)(s.n ? s.first_unit : s.unit);
     if (p.ann_out) {

@@ -306,13 +306,12 @@ def decode_fileset(codec, fs: FilesetData, max_points: int, verify_checksums: bo
     nbytes = int(fs.data.shape[0])
     d_data = torch.empty(nbytes + 16, dtype=torch.uint8, device=dev)
     if nbytes:
-        d_data[:nbytes].copy_(torch.from_numpy(np.ascontiguousarray(fs.data)), non_blocking=False)
+        d_data[:nbytes].copy_(torch.from_numpy(np.array(fs.data, copy=True)), non_blocking=False)
     d_off = torch.from_numpy(fs.offsets).to(dev)
     d_len = torch.from_numpy(fs.sizes).to(dev)
     status = None
     if verify_checksums and n:
-        off1 = torch.cat([d_off, d_off[-1:] + d_len[-1:]])  # [n+1] (only the starts are used with lengths)
-        _, status = codec.segment_checksums(d_data[:nbytes], off1, lengths=d_len,
+        _, status = codec.segment_checksums(d_data[:nbytes], d_off, lengths=d_len,
                                             expected=torch.from_numpy(fs.data_checksums.view(np.int32)).to(dev))
     res = codec.decode(d_data[:nbytes], d_off, max_points, lengths=d_len, want_events=want_events)
     return res, status
