@@ -173,13 +173,15 @@ def recorded_traffic(workload):
         return None
 
 
-def make_config(S, P, int_opt, bytes_per_dp):
+def make_config(S, P, int_opt, bytes_per_dp=7.3):
+    """Identical for the GPU arm and the reference arm (parameters only; the measured compressed
+    size is reported next to it as `compressed_bytes_per_dp`)."""
+    bytes_per_dp = 7.3
     return {"workload": "batch of %d series x %d points per GPU (the north-star target shape "
                         "1M x 1440 = configs[2-4] size; configs[4] = 8M over 8 GPUs), Gaussian "
                         "random walk (x0=100, N(0,1) steps), 60 s cadence, unit=Second; step = "
                         "encode (per-series segments) + decode" % (S, P),
             "series_per_gpu": S, "points": P, "int_optimized": bool(int_opt),
-            "compressed_bytes_per_dp": round(bytes_per_dp, 4),
             "l2": "inputs %.2f GB and outputs %.2f GB per step >> 126 MB L2, no flush needed"
                   % (S * P * 16 / 1e9, S * P * (16 + bytes_per_dp) / 1e9),
             "parallelism": "series sharded per GPU, no data-path collective"}
@@ -392,7 +394,7 @@ def run_reference(args):
         return
     value, info = cpu_oracle_throughput(args.series, args.points, args.int_optimized, budget_s=args.ref_seconds,
                                         steps=args.steps, warmup=args.warmup, full=True)
-    cfg = make_config(args.series, args.points, args.int_optimized, info["compressed_bytes_per_dp"])
+    cfg = make_config(args.series, args.points, args.int_optimized)
     if not info["full_batch"]:
         cfg["reference_sample"] = "bounded: %d of %d series per step" % (info["series_per_step"], args.series)
     line = {
@@ -400,6 +402,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64/f64 (integer bit manipulation; float64 values)", "data": "synthetic", "config": cfg,
+        "compressed_bytes_per_dp": info["compressed_bytes_per_dp"],
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"], "encode_dps": info["encode_dps"],
                          "decode_dps": info["decode_dps"], "note": info["note"], "core_info": info["core_info"]},
@@ -688,6 +691,16 @@ def run_ours(args):
     assert int((pk.status != 0).sum()) == 0 and int(pk.out_len.sum().item()) == compressed_bytes
     encp_ms = time_fn(encp)
     decp_ms = time_fn(lambda: codec.decode(pk.packed, pk.offsets, P, out=dec, lengths=pk.out_len))
+    # decode with point-major ([point][series], step-major) outputs: same datapoints, coalesced stores
+    dec_pm = DecodeResult(ts=dec.ts.view(P, S), values=dec.values.view(P, S), n_points=dec.n_points,
+                          status=dec.status, unit=dec.unit, annotations=None)
+    dpm = lambda: codec.decode(pk.packed, pk.offsets, P, out=dec_pm, lengths=pk.out_len, point_major=True)
+    dpm()
+    torch.cuda.synchronize()
+    assert int((dec.status != 0).sum()) == 0 and bool((dec_pm.ts[:, 0] == ts[0]).all()) and \
+        bool((dec_pm.ts[P - 1] == ts[:, P - 1]).all())
+    dec_pm_ms = time_fn(dpm)
+    codec.decode(pk.packed, pk.offsets, P, out=dec, lengths=pk.out_len)  # series-major again for the extras below
     extras = not args.no_extras
     side = {}
     if extras:
@@ -695,7 +708,7 @@ def run_ours(args):
         n_win = (P * 60 + 299) // 300
         side["fixture_set"] = fixture_set_throughput(codec, dev, time_fn)
         # segment checksums (row N2): Adler-32 of every stream of the packed batch
-            ck, ck_st = codec.segment_checksums(pk.packed, pk.offsets, lengths=pk.out_len)
+        ck, ck_st = codec.segment_checksums(pk.packed, pk.offsets, lengths=pk.out_len)
         assert int((ck_st != 0).sum()) == 0
         ck_ms = time_fn(lambda: codec.segment_checksums(pk.packed, pk.offsets, lengths=pk.out_len))
         side["segment_checksum"] = {"streams": S, "bytes": compressed_bytes, "ms": ck_ms,
@@ -810,9 +823,15 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64/f64 (integer bit manipulation; float64 values)",
-        "data": "synthetic", "config": make_config(S, P, int_opt, compressed_bytes / (S * P)),
+        "data": "synthetic", "config": make_config(S, P, int_opt),
+        "compressed_bytes_per_dp": compressed_bytes / (S * P),
         "encode_dps": S * P / (enc_ms * 1e-3), "decode_dps": S * P / (dec_ms_max * 1e-3),
         "encode_ms": enc_ms, "decode_ms": dec_ms_max,
+        "decode_point_major": {"ms": dec_pm_ms, "dps": S * P / (dec_pm_ms * 1e-3),
+                               "algorithmic_gbs": alg_bytes / (dec_pm_ms * 1e-3) / 1e9,
+                               "frac_of_hbm": alg_bytes / (dec_pm_ms * 1e-3) / 1e9 / peak,
+                               "note": "m3tsz_decode_batch_ex extras.point_major: outputs [point][series] "
+                                       "(step-major), every step stores coalesced 256-byte rows"},
         "encode_packed": {"ms": encp_ms, "dps": S * P / (encp_ms * 1e-3), "decode_from_packed_ms": decp_ms,
                           "step_packed_ms": encp_ms + decp_ms,
                           "note": "encode with one packed output buffer (m3tsz_encode_batch_packed) + decode of it"},

@@ -139,6 +139,13 @@ typedef struct m3tsz_decode_extras {
   uint64_t events_capacity;
   uint64_t *d_event_count;   /* required with d_events; must be zero on entry; receives the number of
                                 events produced (may exceed events_capacity: re-run with a larger table) */
+  int32_t point_major;       /* != 0: d_ts / d_val are POINT-major, [max_points][n_series] (datapoint i of
+                                series s at i * n_series + s) -- the step-major layout the query engine's
+                                step iterators consume (src/query/storage/m3/encoded_step_iterator_generic.go),
+                                like the downsample outputs.  Every decode step then stores 32 consecutive
+                                elements per warp (coalesced 256-byte rows) instead of 32 separate 32-byte
+                                sectors; rows >= n_points[s] of a series are left untouched. */
+  int32_t reserved;
 } m3tsz_decode_extras;
 
 /* ------------------------------------------------------------------------

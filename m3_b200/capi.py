@@ -49,7 +49,8 @@ EVENT_TIME_UNIT, EVENT_ANNOTATION = 1, 2
 class DecodeExtras(C.Structure):
     """m3tsz_decode_extras."""
     _fields_ = [("d_lengths", C.c_void_p), ("d_unit_first", C.c_void_p), ("d_events", C.c_void_p),
-                ("events_capacity", C.c_uint64), ("d_event_count", C.c_void_p)]
+                ("events_capacity", C.c_uint64), ("d_event_count", C.c_void_p), ("point_major", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class AnnotationEntry(C.Structure):

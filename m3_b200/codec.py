@@ -78,19 +78,21 @@ class BatchCodec:
     # ------------------------------------------------------------------ decode
     def decode(self, streams: torch.Tensor, offsets: torch.Tensor, max_points: int,
                want_annotations=False, out: Optional[DecodeResult] = None,
-               lengths: Optional[torch.Tensor] = None, want_events=0) -> DecodeResult:
+               lengths: Optional[torch.Tensor] = None, want_events=0, point_major=False) -> DecodeResult:
         """streams: uint8 [total] on device; offsets: int64 [S+1] on device (byte offsets), or
         int64 [S] starts + `lengths` int64 [S] (streams placed anywhere, index-entry style).
-        want_events = capacity of the per-datapoint unit / annotation event table (0: none)."""
+        want_events = capacity of the per-datapoint unit / annotation event table (0: none).
+        point_major: outputs are [max_points, S] (step-major, coalesced stores) instead of [S, max_points]."""
         assert streams.dtype == torch.uint8 and streams.is_cuda and streams.is_contiguous()
         assert offsets.dtype == torch.int64 and offsets.is_cuda and offsets.is_contiguous()
         S = offsets.numel() - 1 if lengths is None else lengths.numel()
         dev = self.device
-        if lengths is not None or want_events:
+        if lengths is not None or want_events or point_major:
             if out is None:
+                shape = (max_points, S) if point_major else (S, max_points)
                 out = DecodeResult(
-                    ts=torch.empty((S, max_points), dtype=torch.int64, device=dev),
-                    values=torch.empty((S, max_points), dtype=torch.float64, device=dev),
+                    ts=torch.empty(shape, dtype=torch.int64, device=dev),
+                    values=torch.empty(shape, dtype=torch.float64, device=dev),
                     n_points=torch.empty(S, dtype=torch.int32, device=dev),
                     status=torch.empty(S, dtype=torch.int32, device=dev),
                     unit=torch.empty(S, dtype=torch.uint8, device=dev),
@@ -98,6 +100,7 @@ class BatchCodec:
                                  if want_annotations else None))
             ex = capi.DecodeExtras()
             ex.d_lengths = lengths.data_ptr() if lengths is not None else None
+            ex.point_major = 1 if point_major else 0
             if want_events:
                 if out.unit_first is None:
                     out.unit_first = torch.empty(S, dtype=torch.uint8, device=dev)

@@ -144,7 +144,7 @@ int m3tsz_decode_batch_ex(m3tsz_ctx *ctx, const m3tsz_options *opts, const uint8
       p.event_count = reinterpret_cast<unsigned long long *>(ex->d_event_count);
     }
   }
-  CK(launch_decode(p, opts->int_optimized != 0, 0, (cudaStream_t)stream));
+  CK(launch_decode(p, opts->int_optimized != 0, (ex && ex->point_major) ? 3 : 0, (cudaStream_t)stream));
   ctx->launches++;
   return M3TSZ_OK;
 }

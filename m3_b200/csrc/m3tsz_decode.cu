@@ -488,8 +488,13 @@ struct DsAcc {
 // MODE 0: plain decode (ts, value) ; 1: fused 5-tuple-less downsample (sum, count, min, max);
 // 2: downsample + last (+ lastAt scratch).
 template <bool INT_OPT, int MODE>
-__global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCKS_DS : M3_DEC_MIN_BLOCKS)
+__global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_DEC_MIN_BLOCKS_DS : M3_DEC_MIN_BLOCKS)
     decode_kernel(const DecodeParams p) {
+  // MODE 0: plain decode, series-major output [series][point]; 3: plain decode, point-major output
+  // [point][series] (every step's 32 lanes store 32 consecutive elements: coalesced 256-byte rows);
+  // 1: fused downsample (sum, count, min, max); 2: + last / lastAt
+  constexpr bool DS = (MODE == 1 || MODE == 2), LAST = (MODE == 2), PLAIN = (MODE == 0 || MODE == 3),
+                 PM = (MODE == 3);
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -543,7 +548,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
       pos0 = s.pos;
     }
   }
-  if (MODE >= 1 && valid && s.err != 0) {  // rejected before its first datapoint: publish now (see the sink)
+  if (DS && valid && s.err != 0) {  // rejected before its first datapoint: publish now (see the sink)
     if (p.n_points) p.n_points[sidx] = 0;
     if (p.status) p.status[sidx] = s.err;
   }
@@ -579,7 +584,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
     p.ds_count[o] = (int64_t)acc.cnt;
     p.ds_min[o] = none ? kNaN : acc.mn;
     p.ds_max[o] = none ? kNaN : acc.mx;
-    if (MODE == 2) {
+    if (LAST) {
       p.ds_last[o] = __longlong_as_double((long long)acc.last_v);
       p.ds_last_at[o] = acc.last_t;
     }
@@ -590,7 +595,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
     p.ds_count[o] = 0;
     p.ds_min[o] = kNaN;
     p.ds_max[o] = kNaN;
-    if (MODE == 2) {
+    if (LAST) {
       p.ds_last[o] = 0.0;
       p.ds_last_at[o] = 0;
     }
@@ -617,12 +622,16 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
   uint64_t o_t[4] = {0, 0, 0, 0}, o_v[4] = {0, 0, 0, 0};  // the group's datapoints
   // row 0 of every group is 32-byte aligned when the arrays are and cap is a multiple of 4
   const bool out_aligned =
-      MODE == 0 && (((uintptr_t)p.ts | (uintptr_t)p.val) & 31u) == 0 && (p.cap & 3u) == 0;
+      MODE == 0 && (((uintptr_t)p.ts | (uintptr_t)p.val) & 31u) == 0 && (p.cap & 3u) == 0;  // series-major only
   // running output pointers of this lane's series (MODE 0)
   uint64_t *dt = nullptr, *dv = nullptr;
   if (MODE == 0) {
     dt = reinterpret_cast<uint64_t *>(p.ts) + sidx * p.cap;
     dv = reinterpret_cast<uint64_t *>(p.val) + sidx * p.cap;
+  }
+  if (PM) {  // row `r` of series s lives at r * n_series + s: the pointers advance one row per step
+    dt = reinterpret_cast<uint64_t *>(p.ts) + sidx;
+    dv = reinterpret_cast<uint64_t *>(p.val) + sidx;
   }
   // scheme/unit admit the fast path (they only change on the slow path)
   bool su_ok = false;
@@ -683,7 +692,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
     bool pre_ok = fast_en && (((s.pos + 80u * (M3_DEC_CHK - 1)) >> 5) + DEC_FAST_WORDS <= safe) &&
                   (s.pos + 80u * M3_DEC_CHK <= s.end) && (s.prev_time > 0) &&
                   ((uint64_t)s.prev_delta < (1ull << 60)) && (!INT_OPT || s.is_float);
-    if (MODE >= 1) {
+    if (DS) {
       // fused downsample, additionally: timestamps strictly increasing in steps of at most one
       // window (so a datapoint is in the open window or opens the next one), the last datapoint
       // inside the open window, the open window is the newest one (no committed window ahead that
@@ -753,13 +762,22 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
           // window (previous XOR zero) or a malformed uncontained header (lz + n > 64: the
           // reference shifts everything out)
           const uint64_t xr = (n == 0 || tz < 0) ? 0ull : ((field >> (64 - n)) << tz);
-          if (MODE == 0) {
+          if (PLAIN) {
             s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
             s.prev_xor = xr;
             s.prev_bits ^= xr;
             lz_tz(xr, plz, ptz);
-            o_t[rr] = (uint64_t)s.prev_time;
-            o_v[rr] = s.prev_bits;
+            if (PM) {
+              if (active && group_row0 + (uint32_t)rr < (uint32_t)p.cap) {
+                dt[0] = (uint64_t)s.prev_time;
+                dv[0] = s.prev_bits;
+              }
+              dt += p.n_series;
+              dv += p.n_series;
+            } else {
+              o_t[rr] = (uint64_t)s.prev_time;
+              o_v[rr] = s.prev_bits;
+            }
             s.n += (uint32_t)active;
             continue;
           } else {
@@ -768,7 +786,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
             const bool adv = (int32_t)((uint64_t)acc.d >> 32) >= 0;  // sign of the high word
             if (__any_sync(FULL_MASK, adv)) {
               if (adv) {  // it opens the next window: commit the one it leaves
-                if (MODE == 2 && acc.cnt != acc.cnt_gen) {  // `last` of in-order datapoints = the previous one
+                if (LAST && acc.cnt != acc.cnt_gen) {  // `last` of in-order datapoints = the previous one
                   acc.last_t = (int64_t)((uint64_t)acc.d - (uint64_t)s.prev_delta + (uint64_t)acc.w_end);
                   acc.last_v = s.prev_bits;
                 }
@@ -794,10 +812,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
 
       // ---------------- general path (any mix of cases) ----------------
       {
-        if (MODE >= 1 && pre_ok)  // leaving the hot path: prev_time was carried in acc.d
+        if (DS && pre_ok)  // leaving the hot path: prev_time was carried in acc.d
           s.prev_time = (int64_t)((uint64_t)acc.d + (uint64_t)acc.w_end);
         pre_ok = false;  // the group's pre-check does not survive a general-path datapoint
-        if (MODE == 2 && acc.cnt != acc.cnt_gen) {  // hot datapoints since the last visit: the newest is `last`
+        if (LAST && acc.cnt != acc.cnt_gen) {  // hot datapoints since the last visit: the newest is `last`
           acc.last_t = s.prev_time;
           acc.last_v = s.prev_bits;
           acc.cnt_gen = acc.cnt;
@@ -944,11 +962,23 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
       }
 
       // ---------------- sink (general path) ----------------
-      if (MODE == 0) {
+      if (PLAIN) {
         if (emitted) {
-          o_t[rr] = (uint64_t)t;
-          o_v[rr] = v;
+          // (a live lane produces exactly one datapoint per step: this one is row group_row0 + rr)
+          if (PM) {
+            if (group_row0 + (uint32_t)rr < (uint32_t)p.cap) {
+              dt[0] = (uint64_t)t;
+              dv[0] = v;
+            }
+          } else {
+            o_t[rr] = (uint64_t)t;
+            o_v[rr] = v;
+          }
           s.n++;
+        }
+        if (PM) {
+          dt += p.n_series;
+          dv += p.n_series;
         }
       } else {
         if (emitted) {
@@ -980,7 +1010,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
                 acc.mn = kPosInf;
                 acc.mx = kNegInf;
               }
-              if (MODE == 2) {
+              if (LAST) {
                 acc.last_v = (uint64_t)__double_as_longlong(p.ds_last[o]);
                 acc.last_t = p.ds_last_at[o];
               }
@@ -992,7 +1022,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
           acc.in_open = in_win;
           if (in_win) {
             // lastAt.IsZero() || timestamp.After(lastAt), gauge.go:74-81 (NaN values included)
-            if (MODE == 2 && (acc.cnt == 0 || t > acc.last_t)) {
+            if (LAST && (acc.cnt == 0 || t > acc.last_t)) {
               acc.last_t = t;
               acc.last_v = v;
             }
@@ -1013,7 +1043,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
         }
       }
     }
-    if (MODE >= 1 && pre_ok)  // the group stayed hot: materialise prev_time for the next pre-check
+    if (DS && pre_ok)  // the group stayed hot: materialise prev_time for the next pre-check
       s.prev_time = (int64_t)((uint64_t)acc.d + (uint64_t)acc.w_end);
 
     // ---------------- store the group: each lane writes its own series ----------------
@@ -1046,13 +1076,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE >= 1) ? M3_DEC_MIN_BLOCK
   cp_async_wait_all();
 
   // ---------------- epilogue ----------------
-  if (MODE >= 1 && valid) {
+  if (DS && valid) {
     if (acc.cur_w >= 0) ds_store();
     for (int64_t w = (int64_t)acc.hi_w + 1; w < (int64_t)p.n_windows; w++) ds_store_empty((int32_t)w);
   }
   if (valid) {
     int st = s.err;
-    if (MODE == 0) {
+    if (PLAIN) {
       if (p.n_points) p.n_points[sidx] = s.n;
       if (st == 0 && s.n > p.cap) st = M3TSZ_ERR_CAPACITY;
       if (p.status) p.status[sidx] = st;
@@ -1090,12 +1120,13 @@ static cudaError_t launch_one(const DecodeParams &p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-// mode: 0 plain decode, 1 fused downsample (sum/count/min/max), 2 fused downsample + last
+// mode: 0 plain decode (series-major), 1 fused downsample (sum/count/min/max), 2 + last, 3 plain decode (point-major)
 cudaError_t launch_decode(const DecodeParams &p, bool int_optimized, int mode, cudaStream_t stream) {
   switch (mode) {
     case 0: return int_optimized ? launch_one<true, 0>(p, stream) : launch_one<false, 0>(p, stream);
     case 1: return int_optimized ? launch_one<true, 1>(p, stream) : launch_one<false, 1>(p, stream);
     case 2: return int_optimized ? launch_one<true, 2>(p, stream) : launch_one<false, 2>(p, stream);
+    case 3: return int_optimized ? launch_one<true, 3>(p, stream) : launch_one<false, 3>(p, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -1,8 +1,6 @@
 mkdir -p gpurun_out
-(timeout 1800 python -m pytest tests -q -m gpu 2>&1 | tail -60) > gpurun_out/r2e_tests.log 2>&1
-(timeout 600 python scripts/r2_warp_per_series.py 200000) > gpurun_out/r2e_wps.log 2>&1
-(timeout 900 python bench.py --steps 5 --warmup 3) > gpurun_out/r2e_bench.json 2> gpurun_out/r2e_bench.err
-(timeout 600 python bench.py --impl reference --steps 2 --warmup 1) > gpurun_out/r2e_bench_ref.json 2> gpurun_out/r2e_bench_ref.err
-ncu --set full --clock-control none --import-source on -k regex:decode_kernel -s 3 -c 1 -o gpurun_out/r2e_ds_full python scripts/prof_decode.py 1000000 > gpurun_out/r2e_prof.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:decode_warp_per_series -s 1 -c 1 -o gpurun_out/r2e_wps_full python scripts/r2_warp_per_series.py 200000 >> gpurun_out/r2e_prof.log 2>&1
-tail -25 gpurun_out/r2e_tests.log; cat gpurun_out/r2e_wps.log; tail -c 3000 gpurun_out/r2e_bench.json; tail -5 gpurun_out/r2e_bench.err; tail -c 1500 gpurun_out/r2e_bench_ref.json; tail -5 gpurun_out/r2e_bench_ref.err
+(timeout 600 python -m pytest tests/test_gpu_round2.py -q -m gpu -k "point_major" 2>&1 | tail -5) > gpurun_out/r2g_tests.log 2>&1
+(timeout 300 python scripts/r2_quick.py 1000000 1) > gpurun_out/r2g_quick.log 2>&1
+(timeout 1500 python bench.py --steps 5 --warmup 3) > gpurun_out/r2g_bench.json 2> gpurun_out/r2g_bench.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2g_smoke.log 2>&1
+tail -5 gpurun_out/r2g_tests.log; cat gpurun_out/r2g_quick.log; tail -3 gpurun_out/r2g_smoke.log; tail -c 7000 gpurun_out/r2g_bench.json; tail -8 gpurun_out/r2g_bench.err

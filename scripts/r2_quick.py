@@ -46,7 +46,11 @@ for int_opt in modes:
     dec2 = codec.decode(pk.packed, pk.offsets, P, lengths=pk.out_len, out=dec)
     t_dec2 = timeit(lambda: codec.decode(pk.packed, pk.offsets, P, lengths=pk.out_len, out=dec))
     ok2 = torch.equal(dec2.ts, ts) and torch.equal(dec2.values.view(torch.int64), vals.view(torch.int64))
-    del dec, dec2
+    del dec2
+    pm = codec.decode(packed, offsets, P, point_major=True)
+    t_pm = timeit(lambda: codec.decode(packed, offsets, P, point_major=True, out=pm))
+    ok_pm = torch.equal(pm.ts.t(), dec.ts) and torch.equal(pm.values.t().contiguous().view(torch.int64), dec.values.view(torch.int64))
+    del dec, pm
     s0 = int(start[0].item())
     ds = codec.decode_downsample(packed, offsets, s0, 300 * 10**9, 288)
     t_ds = timeit(lambda: codec.decode_downsample(packed, offsets, s0, 300 * 10**9, 288, out=ds))
@@ -60,6 +64,7 @@ for int_opt in modes:
     print(f"  encode_packed {t_pk:7.3f} ms  {dp/t_pk/1e6:6.1f} Gdp/s  {(16+bc)*dp/t_pk/1e6:5.0f} GB/s")
     print(f"  decode        {t_dec:7.3f} ms  {dp/t_dec/1e6:6.1f} Gdp/s  {(16+bc)*dp/t_dec/1e6:5.0f} GB/s")
     print(f"  decode(off,len){t_dec2:6.3f} ms  {dp/t_dec2/1e6:6.1f} Gdp/s")
+    print(f"  decode(point-major){t_pm:6.3f} ms  {dp/t_pm/1e6:6.1f} Gdp/s  {(16+bc)*dp/t_pm/1e6:5.0f} GB/s  same_as_series_major={ok_pm}")
     print(f"  dec+ds        {t_ds:7.3f} ms  {dp/t_ds/1e6:6.1f} Gdp/s  {(6.4+bc)*dp/t_ds/1e6:5.0f} GB/s")
     print(f"  dec+ds+last   {t_dsl:7.3f} ms  {dp/t_dsl/1e6:6.1f} Gdp/s  {(9.6+bc)*dp/t_dsl/1e6:5.0f} GB/s")
     del ds, dsl, pk, packed

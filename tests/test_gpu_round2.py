@@ -605,3 +605,37 @@ def test_fileset_ingest_and_tool(codecs, tmp_path, capsys):
     rc = read_data_files.main(["-p", str(tmp_path), "-n", "ns", "-s", "3", "-b", str(START), "-f", "id-0007"])
     out = capsys.readouterr().out
     assert rc == 0 and out.count("{id: id-0007") == P
+
+
+# ------------------------------------------------------------------ point-major decode output
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_point_major_decode_equals_series_major(codecs, int_opt):
+    """extras.point_major: same datapoints, [point][series] layout (coalesced stores)."""
+    rng = np.random.default_rng(12)
+    S, P = 333, 150
+    ts, vals, start = _mixed(rng, S, P)
+    n_points = rng.integers(0, P + 1, size=S).astype(np.int32)
+    n_points[::2] = P
+    streams = []
+    for s in range(S):
+        streams.append(O.encode_series(ts[s, : n_points[s]], vals[s, : n_points[s]], start, O.UNIT_S, int_opt)
+                       if n_points[s] else b"")
+    ann_streams, _ = _annotated_streams(rng, 40, 60, int_opt)  # markers, unit changes: the slow path
+    streams += ann_streams
+    d, off = to_device_streams(streams, 1)
+    codec = codecs[int_opt]
+    for cap in (P, 64):
+        a = codec.decode(d, off, cap)
+        b = codec.decode(d, off, cap, point_major=True)
+        b.ts.fill_(-7)
+        b.values.fill_(-7.0)
+        b = codec.decode(d, off, cap, point_major=True, out=b)
+        torch.cuda.synchronize()
+        assert torch.equal(a.n_points, b.n_points) and torch.equal(a.status, b.status) and torch.equal(a.unit, b.unit)
+        n = a.n_points.cpu().numpy().view(np.uint32).astype(np.int64)
+        at, av = a.ts.cpu().numpy(), a.values.cpu().numpy().view(np.uint64)
+        bt, bv = b.ts.cpu().numpy().T, b.values.cpu().numpy().view(np.uint64).T
+        for s in range(len(streams)):
+            k = min(int(n[s]), cap)
+            assert (at[s, :k] == bt[s, :k]).all() and (av[s, :k] == bv[s, :k]).all(), (s, cap)
+            assert (bt[s, k:] == -7).all(), (s, cap)  # rows past the series' end are untouched
