@@ -121,19 +121,20 @@ def available_host_bytes():
 def bind_to_gpu_numa_node(local_rank):
     """Pins this rank's threads (and so its first-touch pinned allocations) to the NUMA node
     its GPU hangs off; several ranks staging through one socket is what bent the N=8 e2e curve."""
+    bdf = None
     try:
         import torch
-        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id  # torch >= 2.3
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
     except Exception:
+        bdf = None
+    if bdf is None:
         try:
-            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id",
+            bdf = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id",
                                   "--format=csv,noheader"], capture_output=True, text=True, timeout=20).stdout.strip()
-            bdf = out
         except Exception:
             return None
     try:
-        if isinstance(bdf, int):
-            return None
         bdf = bdf.lower()
         if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
             bdf = bdf[4:]
@@ -180,7 +181,8 @@ def make_config(S, P, int_opt, bytes_per_dp=7.3):
     return {"workload": "batch of %d series x %d points per GPU (the north-star target shape "
                         "1M x 1440 = configs[2-4] size; configs[4] = 8M over 8 GPUs), Gaussian "
                         "random walk (x0=100, N(0,1) steps), 60 s cadence, unit=Second; step = "
-                        "encode (per-series segments) + decode" % (S, P),
+                        "encode (series-major inputs -> per-series segments) + decode (-> point-major "
+                        "[point][series] outputs)" % (S, P),
             "series_per_gpu": S, "points": P, "int_optimized": bool(int_opt),
             "l2": "inputs %.2f GB and outputs %.2f GB per step >> 126 MB L2, no flush needed"
                   % (S * P * 16 / 1e9, S * P * (16 + bytes_per_dp) / 1e9),
@@ -599,18 +601,25 @@ def run_ours(args):
                        status=torch.empty(S, dtype=torch.int32, device=dev))
     seg_off = torch.arange(S, dtype=torch.int64, device=dev) * stride
     seg_flat = enc.out.view(-1)
-    dec = DecodeResult(ts=torch.empty((S, P), dtype=torch.int64, device=dev),
-                       values=torch.empty((S, P), dtype=torch.float64, device=dev),
-                       n_points=torch.empty(S, dtype=torch.int32, device=dev),
-                       status=torch.empty(S, dtype=torch.int32, device=dev),
-                       unit=torch.empty(S, dtype=torch.uint8, device=dev), annotations=None)
+    # Encode reads series-major inputs (datapoints arrive per series on the write path); decode writes
+    # POINT-major outputs ([point][series], step-major: what the query engine's step iterators consume,
+    # and every decode step of a warp then stores 32 consecutive elements).  The other combinations
+    # (series-major decode, point-major encode) are timed next to it below.
+    ts_pm, vals_pm = ts.t().contiguous(), vals.t().contiguous()
+    dec_pm = DecodeResult(ts=torch.empty((P, S), dtype=torch.int64, device=dev),
+                          values=torch.empty((P, S), dtype=torch.float64, device=dev),
+                          n_points=torch.empty(S, dtype=torch.int32, device=dev),
+                          status=torch.empty(S, dtype=torch.int32, device=dev),
+                          unit=torch.empty(S, dtype=torch.uint8, device=dev), annotations=None)
+    dec = DecodeResult(ts=dec_pm.ts.view(S, P), values=dec_pm.values.view(S, P), n_points=dec_pm.n_points,
+                       status=dec_pm.status, unit=dec_pm.unit, annotations=None)  # same memory, series-major view
     dec_events = []
 
     def encode():
         codec.encode(ts, vals, start, unit=1, out=enc)
 
     def decode():
-        codec.decode(seg_flat, seg_off, P, out=dec, lengths=enc.out_len)
+        codec.decode(seg_flat, seg_off, P, out=dec_pm, lengths=enc.out_len, point_major=True)
 
     def step(record=False):
         encode()
@@ -634,9 +643,9 @@ def run_ours(args):
     barrier()
     # sanity: the timed path round-trips (float mode exactly; int mode up to the reference's own
     # near-integer rounding -- the parity tests compare those series with the oracle bit for bit)
-    assert int((enc.status != 0).sum()) == 0 and int((dec.status != 0).sum()) == 0
-    assert torch.equal(dec.ts, ts)
-    mism = int((dec.values.view(torch.int64) != vals.view(torch.int64)).sum())
+    assert int((enc.status != 0).sum()) == 0 and int((dec_pm.status != 0).sum()) == 0
+    assert torch.equal(dec_pm.ts, ts_pm)
+    mism = int((dec_pm.values.view(torch.int64) != vals_pm.view(torch.int64)).sum())
     assert mism <= S * P * 1e-6, mism
     compressed_bytes = int(enc.out_len.sum().item())
 
@@ -677,6 +686,12 @@ def run_ours(args):
         return a.elapsed_time(b) / n
 
     enc_ms = time_fn(encode)
+    # the other layouts: point-major encode inputs, series-major decode outputs (round 1's layout)
+    enc_pm_ms = time_fn(lambda: codec.encode(ts_pm, vals_pm, start, unit=1, out=enc, point_major=True))
+    assert int(enc.out_len.sum().item()) == compressed_bytes
+    dec_sm_ms = time_fn(lambda: codec.decode(seg_flat, seg_off, P, out=dec, lengths=enc.out_len))
+    assert torch.equal(dec.ts, ts)
+    del ts_pm, vals_pm
     # the persist variant: encode straight into one packed buffer (fileset data-file layout)
     del enc, seg_flat, seg_off
     torch.cuda.empty_cache()
@@ -691,16 +706,6 @@ def run_ours(args):
     assert int((pk.status != 0).sum()) == 0 and int(pk.out_len.sum().item()) == compressed_bytes
     encp_ms = time_fn(encp)
     decp_ms = time_fn(lambda: codec.decode(pk.packed, pk.offsets, P, out=dec, lengths=pk.out_len))
-    # decode with point-major ([point][series], step-major) outputs: same datapoints, coalesced stores
-    dec_pm = DecodeResult(ts=dec.ts.view(P, S), values=dec.values.view(P, S), n_points=dec.n_points,
-                          status=dec.status, unit=dec.unit, annotations=None)
-    dpm = lambda: codec.decode(pk.packed, pk.offsets, P, out=dec_pm, lengths=pk.out_len, point_major=True)
-    dpm()
-    torch.cuda.synchronize()
-    assert int((dec.status != 0).sum()) == 0 and bool((dec_pm.ts[:, 0] == ts[0]).all()) and \
-        bool((dec_pm.ts[P - 1] == ts[:, P - 1]).all())
-    dec_pm_ms = time_fn(dpm)
-    codec.decode(pk.packed, pk.offsets, P, out=dec, lengths=pk.out_len)  # series-major again for the extras below
     extras = not args.no_extras
     side = {}
     if extras:
@@ -806,7 +811,7 @@ def run_ours(args):
     achieved = alg_bytes / (dec_ms_max * 1e-3) / 1e9
     workload = "%dx%d" % (S, P)
     traffic = recorded_traffic(workload)
-    roofline = {"bound": "hbm", "kernel": "m3tsz::decode_kernel<%s,0>" % ("true" if int_opt else "false"),
+    roofline = {"bound": "hbm", "kernel": "m3tsz::decode_kernel<%s,3> (point-major outputs)" % ("true" if int_opt else "false"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": "profiles/traffic.json (ncu --set full capture, committed)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms_max,
@@ -827,11 +832,11 @@ def run_ours(args):
         "compressed_bytes_per_dp": compressed_bytes / (S * P),
         "encode_dps": S * P / (enc_ms * 1e-3), "decode_dps": S * P / (dec_ms_max * 1e-3),
         "encode_ms": enc_ms, "decode_ms": dec_ms_max,
-        "decode_point_major": {"ms": dec_pm_ms, "dps": S * P / (dec_pm_ms * 1e-3),
-                               "algorithmic_gbs": alg_bytes / (dec_pm_ms * 1e-3) / 1e9,
-                               "frac_of_hbm": alg_bytes / (dec_pm_ms * 1e-3) / 1e9 / peak,
-                               "note": "m3tsz_decode_batch_ex extras.point_major: outputs [point][series] "
-                                       "(step-major), every step stores coalesced 256-byte rows"},
+        "other_layouts": {"decode_series_major_ms": dec_sm_ms,
+                          "decode_series_major_frac_of_hbm": alg_bytes / (dec_sm_ms * 1e-3) / 1e9 / peak,
+                          "step_series_major_ms": enc_ms + dec_sm_ms, "encode_point_major_ms": enc_pm_ms,
+                          "note": "series-major decode outputs ([series][point], round 1's layout); encode from "
+                                  "point-major inputs (direct coalesced loads, currently latency-bound)"},
         "encode_packed": {"ms": encp_ms, "dps": S * P / (encp_ms * 1e-3), "decode_from_packed_ms": decp_ms,
                           "step_packed_ms": encp_ms + decp_ms,
                           "note": "encode with one packed output buffer (m3tsz_encode_batch_packed) + decode of it"},

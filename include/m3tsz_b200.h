@@ -233,6 +233,7 @@ int m3tsz_encode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t 
  *   d_last_value: Encoder.LastEncoded().Value (encoder.go:305-319) -- the float in float mode,
  *                 else the encoder's intVal: the SCALED integer in int mode and 0 when
  *                 int_optimized == 0 (the reference never sets isFloat there);
+ *   point_major_input: see the struct;
  *   d_out_bits  : stream length in bits incl. the end-of-stream marker, before the zero
  *                 padding (splits the bytes into ts.Segment head / tail: the tail is the
  *                 last ceil((pos + 11) / 8) bytes, pos = ((bits - 12) mod 8) + 1,
@@ -240,6 +241,12 @@ int m3tsz_encode_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t 
 typedef struct m3tsz_encode_extras {
   double *d_last_value;
   uint64_t *d_out_bits;
+  int32_t point_major_input; /* != 0: d_ts / d_val are POINT-major, [points_stride][n_series] (datapoint i of
+                                series s at i * n_series + s; the layout m3tsz_decode_batch_ex writes with
+                                extras.point_major): every encode step reads 32 consecutive elements per warp,
+                                no shared-memory staging.  Per-datapoint units and annotations are not
+                                supported with it (M3TSZ_ERR_INVALID_ARG). */
+  int32_t reserved;
 } m3tsz_encode_extras;
 int m3tsz_encode_batch_ex(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *d_ts,
                           const double *d_val, uint64_t n_series, uint64_t points_stride,

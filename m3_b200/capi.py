@@ -53,6 +53,12 @@ class DecodeExtras(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class EncodeExtras(C.Structure):
+    """m3tsz_encode_extras."""
+    _fields_ = [("d_last_value", C.c_void_p), ("d_out_bits", C.c_void_p), ("point_major_input", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class AnnotationEntry(C.Structure):
     _fields_ = [("dp_index", C.c_uint32), ("length", C.c_uint32), ("byte_offset", C.c_uint64)]
 
@@ -124,7 +130,7 @@ def lib():
     pv, pu64 = C.POINTER(vp), C.POINTER(u64)
     L.m3tsz_encode_batch_ex.restype = C.c_int
     L.m3tsz_encode_batch_ex.argtypes = [vp, po, vp, vp, u64, u64, vp, vp, i32, vp, vp, vp, vp, vp, u64,
-                                        vp, vp, vp, vp]
+                                        vp, vp, C.POINTER(EncodeExtras), vp]
     L.m3tsz_encoder_create.restype = C.c_int
     L.m3tsz_encoder_create.argtypes = [vp, po, i64, pv]
     L.m3tsz_encoder_destroy.restype = None

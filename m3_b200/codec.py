@@ -179,13 +179,15 @@ class BatchCodec:
     def encode(self, ts: torch.Tensor, values: torch.Tensor, start: torch.Tensor,
                unit=capi.UNIT_S, n_points: Optional[torch.Tensor] = None,
                units: Optional[torch.Tensor] = None, annotations=None,
-               out_stride: Optional[int] = None, out: Optional[EncodeResult] = None) -> EncodeResult:
+               out_stride: Optional[int] = None, out: Optional[EncodeResult] = None,
+               point_major=False) -> EncodeResult:
         """ts int64 [S,P], values float64 [S,P], start int64 [S] (all on device).
-        annotations: optional (series_off int64 [S+1], entries uint8 [E,16], bytes uint8 [B])."""
+        annotations: optional (series_off int64 [S+1], entries uint8 [E,16], bytes uint8 [B]).
+        point_major: ts / values are [P,S] (step-major, what decode(point_major=True) writes)."""
         assert ts.dtype == torch.int64 and values.dtype == torch.float64
         assert ts.is_cuda and values.is_cuda and ts.is_contiguous() and values.is_contiguous()
         assert start.dtype == torch.int64 and start.is_cuda
-        S, P = ts.shape
+        S, P = (ts.shape[1], ts.shape[0]) if point_major else ts.shape
         dev = self.device
         if out_stride is None:
             out_stride = self.encode_bound(P)
@@ -197,6 +199,15 @@ class BatchCodec:
         a_off = a_ent = a_bytes = None
         if annotations is not None:
             a_off, a_ent, a_bytes = annotations
+        if point_major:
+            ex = capi.EncodeExtras(None, None, 1, 0)
+            rc = capi.lib().m3tsz_encode_batch_ex(
+                self.ctx.handle, C.byref(self.opts), _ptr(ts), _ptr(values), S, P, _ptr(n_points),
+                _ptr(start), int(unit), _ptr(units), _ptr(a_off), _ptr(a_ent), _ptr(a_bytes),
+                _ptr(out.out), out.out.shape[1], _ptr(out.out_len), _ptr(out.status), C.byref(ex),
+                _cuda_stream_ptr(dev))
+            self.ctx.check(rc, "m3tsz_encode_batch_ex")
+            return out
         rc = capi.lib().m3tsz_encode_batch(
             self.ctx.handle, C.byref(self.opts), _ptr(ts), _ptr(values), S, P, _ptr(n_points),
             _ptr(start), int(unit), _ptr(units), _ptr(a_off), _ptr(a_ent), _ptr(a_bytes),

@@ -266,6 +266,10 @@ int m3tsz_encode_batch_ex(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64
   if (extras) {
     p.last_value = extras->d_last_value;
     p.out_bits = extras->d_out_bits;
+    if (extras->point_major_input) {
+      if (d_units || d_ann_series_off) return M3TSZ_ERR_INVALID_ARG;
+      p.in_mode = 1;
+    }
   }
   CK(launch_encode(p, opts->int_optimized != 0, (cudaStream_t)stream));
   ctx->launches++;
@@ -433,7 +437,7 @@ int m3tsz_aggregate_tiles_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const
   if (!guard.ok) return set_cuda_error(ctx, guard.err, "cudaSetDevice");
   // context scratch: window-major aggregates, then series-major tiles
   const size_t wb = (size_t)n_series * n_windows * 8;
-  void *d_sum, *d_cnt, *d_min, *d_max, *d_last, *d_lat, *d_tts, *d_tval, *d_nt, *d_sst, *d_np, *d_es;
+  void *d_sum, *d_cnt, *d_min, *d_max, *d_last, *d_lat, *d_sst, *d_np, *d_es = nullptr;
   int rc;
   if ((rc = ensure(ctx, 8, wb, &d_sum))) return rc;
   if ((rc = ensure(ctx, 9, wb, &d_cnt))) return rc;
@@ -441,43 +445,61 @@ int m3tsz_aggregate_tiles_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const
   if ((rc = ensure(ctx, 11, wb, &d_max))) return rc;
   if ((rc = ensure(ctx, 12, wb, &d_lat))) return rc;
   if ((rc = ensure(ctx, 38, wb, &d_last))) return rc;
-  if ((rc = ensure(ctx, 2, wb, &d_tts))) return rc;
-  if ((rc = ensure(ctx, 3, wb, &d_tval))) return rc;
   if ((rc = ensure(ctx, 4, n_series * 4, &d_np))) return rc;
   if ((rc = ensure(ctx, 5, n_series * 4, &d_sst))) return rc;
-  if ((rc = ensure(ctx, 6, n_series * 4, &d_nt))) return rc;
-  if ((rc = ensure(ctx, 39, n_series * 8, &d_es))) return rc;
   // 1. fused decode + Gauge windows (with `last`)
   rc = downsample_impl(ctx, opts, d_streams, streams_bytes, d_offsets, d_lengths, n_series, start_ns, step_ns,
                        n_windows, (double *)d_sum, (int64_t *)d_cnt, (double *)d_min, (double *)d_max,
                        (double *)d_last, (int64_t *)d_lat, true, (uint32_t *)d_np, (int32_t *)d_sst, st);
   if (rc) return rc;
-  // 2. one datapoint per non-empty window
-  TileParams t;
-  memset(&t, 0, sizeof(t));
-  t.sum = (const double *)d_sum;
-  t.count = (const int64_t *)d_cnt;
-  t.mn = (const double *)d_min;
-  t.mx = (const double *)d_max;
-  t.last = (const double *)d_last;
-  t.src_status = (const int32_t *)d_sst;
-  t.n_series = n_series;
-  t.n_windows = n_windows;
-  t.start = start_ns;
-  t.step = step_ns;
-  t.agg_type = agg_type;
-  t.ts_out = (int64_t *)d_tts;
-  t.val_out = (double *)d_tval;
-  t.n_out = d_n_tiles ? d_n_tiles : (uint32_t *)d_nt;
-  t.enc_start = (int64_t *)d_es;
-  CK(launch_tiles_gather(t, st));
-  ctx->launches++;
-  // 3. re-encode into the packed target buffer
-  rc = m3tsz_encode_batch_packed(ctx, opts, (const int64_t *)d_tts, (const double *)d_tval, n_series, n_windows,
-                                 t.n_out, (const int64_t *)d_es, out_unit, nullptr, nullptr, nullptr, nullptr,
-                                 0, align, d_packed, packed_capacity, d_out_offsets, d_out_len, d_status,
-                                 d_total_bytes, st);
-  if (rc) return rc;
+  // 2. re-encode straight from the window-major aggregates (the encoder's input stage skips empty
+  //    windows, stamps the window end and takes Gauge.ValueOf(agg_type)) into the packed buffer
+  {
+    if (!(align == 1 || align == 4 || align == 8 || align == 16 || align == 32 || align == 64))
+      return M3TSZ_ERR_INVALID_ARG;
+    if (!d_packed || !d_out_offsets || !d_out_len || ((uintptr_t)d_packed & 63u)) return M3TSZ_ERR_INVALID_ARG;
+    CK(cudaMemsetAsync(d_total_bytes, 0, sizeof(uint64_t), st));
+    const uint64_t slot_bytes = m3tsz_encode_bound(n_windows);
+    const uint64_t slots = encode_packed_scratch_slots(n_series);
+    if (slots == 0) return set_cuda_error(ctx, cudaGetLastError(), "encode_packed_scratch_slots");
+    void *scratch = nullptr, *ctr = nullptr;
+    if ((rc = ensure(ctx, 36, slots * slot_bytes, &scratch))) return rc;
+    if ((rc = ensure(ctx, 37, 64, &ctr))) return rc;
+    CK(cudaMemsetAsync(ctr, 0, 64, st));
+    // every series' encoder starts at the tile range's start (the target block's start)
+    if ((rc = ensure(ctx, 39, n_series * 8, &d_es))) return rc;
+    CK(launch_fill_i64((int64_t *)d_es, start_ns, n_series, st));
+    EncodeParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_series = n_series;
+    p.points_stride = n_windows;
+    p.start = (const int64_t *)d_es;
+    p.unit = out_unit;
+    p.default_unit = opts->default_time_unit;
+    p.out = (uint8_t *)scratch;
+    p.out_stride = slot_bytes;
+    p.out_len = d_out_len;
+    p.status = d_status;
+    p.packed = d_packed;
+    p.packed_capacity = packed_capacity;
+    p.packed_off = d_out_offsets;
+    p.packed_cursor = reinterpret_cast<unsigned long long *>(d_total_bytes);
+    p.batch_counter = reinterpret_cast<unsigned long long *>(ctr);
+    p.align = align;
+    p.in_mode = 2;
+    p.tile_sum = (const double *)d_sum;
+    p.tile_count = (const int64_t *)d_cnt;
+    p.tile_min = (const double *)d_min;
+    p.tile_max = (const double *)d_max;
+    p.tile_last = (const double *)d_last;
+    p.tile_src_status = (const int32_t *)d_sst;
+    p.tile_start = start_ns;
+    p.tile_step = step_ns;
+    p.agg_type = agg_type;
+    p.n_tiles_out = d_n_tiles;
+    CK(launch_encode(p, opts->int_optimized != 0, st));
+    ctx->launches += 2;
+  }
   CK(launch_tiles_status((const int32_t *)d_sst, d_status, n_series, st));
   ctx->launches++;
   return M3TSZ_OK;

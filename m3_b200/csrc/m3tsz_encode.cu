@@ -599,15 +599,27 @@ __device__ __forceinline__ void enc_cp_async8(uint32_t dst, const void *src) {
 //   of finished warps overlap the bit packing of the others.  Streams land in completion
 //   order: p.packed_off[s] / p.out_len[s] are the index entry (Offset, Size) of stream s
 //   (persist/schema/types.go:70-78).
-template <bool INT_OPT, bool PACKED>
+// IN = 0: series-major inputs ts/val[S][stride], staged through transposed shared-memory tiles;
+// IN = 1: point-major inputs ts/val[stride][S]: the same tiles, filled lane-locally (a tile row is 32
+//         consecutive elements of the array: coalesced sources, no shuffles).  Direct LDG.64 with two rows
+//         in flight was measured first: 13.0 ms vs 10.3 -- the loads' latency is exposed
+//         (profiles/r02_encode_pm_1Mx1440.ncu_summary.txt: long_scoreboard 4.3);
+// IN = 2: the Gauge aggregates of the fused decode+downsample kernel (window-major): datapoint i of a
+//         series = (tile_start + (i+1)*tile_step, Gauge.ValueOf(agg)) unless window i is empty
+//         (count == 0: skipped) -- the tile aggregation's re-encode without a gather pass.
+template <bool INT_OPT, bool PACKED, int IN>
 __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kernel(const EncodeParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  uint8_t *wbase = reinterpret_cast<uint8_t *>(smem) + warp * ENC_WARP_SMEM;
+  // the direct input stages (IN != 0) need no input tiles: only the output tile lives in shared memory
+  constexpr bool STAGED = (IN == 0 || IN == 1);  // inputs go through the shared-memory tiles
+  constexpr size_t WARP_SMEM = STAGED ? ENC_WARP_SMEM : (size_t)ENC_OUT_TILE_WORDS * 4;
+  uint8_t *wbase = reinterpret_cast<uint8_t *>(smem) + warp * WARP_SMEM;
   // in_tiles: [buffer][array (0 ts, 1 val)][row][lane]
   uint64_t *in_tiles = reinterpret_cast<uint64_t *>(wbase);
-  uint32_t *out_tile = reinterpret_cast<uint32_t *>(in_tiles + 4 * ENC_IN_TILE_DWORDS);
+  uint32_t *out_tile = STAGED ? reinterpret_cast<uint32_t *>(in_tiles + 4 * ENC_IN_TILE_DWORDS)
+                              : reinterpret_cast<uint32_t *>(wbase);
 
   const uint64_t n_batches = (p.n_series + 31) >> 5;
   const uint64_t warp_slot = (uint64_t)blockIdx.x * ENC_WARPS + warp;  // PACKED: scratch slot set
@@ -667,7 +679,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   uint32_t last_ann_len = 0;  // 0 = no annotation written yet
   const uint32_t slot_words = (uint32_t)(p.out_stride >> 2);
   if (valid) {
-    n_pts = p.n_points ? p.n_points[sidx] : (uint32_t)p.points_stride;
+    n_pts = (IN != 2 && p.n_points) ? p.n_points[sidx] : (uint32_t)p.points_stride;
+    if (IN == 2 && p.tile_src_status && p.tile_src_status[sidx] != 0) n_pts = 0;  // failed source stream: no tiles
     if (n_pts > p.points_stride) {
       s.err = M3TSZ_ERR_INVALID_ARG;
       n_pts = 0;
@@ -735,6 +748,24 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   auto stage = [&](uint32_t tile) {
     const uint32_t row0 = tile * ENC_IN_T;
     if (row0 >= max_pts) return;
+    if (IN == 1) {
+      // point-major inputs: a row of the tile is 32 consecutive elements of the array -- every lane
+      // copies its own column (8 rows x 2 arrays), sources coalesced across the warp, no shuffles
+      const uint64_t *st = reinterpret_cast<const uint64_t *>(p.ts) + (uint64_t)row0 * p.n_series + sidx;
+      const uint64_t *sv = reinterpret_cast<const uint64_t *>(p.val) + (uint64_t)row0 * p.n_series + sidx;
+      const uint32_t d0 = enc_smem_addr(in_tiles + ((tile & 1u) * 2u) * ENC_IN_TILE_DWORDS + lane);
+      const uint32_t lim = (valid && s.err == 0) ? n_pts : 0u;
+#pragma unroll
+      for (int r = 0; r < ENC_IN_T; r++) {
+        if (row0 + (uint32_t)r < lim) {
+          enc_cp_async8(d0 + (uint32_t)(r * ENC_STRIDE) * 8u, st);
+          enc_cp_async8(d0 + (uint32_t)(ENC_IN_TILE_DWORDS + r * ENC_STRIDE) * 8u, sv);
+        }
+        st += p.n_series;
+        sv += p.n_series;
+      }
+      return;
+    }
     const uint64_t *src = (st_arr ? reinterpret_cast<const uint64_t *>(p.val)
                                   : reinterpret_cast<const uint64_t *>(p.ts)) +
                           (warp_s0 + st_jo) * p.points_stride + row0 + st_r;
@@ -756,20 +787,53 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
     }
   };
 
-  stage(0);
-  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  if (STAGED) {
+    stage(0);
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  // direct input stages: element `row` of this lane's series
+  auto load_row = [&](uint32_t row, int64_t &t_o, uint64_t &v_o, bool &skip_o) {
+    skip_o = false;
+    t_o = 0;
+    v_o = 0;
+    if (!valid || row >= n_pts) return;
+    const uint64_t o = (uint64_t)row * p.n_series + sidx;
+    if (IN == 2) {
+      const int64_t c = __ldg(p.tile_count + o);
+      skip_o = (c == 0);
+      t_o = p.tile_start + (int64_t)(row + 1) * p.tile_step;  // the window's end boundary
+      double v = 0.0;
+      switch (p.agg_type) {  // Gauge.ValueOf, gauge.go:144-165 (uniform switch)
+        case M3TSZ_AGG_LAST: v = __ldg(p.tile_last + o); break;
+        case M3TSZ_AGG_MIN: v = __ldg(p.tile_min + o); break;
+        case M3TSZ_AGG_MAX: v = __ldg(p.tile_max + o); break;
+        case M3TSZ_AGG_MEAN: v = c == 0 ? 0.0 : __ddiv_rn(__ldg(p.tile_sum + o), __ll2double_rn(c)); break;
+        case M3TSZ_AGG_COUNT: v = __ll2double_rn(c); break;
+        case M3TSZ_AGG_SUM: v = __ldg(p.tile_sum + o); break;
+        default: break;
+      }
+      v_o = (uint64_t)__double_as_longlong(v);
+    }
+  };
+  int64_t t_pf1 = 0;
+  uint64_t fb_pf1 = 0;
+  bool sk_pf = false, sk_pf1 = false;
 
   uint32_t iter = 0;
   int64_t t_pf = 0;
   uint64_t fb_pf = 0;
+  if (!STAGED) {  // two rows in flight
+    load_row(0, t_pf, fb_pf, sk_pf);
+    load_row(1, t_pf1, fb_pf1, sk_pf1);
+  }
   bool steady = false;  // same s/ms/us/ns unit as the batch's and not the first datapoint
   const uint64_t *in_next = in_tiles + lane;  // this lane's ts cell of the row to fetch next (value: + one tile)
   for (;;) {
     if (iter >= max_pts) break;  // warp-uniform (n_pts is 0 for lanes without a series)
-    const bool active = valid && s.err == 0 && iter < n_pts;
+    const bool active = valid && s.err == 0 && iter < n_pts && !(IN == 2 && sk_pf);
 
     // ---- input pipeline: request tile t+1, wait for tile t ----
-    if ((iter & (ENC_IN_T - 1)) == 0) {
+    if (STAGED && (iter & (ENC_IN_T - 1)) == 0) {
       __syncwarp();  // everyone is done reading the buffer about to be overwritten
       stage(iter / ENC_IN_T + 1);
       asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -847,10 +911,17 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
       // hides behind the previous bit packing); fetch the next row of the tile now
       const int64_t t = t_pf;
       const uint64_t fb = fb_pf;
-      if ((iter & (ENC_IN_T - 1)) != ENC_IN_T - 1) {
-        t_pf = (int64_t)in_next[0];
-        fb_pf = in_next[ENC_IN_TILE_DWORDS];
-        in_next += ENC_STRIDE;
+      if (STAGED) {
+        if ((iter & (ENC_IN_T - 1)) != ENC_IN_T - 1) {
+          t_pf = (int64_t)in_next[0];
+          fb_pf = in_next[ENC_IN_TILE_DWORDS];
+          in_next += ENC_STRIDE;
+        }
+      } else {  // rotate the two-deep prefetch; request row iter + 2
+        t_pf = t_pf1;
+        fb_pf = fb_pf1;
+        sk_pf = sk_pf1;
+        load_row(iter + 2, t_pf1, fb_pf1, sk_pf1);
       }
       const double v = __longlong_as_double((long long)fb);
       const bool room = s.words_out + s.k + (uint32_t)(ENC_GUARD + 4) <= slot_words;  // < 2^31 words
@@ -861,8 +932,11 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
       if (INT_OPT) hot = hot && s.is_float && fb != s.prev_bits && !maybe_int(v);
       Tier2 c2;
       if (__all_sync(FULL_MASK, hot || !active)) {
-        // every live lane: '0' (zero DoD) [+ '1' no-update] + XOR code, one merge
-        s.prev_time = t;
+        // every live lane: '0' (zero DoD) [+ '1' no-update] + XOR code, one merge.  The state update is
+        // unconditional where an inactive lane is a FINISHED lane (IN 0 / 1); with IN = 2 a lane may sit
+        // out one row (an empty window) and must keep its state.
+        const bool upd = (IN != 2) || active;
+        if (upd) s.prev_time = t;
         const uint32_t pre = INT_OPT ? 1u : 0u;  // '0' zero DoD [+ '1' no-update]
         const int pb = INT_OPT ? 2 : 1;
         const uint64_t x = s.prev_bits ^ fb;
@@ -878,9 +952,11 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
                                   : (cont ? ((pre << 2) | 2u)
                                           : ((pre << 14) | (3u << 12) | ((uint32_t)cl << 6) | (uint32_t)(nm - 1)));
         const int hb = pb + (zero ? 1 : (cont ? 2 : 14));
-        s.plz = cl;  // PrevXOR := x
-        s.ptz = ct;
-        s.prev_bits = fb;
+        if (upd) {
+          s.plz = cl;  // PrevXOR := x
+          s.ptz = ct;
+          s.prev_bits = fb;
+        }
         if (active) {
           emit_code_p(s, out_tile, lane, hdr, hb, P, plen);
           s.n_enc++;
@@ -917,7 +993,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
     }
     iter++;
   }
-  asm volatile("cp.async.wait_all;\n" ::: "memory");
+  if (STAGED) asm volatile("cp.async.wait_all;\n" ::: "memory");
 
   // ---- tail: end-of-stream marker + zero padding (scheme.go:198-211) ----
   uint64_t total_bits = 0;
@@ -943,6 +1019,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   }
   flush_out();
   const uint64_t my_len = (total_bits + 7) >> 3;
+  if (valid && IN == 2 && p.n_tiles_out) p.n_tiles_out[sidx] = s.n_enc;
   if (valid && p.out_bits) p.out_bits[sidx] = total_bits;  // incl. the end-of-stream marker, before padding
   if (valid && p.last_value) {
     // Encoder.LastEncoded().Value (encoder.go:305-319): the float when the encoder is in float
@@ -1022,14 +1099,19 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   }  // batch loop
 }
 
-template <bool INT_OPT, bool PACKED>
+template <int IN>
+constexpr size_t enc_block_smem() {
+  return ((IN == 0 || IN == 1) ? ENC_WARP_SMEM : (size_t)ENC_OUT_TILE_WORDS * 4) * ENC_WARPS;
+}
+
+template <bool INT_OPT, bool PACKED, int IN>
 static cudaError_t launch_encode_one(const EncodeParams &p, cudaStream_t stream) {
-  constexpr size_t smem = ENC_WARP_SMEM * ENC_WARPS;
+  constexpr size_t smem = enc_block_smem<IN>();
   const uint64_t per_block = (uint64_t)ENC_WARPS * 32ull;
   uint64_t blocks = (p.n_series + per_block - 1) / per_block;
   if (blocks == 0) return cudaSuccess;
   if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(encode_kernel<INT_OPT, PACKED>,
+  cudaError_t e = cudaFuncSetAttribute(encode_kernel<INT_OPT, PACKED, IN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (PACKED) {
@@ -1037,31 +1119,28 @@ static cudaError_t launch_encode_one(const EncodeParams &p, cudaStream_t stream)
     if (resident == 0) return cudaErrorInvalidValue;
     if (blocks > resident) blocks = resident;
   }
-  encode_kernel<INT_OPT, PACKED><<<(unsigned)blocks, ENC_WARPS * 32, smem, stream>>>(p);
+  encode_kernel<INT_OPT, PACKED, IN><<<(unsigned)blocks, ENC_WARPS * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
 // Persistent grid of the packed mode: resident blocks on the current device (also the number
 // of scratch slot sets: resident blocks x ENC_WARPS x 32 slots of out_stride bytes).
 uint64_t encode_packed_resident_blocks() {
-  constexpr size_t smem = ENC_WARP_SMEM * ENC_WARPS;
-  int dev = 0, sms = 0, per_sm = 0;
+  int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  if (cudaFuncSetAttribute(encode_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem) != cudaSuccess)
-    return 0;
-  if (cudaFuncSetAttribute(encode_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)smem) != cudaSuccess)
-    return 0;
-  int a = 0, b = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, encode_kernel<true, true>, ENC_WARPS * 32, smem) !=
-          cudaSuccess ||
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, encode_kernel<false, true>, ENC_WARPS * 32, smem) !=
-          cudaSuccess)
-    return 0;
-  per_sm = a > b ? a : b;
-  return (uint64_t)sms * (uint64_t)per_sm;
+  int best = 0;
+  auto probe = [&](auto kernel, size_t sm) {
+    int n = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, ENC_WARPS * 32, sm) == cudaSuccess && n > best)
+      best = n;
+  };
+  probe(encode_kernel<true, true, 0>, enc_block_smem<0>());
+  probe(encode_kernel<false, true, 0>, enc_block_smem<0>());
+  probe(encode_kernel<true, true, 2>, enc_block_smem<2>());
+  probe(encode_kernel<false, true, 2>, enc_block_smem<2>());
+  return (uint64_t)sms * (uint64_t)best;
 }
 uint64_t encode_packed_scratch_slots(uint64_t n_series) {
   const uint64_t per_block = (uint64_t)ENC_WARPS * 32ull;
@@ -1071,11 +1150,22 @@ uint64_t encode_packed_scratch_slots(uint64_t n_series) {
   return blocks * per_block;
 }
 
+// in_mode 0: series-major inputs; 1: point-major inputs (segments output only); 2: Gauge aggregates
+// (packed output only)
 cudaError_t launch_encode(const EncodeParams &p, bool int_optimized, cudaStream_t stream) {
-  if (p.packed) {
-    return int_optimized ? launch_encode_one<true, true>(p, stream) : launch_encode_one<false, true>(p, stream);
+  if (p.in_mode == 2) {
+    if (!p.packed) return cudaErrorInvalidValue;
+    return int_optimized ? launch_encode_one<true, true, 2>(p, stream) : launch_encode_one<false, true, 2>(p, stream);
   }
-  return int_optimized ? launch_encode_one<true, false>(p, stream) : launch_encode_one<false, false>(p, stream);
+  if (p.in_mode == 1) {
+    if (p.packed) return cudaErrorInvalidValue;
+    return int_optimized ? launch_encode_one<true, false, 1>(p, stream)
+                         : launch_encode_one<false, false, 1>(p, stream);
+  }
+  if (p.packed) {
+    return int_optimized ? launch_encode_one<true, true, 0>(p, stream) : launch_encode_one<false, true, 0>(p, stream);
+  }
+  return int_optimized ? launch_encode_one<true, false, 0>(p, stream) : launch_encode_one<false, false, 0>(p, stream);
 }
 
 // ---------------------------------------------------------------------------

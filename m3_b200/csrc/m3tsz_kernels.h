@@ -71,6 +71,14 @@ struct EncodeParams {
   unsigned long long *batch_counter;   // work counter (zero on entry)
   uint32_t align;
   uint64_t stagger_ns;  // start-up phase spread of the persistent warps (0 = none)
+  // input stage (see encode_kernel): 0 series-major ts/val, 1 point-major ts/val, 2 Gauge aggregates
+  int in_mode;
+  const double *tile_sum, *tile_min, *tile_max, *tile_last;  // window-major [points_stride][n_series]
+  const int64_t *tile_count;
+  const int32_t *tile_src_status;  // optional [n_series]
+  int64_t tile_start, tile_step;
+  int agg_type;
+  uint32_t *n_tiles_out;  // optional [n_series]
 };
 
 uint64_t encode_packed_resident_blocks();
@@ -128,21 +136,7 @@ struct PromParams {
 cudaError_t launch_prom(const PromParams &p, cudaStream_t stream);
 
 // tile aggregation glue (m3tsz_query.cu)
-struct TileParams {
-  const double *sum;  // window-major [n_windows][n_series]
-  const int64_t *count;
-  const double *mn, *mx, *last;
-  const int32_t *src_status;  // optional
-  uint64_t n_series;
-  uint32_t n_windows;
-  int64_t start, step;
-  int agg_type;
-  int64_t *ts_out;  // [n_series][n_windows]
-  double *val_out;
-  uint32_t *n_out;
-  int64_t *enc_start;  // [n_series] encoder start of the target block
-};
-cudaError_t launch_tiles_gather(const TileParams &p, cudaStream_t stream);
+cudaError_t launch_fill_i64(int64_t *dst, int64_t v, uint64_t n, cudaStream_t stream);
 cudaError_t launch_tiles_status(const int32_t *src_status, int32_t *status, uint64_t n, cudaStream_t stream);
 
 // exclusive scan of aligned lengths + gather into a packed buffer

@@ -5,11 +5,10 @@
 //    valueDecreaseTolerance, counter-reset cumulativeSum per resolution window), over the
 //    decoded / merged (ts, value) arrays that m3tsz_decode_batch / m3tsz_merge_series_batch
 //    leave in HBM -- the last per-datapoint host loop of a fetch.
-//  * Tile gather: turns the window-major Gauge aggregates of the fused decode+downsample
-//    kernel into per-series (window end, Gauge.ValueOf(type)) datapoints for the encoder
-//    (storage.TileAggregator, src/dbnode/storage/types.go:1444-1472;
-//    aggregation.Gauge.ValueOf, src/aggregator/aggregation/gauge.go:144-165;
-//    standardMetricTimestampNanos, src/aggregator/aggregator/list.go:541-543).
+//  * Tile aggregation glue (storage.TileAggregator, src/dbnode/storage/types.go:1444-1472): the
+//    fused decode+downsample kernel leaves window-major Gauge aggregates, the encoder's IN = 2 input
+//    stage (m3tsz_encode.cu) turns them into (window end, Gauge.ValueOf(type)) datapoints on the fly;
+//    only small helper kernels live here.
 #include "m3tsz_common.cuh"
 #include "m3tsz_kernels.h"
 
@@ -113,50 +112,16 @@ cudaError_t launch_prom(const PromParams &p, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------
-// Tile gather: window-major aggregates -> series-major datapoints for the encoder
+// Tile aggregation glue (the re-encode itself is the encoder's IN = 2 input stage, m3tsz_encode.cu)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double gauge_value_of(int type, double sum, int64_t count, double mn, double mx,
-                                                 double last) {  // gauge.go:144-165
-  switch (type) {
-    case M3TSZ_AGG_LAST: return last;
-    case M3TSZ_AGG_MIN: return mn;
-    case M3TSZ_AGG_MAX: return mx;
-    case M3TSZ_AGG_MEAN: return count == 0 ? 0.0 : __ddiv_rn(sum, __ll2double_rn(count));  // gauge.go:117-122
-    case M3TSZ_AGG_COUNT: return __ll2double_rn(count);
-    case M3TSZ_AGG_SUM: return sum;
-    default: return 0.0;
-  }
+__global__ void fill_i64_kernel(int64_t *dst, int64_t v, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
 }
-
-// One thread per series: reads of the window-major aggregates are coalesced across the
-// warp; the series-major writes of one thread fill whole sectors over consecutive windows.
-__global__ void tiles_gather_kernel(const TileParams p) {
-  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= p.n_series) return;
-  int64_t *to = p.ts_out + s * p.n_windows;
-  double *vo = p.val_out + s * p.n_windows;
-  uint32_t k = 0;
-  const bool failed = p.src_status && p.src_status[s] != 0;  // a stream that failed to decode yields no tile
-  if (!failed) {
-    for (uint32_t w = 0; w < p.n_windows; w++) {
-      const uint64_t o = (uint64_t)w * p.n_series + s;
-      const int64_t c = p.count[o];
-      if (c == 0) continue;  // empty windows produce nothing
-      to[k] = p.start + (int64_t)(w + 1) * p.step;  // the window's end boundary, list.go:541-543
-      vo[k] = gauge_value_of(p.agg_type, p.sum[o], c, p.mn[o], p.mx[o], p.last ? p.last[o] : 0.0);
-      k++;
-    }
-  }
-  p.n_out[s] = k;
-  p.enc_start[s] = p.start;
-}
-
-cudaError_t launch_tiles_gather(const TileParams &p, cudaStream_t stream) {
-  if (p.n_series == 0) return cudaSuccess;
-  const unsigned tb = 128;
-  const uint64_t blocks = (p.n_series + tb - 1) / tb;
-  if (blocks > 0x7fffffffull) return cudaErrorInvalidValue;
-  tiles_gather_kernel<<<(unsigned)blocks, tb, 0, stream>>>(p);
+cudaError_t launch_fill_i64(int64_t *dst, int64_t v, uint64_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const unsigned tb = 256;
+  fill_i64_kernel<<<(unsigned)((n + tb - 1) / tb), tb, 0, stream>>>(dst, v, n);
   return cudaGetLastError();
 }
 

@@ -211,6 +211,7 @@ int encoder_materialise(m3tsz_encoder *e) {
       CK(cudaMemcpyAsync(d_ab, e->ann_bytes.data(), e->ann_bytes.size(), cudaMemcpyHostToDevice, st));
   }
   m3tsz_encode_extras ex;
+  memset(&ex, 0, sizeof(ex));
   ex.d_last_value = (double *)d_last;
   ex.d_out_bits = (uint64_t *)d_bits;
   rc = m3tsz_encode_batch_ex(ctx, &e->opts, (const int64_t *)d_ts, (const double *)d_val, 1, n, nullptr,

@@ -639,3 +639,48 @@ def test_point_major_decode_equals_series_major(codecs, int_opt):
             k = min(int(n[s]), cap)
             assert (at[s, :k] == bt[s, :k]).all() and (av[s, :k] == bv[s, :k]).all(), (s, cap)
             assert (bt[s, k:] == -7).all(), (s, cap)  # rows past the series' end are untouched
+
+
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_point_major_encode_byte_identical(codecs, int_opt):
+    """extras.point_major_input: [point][series] inputs, same bytes as the series-major path and the oracle."""
+    rng = np.random.default_rng(19)
+    S, P = 517, 130
+    ts, vals, start = _mixed(rng, S, P)
+    n_points = rng.integers(0, P + 1, size=S).astype(np.int32)
+    n_points[::3] = P
+    codec = codecs[int_opt]
+    d_ts, d_vals = torch.from_numpy(ts).cuda(), torch.from_numpy(vals).cuda()
+    d_start = torch.full((S,), start, dtype=torch.int64, device="cuda")
+    d_n = torch.from_numpy(n_points).cuda()
+    a = codec.encode(d_ts, d_vals, d_start, unit=O.UNIT_S, n_points=d_n)
+    b = codec.encode(d_ts.t().contiguous(), d_vals.t().contiguous(), d_start, unit=O.UNIT_S, n_points=d_n,
+                     point_major=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a.status, b.status) and int((a.status != 0).sum()) == 0
+    assert torch.equal(a.out_len, b.out_len)
+    la, oa, ob = a.out_len.cpu().numpy(), a.out.cpu().numpy(), b.out.cpu().numpy()
+    for s in range(S):
+        assert (oa[s, : la[s]] == ob[s, : la[s]]).all(), s
+    for s in range(0, S, 17):
+        exp = O.encode_series(ts[s, : n_points[s]], vals[s, : n_points[s]], start, O.UNIT_S, int_opt) \
+            if n_points[s] else b""
+        assert ob[s, : la[s]].tobytes() == exp, s
+    # decode(point-major) -> encode(point-major): the device-resident round trip in one layout
+    stride = a.out.shape[1]
+    off = torch.arange(S, dtype=torch.int64, device="cuda") * stride
+    dec = codec.decode(a.out.view(-1), off, P, lengths=a.out_len, point_major=True)
+    c = codec.encode(dec.ts, dec.values, d_start, unit=O.UNIT_S, n_points=dec.n_points, point_major=True)
+    torch.cuda.synchronize()
+    assert int((c.status != 0).sum()) == 0
+    oc, lc = c.out.cpu().numpy(), c.out_len.cpu().numpy()
+    # re-encoding decoded values is byte-identical where decode is lossless (always in float mode; in
+    # int mode whenever the values were exactly representable -- compare against the oracle re-encode)
+    for s in range(0, S, 13):
+        k = int(n_points[s])
+        if not k:
+            assert lc[s] == 0
+            continue
+        dps, err = O.decode_all(oa[s, : la[s]].tobytes(), int_opt)
+        exp = O.encode_series([d[0] for d in dps], [d[1] for d in dps], start, O.UNIT_S, int_opt)
+        assert oc[s, : lc[s]].tobytes() == exp, s
