@@ -181,8 +181,8 @@ def make_config(S, P, int_opt, bytes_per_dp=7.3):
     return {"workload": "batch of %d series x %d points per GPU (the north-star target shape "
                         "1M x 1440 = configs[2-4] size; configs[4] = 8M over 8 GPUs), Gaussian "
                         "random walk (x0=100, N(0,1) steps), 60 s cadence, unit=Second; step = "
-                        "encode (series-major inputs -> per-series segments) + decode (-> point-major "
-                        "[point][series] outputs)" % (S, P),
+                        "encode (per-series segments) + decode, datapoints resident point-major "
+                        "([point][series])" % (S, P),
             "series_per_gpu": S, "points": P, "int_optimized": bool(int_opt),
             "l2": "inputs %.2f GB and outputs %.2f GB per step >> 126 MB L2, no flush needed"
                   % (S * P * 16 / 1e9, S * P * (16 + bytes_per_dp) / 1e9),
@@ -601,10 +601,10 @@ def run_ours(args):
                        status=torch.empty(S, dtype=torch.int32, device=dev))
     seg_off = torch.arange(S, dtype=torch.int64, device=dev) * stride
     seg_flat = enc.out.view(-1)
-    # Encode reads series-major inputs (datapoints arrive per series on the write path); decode writes
-    # POINT-major outputs ([point][series], step-major: what the query engine's step iterators consume,
-    # and every decode step of a warp then stores 32 consecutive elements).  The other combinations
-    # (series-major decode, point-major encode) are timed next to it below.
+    # The device-resident batch is kept POINT-major ([point][series], step-major): what the query
+    # engine's step iterators consume, and every encode / decode step of a warp then touches 32
+    # consecutive elements.  Series-major in and out (the layout of the *_host entry points and of
+    # round 1) is timed next to it below.
     ts_pm, vals_pm = ts.t().contiguous(), vals.t().contiguous()
     dec_pm = DecodeResult(ts=torch.empty((P, S), dtype=torch.int64, device=dev),
                           values=torch.empty((P, S), dtype=torch.float64, device=dev),
@@ -616,7 +616,7 @@ def run_ours(args):
     dec_events = []
 
     def encode():
-        codec.encode(ts, vals, start, unit=1, out=enc)
+        codec.encode(ts_pm, vals_pm, start, unit=1, out=enc, point_major=True)
 
     def decode():
         codec.decode(seg_flat, seg_off, P, out=dec_pm, lengths=enc.out_len, point_major=True)
@@ -686,8 +686,8 @@ def run_ours(args):
         return a.elapsed_time(b) / n
 
     enc_ms = time_fn(encode)
-    # the other layouts: point-major encode inputs, series-major decode outputs (round 1's layout)
-    enc_pm_ms = time_fn(lambda: codec.encode(ts_pm, vals_pm, start, unit=1, out=enc, point_major=True))
+    # series-major inputs and outputs (round 1's layout)
+    enc_sm_ms = time_fn(lambda: codec.encode(ts, vals, start, unit=1, out=enc))
     assert int(enc.out_len.sum().item()) == compressed_bytes
     dec_sm_ms = time_fn(lambda: codec.decode(seg_flat, seg_off, P, out=dec, lengths=enc.out_len))
     assert torch.equal(dec.ts, ts)
@@ -767,6 +767,18 @@ def run_ours(args):
         side["series_merge"] = {"replicas": 3, "series": Sm // 3, "ms": merge_ms,
                                 "input_dps": Sm * P / (merge_ms * 1e-3),
                                 "algorithmic_gbs": (Sm * P * 16 + (Sm // 3) * P * 16) / (merge_ms * 1e-3) / 1e9}
+        # the same merge over point-major arrays (what decode writes in the timed step)
+        pm_ts, pm_v = dec.ts[:Sm].t().contiguous(), dec.values[:Sm].t().contiguous()
+        mgp = lambda: codec.merge_series(pm_ts, pm_v, dec.n_points[:Sm], dec.status[:Sm], m_slice, m_rep, m_ser, P,
+                                         point_major=True)
+        m_out = mgp()
+        assert int((m_out[3] != 0).sum()) == 0 and bool((m_out[2] == P).all())
+        del m_out
+        mergep_ms = time_fn(mgp, n=3)
+        side["series_merge"].update({"point_major_ms": mergep_ms, "point_major_input_dps": Sm * P / (mergep_ms * 1e-3),
+                                     "point_major_algorithmic_gbs": (Sm * P * 16 + (Sm // 3) * P * 16) /
+                                     (mergep_ms * 1e-3) / 1e9})
+        del pm_ts, pm_v
         # Prometheus epilogue (row N4) over the decoded batch: ns -> ms, plain and counter-normalised
         Sp = min(S, 300_000)
         pr = lambda: codec.prom_convert(dec.ts[:Sp], dec.values[:Sp], dec.n_points[:Sp])
@@ -832,11 +844,9 @@ def run_ours(args):
         "compressed_bytes_per_dp": compressed_bytes / (S * P),
         "encode_dps": S * P / (enc_ms * 1e-3), "decode_dps": S * P / (dec_ms_max * 1e-3),
         "encode_ms": enc_ms, "decode_ms": dec_ms_max,
-        "other_layouts": {"decode_series_major_ms": dec_sm_ms,
-                          "decode_series_major_frac_of_hbm": alg_bytes / (dec_sm_ms * 1e-3) / 1e9 / peak,
-                          "step_series_major_ms": enc_ms + dec_sm_ms, "encode_point_major_ms": enc_pm_ms,
-                          "note": "series-major decode outputs ([series][point], round 1's layout); encode from "
-                                  "point-major inputs (direct coalesced loads, currently latency-bound)"},
+        "series_major": {"encode_ms": enc_sm_ms, "decode_ms": dec_sm_ms, "step_ms": enc_sm_ms + dec_sm_ms,
+                         "decode_frac_of_hbm": alg_bytes / (dec_sm_ms * 1e-3) / 1e9 / peak,
+                         "note": "the same step with series-major ([series][point]) inputs and outputs"},
         "encode_packed": {"ms": encp_ms, "dps": S * P / (encp_ms * 1e-3), "decode_from_packed_ms": decp_ms,
                           "step_packed_ms": encp_ms + decp_ms,
                           "note": "encode with one packed output buffer (m3tsz_encode_batch_packed) + decode of it"},

@@ -574,6 +574,19 @@ int m3tsz_allgather_decoded(m3tsz_ctx *ctx, const m3tsz_options *opts, void *ncc
                             uint64_t max_points, uint64_t chunk_series, int64_t *d_ts_all, double *d_val_all,
                             uint32_t *d_n_points_all, int32_t *d_status_all, void *stream);
 
+/* m3tsz_merge_series_batch with POINT-major arrays: point_major_in: d_ts / d_val are
+ * [cap][n_seq] (datapoint i of sequence q at i * n_seq + q, what m3tsz_decode_batch_ex writes with
+ * extras.point_major); point_major_out: outputs are [out_cap][n_series].  With replicas that
+ * advance in step (the normal RF = 3 fetch) the threads of a warp then read and write
+ * consecutive elements. */
+int m3tsz_merge_series_batch_ex(m3tsz_ctx *ctx, const int64_t *d_ts, const double *d_val, uint64_t cap,
+                                const uint32_t *d_n_points, const int32_t *d_seq_status,
+                                const uint64_t *d_slice_off, const uint64_t *d_replica_off,
+                                const uint64_t *d_series_off, uint64_t n_series, int64_t start_ns,
+                                int64_t end_ns, int32_t strategy, int64_t *d_ts_out, double *d_val_out,
+                                uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, uint64_t n_seq,
+                                int32_t point_major_in, int32_t point_major_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

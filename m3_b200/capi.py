@@ -81,7 +81,7 @@ EXPORTED_SYMBOLS = [
     "m3tsz_decode_downsample_batch_host", "m3tsz_merge_series_batch", "m3tsz_checksum_batch",
     "m3tsz_decode_batch_ex", "m3tsz_decode_downsample_last_batch", "m3tsz_encode_bound_units",
     "m3tsz_encode_batch_packed", "m3tsz_prom_convert_batch", "m3tsz_aggregate_tiles_batch",
-    "m3tsz_encode_batch_ex", "m3tsz_fetch_batch_host", "m3tsz_nccl_unique_id", "m3tsz_nccl_comm_create",
+    "m3tsz_encode_batch_ex", "m3tsz_fetch_batch_host", "m3tsz_merge_series_batch_ex", "m3tsz_nccl_unique_id", "m3tsz_nccl_comm_create",
     "m3tsz_nccl_comm_destroy", "m3tsz_allgather_decoded",
     "m3tsz_encoder_create", "m3tsz_encoder_destroy", "m3tsz_encoder_reset", "m3tsz_encoder_encode",
     "m3tsz_encoder_num_encoded", "m3tsz_encoder_failed_dod", "m3tsz_encoder_last_encoded", "m3tsz_encoder_last_annotation_checksum",
@@ -224,6 +224,9 @@ def lib():
     L.m3tsz_merge_series_batch.restype = C.c_int
     L.m3tsz_merge_series_batch.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp, u64, i64, i64, i32, vp, vp,
                                            u64, vp, vp, vp]
+    L.m3tsz_merge_series_batch_ex.restype = C.c_int
+    L.m3tsz_merge_series_batch_ex.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, vp, u64, i64, i64, i32, vp, vp,
+                                              u64, vp, vp, u64, i32, i32, vp]
     L.m3tsz_checksum_batch.restype = C.c_int
     L.m3tsz_checksum_batch.argtypes = [vp, vp, u64, vp, vp, u64, vp, vp, vp, vp]
     _lib = L

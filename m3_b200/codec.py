@@ -260,22 +260,24 @@ class BatchCodec:
 
     # ------------------------------------------------------------------ merge (row N1)
     def merge_series(self, ts, values, n_points, seq_status, slice_off, replica_off, series_off,
-                     out_cap, start_ns=0, end_ns=0, strategy=0):
+                     out_cap, start_ns=0, end_ns=0, strategy=0, point_major=False):
         """seriesIterator / multiReaderIterator semantics over decoded streams (device tensors;
-        offsets int64).  Returns (ts_out [S,out_cap], val_out, n_out int32 [S], status int32 [S])."""
+        offsets int64).  Returns (ts_out [S,out_cap], val_out, n_out int32 [S], status int32 [S]);
+        point_major: inputs are [cap, n_seq] and outputs [out_cap, S] (step-major)."""
         S = series_off.numel() - 1
         dev = self.device
-        ts_out = torch.empty((S, out_cap), dtype=torch.int64, device=dev)
-        val_out = torch.empty((S, out_cap), dtype=torch.float64, device=dev)
+        shape = (out_cap, S) if point_major else (S, out_cap)
+        ts_out = torch.empty(shape, dtype=torch.int64, device=dev)
+        val_out = torch.empty(shape, dtype=torch.float64, device=dev)
         n_out = torch.empty(S, dtype=torch.int32, device=dev)
         status = torch.empty(S, dtype=torch.int32, device=dev)
-        cap = ts.shape[1]
-        rc = capi.lib().m3tsz_merge_series_batch(
+        cap, n_seq = (ts.shape[0], ts.shape[1]) if point_major else (ts.shape[1], ts.shape[0])
+        rc = capi.lib().m3tsz_merge_series_batch_ex(
             self.ctx.handle, _ptr(ts), _ptr(values), cap, _ptr(n_points), _ptr(seq_status),
             _ptr(slice_off), _ptr(replica_off), _ptr(series_off), S, int(start_ns), int(end_ns),
-            int(strategy), _ptr(ts_out), _ptr(val_out), out_cap, _ptr(n_out), _ptr(status),
-            _cuda_stream_ptr(dev))
-        self.ctx.check(rc, "m3tsz_merge_series_batch")
+            int(strategy), _ptr(ts_out), _ptr(val_out), out_cap, _ptr(n_out), _ptr(status), n_seq,
+            1 if point_major else 0, 1 if point_major else 0, _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_merge_series_batch_ex")
         return ts_out, val_out, n_out, status
 
     # ------------------------------------------------------------ query-side consumers (rows N3, N4)

@@ -505,12 +505,13 @@ int m3tsz_aggregate_tiles_batch(m3tsz_ctx *ctx, const m3tsz_options *opts, const
   return M3TSZ_OK;
 }
 
-int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *d_val, uint64_t cap,
-                             const uint32_t *d_n_points, const int32_t *d_seq_status,
-                             const uint64_t *d_slice_off, const uint64_t *d_replica_off,
-                             const uint64_t *d_series_off, uint64_t n_series, int64_t start_ns,
-                             int64_t end_ns, int32_t strategy, int64_t *d_ts_out, double *d_val_out,
-                             uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, void *stream) {
+int m3tsz_merge_series_batch_ex(m3tsz_ctx *ctx, const int64_t *d_ts, const double *d_val, uint64_t cap,
+                                const uint32_t *d_n_points, const int32_t *d_seq_status,
+                                const uint64_t *d_slice_off, const uint64_t *d_replica_off,
+                                const uint64_t *d_series_off, uint64_t n_series, int64_t start_ns,
+                                int64_t end_ns, int32_t strategy, int64_t *d_ts_out, double *d_val_out,
+                                uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, uint64_t n_seq,
+                                int32_t point_major_in, int32_t point_major_out, void *stream) {
   if (!ctx) return M3TSZ_ERR_INVALID_ARG;
   if (n_series == 0) return M3TSZ_OK;
   if (!d_ts || !d_val || !d_n_points || !d_slice_off || !d_replica_off || !d_series_off || !d_ts_out ||
@@ -538,9 +539,25 @@ int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *
   p.out_cap = out_cap;
   p.n_out = d_n_out;
   p.status = d_status;
+  if (point_major_in && n_seq == 0) return M3TSZ_ERR_INVALID_ARG;
+  p.in_seq_stride = point_major_in ? 1 : cap;
+  p.in_pt_stride = point_major_in ? n_seq : 1;
+  p.out_seq_stride = point_major_out ? 1 : out_cap;
+  p.out_pt_stride = point_major_out ? n_series : 1;
   CK(launch_merge(p, (cudaStream_t)stream));
   ctx->launches++;
   return M3TSZ_OK;
+}
+
+int m3tsz_merge_series_batch(m3tsz_ctx *ctx, const int64_t *d_ts, const double *d_val, uint64_t cap,
+                             const uint32_t *d_n_points, const int32_t *d_seq_status,
+                             const uint64_t *d_slice_off, const uint64_t *d_replica_off,
+                             const uint64_t *d_series_off, uint64_t n_series, int64_t start_ns,
+                             int64_t end_ns, int32_t strategy, int64_t *d_ts_out, double *d_val_out,
+                             uint64_t out_cap, uint32_t *d_n_out, int32_t *d_status, void *stream) {
+  return m3tsz_merge_series_batch_ex(ctx, d_ts, d_val, cap, d_n_points, d_seq_status, d_slice_off, d_replica_off,
+                                     d_series_off, n_series, start_ns, end_ns, strategy, d_ts_out, d_val_out,
+                                     out_cap, d_n_out, d_status, 0, 0, 0, stream);
 }
 
 int m3tsz_checksum_batch(m3tsz_ctx *ctx, const uint8_t *d_streams, uint64_t streams_bytes,

@@ -53,6 +53,15 @@ constexpr int DEC_FAST_WORDS = 4; // the fast path reads 4 consecutive words
 constexpr int DEC_QUADS = DEC_RING / 4;  // + 1 mirror quad (copy of quad 0) so quad q+1 is always at +1
 constexpr int DEC_IN_TILE_WORDS = (DEC_QUADS + 1) * 32 * 4;
 static_assert(M3_DEC_CHK == DEC_GROUP, "ring bookkeeping runs once per output group");
+// The kernels without register-resident output groups (point-major decode, fused downsample) may
+// run the ring bookkeeping / group pre-check every CHK_WIDE datapoints; the refill trigger then has
+// to leave CHK_WIDE * 80 bits + the window landed after a group: TRIGGER_WIDE.
+#ifndef M3_DEC_CHK_WIDE
+#define M3_DEC_CHK_WIDE 4
+#endif
+#ifndef M3_DEC_TRIGGER_WIDE
+#define M3_DEC_TRIGGER_WIDE 24
+#endif
 constexpr size_t DEC_WARP_SMEM_PLAIN = (size_t)DEC_IN_TILE_WORDS * 4;
 static_assert(DEC_WARP_SMEM_PLAIN % 16 == 0, "every warp's ring must stay 16-byte aligned");
 
@@ -495,6 +504,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
   // 1: fused downsample (sum, count, min, max); 2: + last / lastAt
   constexpr bool DS = (MODE == 1 || MODE == 2), LAST = (MODE == 2), PLAIN = (MODE == 0 || MODE == 3),
                  PM = (MODE == 3);
+  constexpr int CHK = (MODE == 0) ? M3_DEC_CHK : M3_DEC_CHK_WIDE;
+  constexpr int TRIGGER = (MODE == 0) ? DEC_TRIGGER : M3_DEC_TRIGGER_WIDE;
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -651,7 +662,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
       const bool active = live;
       const uint32_t cw = s.pos >> 5;
       int avail = (int)(filled - cw);
-      if (__any_sync(FULL_MASK, active && (avail <= DEC_TRIGGER ||
+      if (__any_sync(FULL_MASK, active && (avail <= TRIGGER ||
                                            ((int)(safe - cw) < M3_DEC_SAFE_MIN && filled > safe)))) {
         cp_async_wait_all();
         __syncwarp();
@@ -664,10 +675,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
         for (int rep = 0; rep < 3; rep++) {
           // first pass: everyone with room tops up when someone is at the trigger level;
           // later passes only serve lanes that are still short (start-up / restart)
-          const bool trig = __any_sync(FULL_MASK, active && avail <= DEC_TRIGGER);
+          const bool trig = __any_sync(FULL_MASK, active && avail <= TRIGGER);
           if (!trig) break;
           const uint32_t fmask =
-              __ballot_sync(FULL_MASK, active && avail <= (rep == 0 ? DEC_ACCEPT : DEC_TRIGGER));
+              __ballot_sync(FULL_MASK, active && avail <= (rep == 0 ? DEC_ACCEPT : TRIGGER));
           if (!fmask) break;
           ring_fill(ring_lane_addr, p.streams, p.streams_bytes, (fmask >> lane) & 1u, gbase + filled,
                     (filled >> 2) & (DEC_QUADS - 1));
@@ -689,8 +700,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
     // landed, distance to the end of the stream, not the first datapoint and no
     // wrap of prev_time to 0 (first <=> PrevTime == 0, timestamp_iterator.go:89),
     // float mode.
-    bool pre_ok = fast_en && (((s.pos + 80u * (M3_DEC_CHK - 1)) >> 5) + DEC_FAST_WORDS <= safe) &&
-                  (s.pos + 80u * M3_DEC_CHK <= s.end) && (s.prev_time > 0) &&
+    bool pre_ok = fast_en && (((s.pos + 80u * (CHK - 1)) >> 5) + DEC_FAST_WORDS <= safe) &&
+                  (s.pos + 80u * CHK <= s.end) && (s.prev_time > 0) &&
                   ((uint64_t)s.prev_delta < (1ull << 60)) && (!INT_OPT || s.is_float);
     if (DS) {
       // fused downsample, additionally: timestamps strictly increasing in steps of at most one
@@ -702,11 +713,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
       // (a finished lane keeps d < 0 and delta == 0: the hot path's advance test needs no `active`)
       acc.d = live ? (int64_t)((uint64_t)s.prev_time - (uint64_t)acc.w_end) : -1ll;
       pre_ok = pre_ok && acc.in_open && acc.cur_w == acc.hi_w && s.prev_delta > 0 && s.prev_delta <= p.window &&
-               (uint32_t)acc.cur_w + (uint32_t)M3_DEC_CHK < p.n_windows;
+               (uint32_t)acc.cur_w + (uint32_t)CHK < p.n_windows;
     }
 
 #pragma unroll
-    for (int rr = 0; rr < M3_DEC_CHK; rr++) {
+    for (int rr = 0; rr < CHK; rr++) {
       const bool active = live;
       const uint32_t cw = s.pos >> 5;
       int64_t t = 0;
@@ -1071,7 +1082,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
       dt += DEC_GROUP;
       dv += DEC_GROUP;
     }
-    group_row0 += DEC_GROUP;
+    group_row0 += CHK;
   }
   cp_async_wait_all();
 

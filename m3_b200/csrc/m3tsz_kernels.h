@@ -101,6 +101,8 @@ struct MergeParams {
   uint64_t out_cap;
   uint32_t *n_out;
   int32_t *status;
+  // element strides: series-major [seq][cap] = (cap, 1); point-major [cap][n_seq] = (1, n_seq)
+  uint64_t in_seq_stride, in_pt_stride, out_seq_stride, out_pt_stride;
 };
 cudaError_t launch_merge(const MergeParams &p, cudaStream_t stream);
 

@@ -207,7 +207,7 @@ struct ReaderSet {  // member set of an Mri: its current slice's readers
       v = 0.0;
       return;
     }
-    const uint64_t o = c.q * p.cap + (uint64_t)(c.idx < 0 ? 0 : c.idx);
+    const uint64_t o = c.q * p.in_seq_stride + (uint64_t)(c.idx < 0 ? 0 : c.idx) * p.in_pt_stride;
     t = p.ts[o];
     v = p.val[o];
   }
@@ -325,7 +325,7 @@ __device__ __forceinline__ bool fast_advance(FastState<R> &st, const MergeParams
     int64_t tn = 0;
     if (st.idx[r] + 1 < st.n[r]) {
       st.idx[r]++;
-      tn = p.ts[st.base[r] + (uint64_t)st.idx[r]];
+      tn = p.ts[st.base[r] + (uint64_t)st.idx[r] * p.in_pt_stride];
       got = true;
     } else {
       while (st.slice_cur[r] < st.slice_end[r]) {
@@ -339,7 +339,7 @@ __device__ __forceinline__ bool fast_advance(FastState<R> &st, const MergeParams
         const uint32_t np = p.n_points[q0];
         const int32_t n = (int32_t)(np < p.cap ? np : p.cap);
         if (n == 0) continue;
-        st.base[r] = q0 * p.cap;
+        st.base[r] = q0 * p.in_seq_stride;
         st.idx[r] = 0;
         st.n[r] = n;
         tn = p.ts[st.base[r]];
@@ -385,8 +385,8 @@ __device__ void merge_fast(const MergeParams &p, uint64_t s, uint64_t rep0) {
       nv++;
     }
   }
-  int64_t *ts_out = p.ts_out + s * p.out_cap;
-  double *val_out = p.val_out + s * p.out_cap;
+  int64_t *ts_out = p.ts_out + s * p.out_seq_stride;
+  double *val_out = p.val_out + s * p.out_seq_stride;
   uint32_t n_out = 0;
   while (nv > 0 && !st.bail) {
     // earliest timestamp and its members in position order; the value of the last one
@@ -407,13 +407,13 @@ __device__ void merge_fast(const MergeParams &p, uint64_t s, uint64_t rep0) {
         if ((uint32_t)r == id && st.t[r] == tmin) {
           e_ids |= id << (4 * ne);
           ne++;
-          win_addr = st.base[r] + (uint64_t)st.idx[r];
+          win_addr = st.base[r] + (uint64_t)st.idx[r] * p.in_pt_stride;
         }
       }
     }
     if (n_out < p.out_cap) {
-      ts_out[n_out] = tmin;
-      val_out[n_out] = p.val[win_addr];
+      ts_out[(uint64_t)n_out * p.out_pt_stride] = tmin;
+      val_out[(uint64_t)n_out * p.out_pt_stride] = p.val[win_addr];
     }
     n_out++;
     // advance the earliest members in list order; an exhausted member's place in
@@ -494,8 +494,8 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeParams p, bool re
       if (m.err) err = m.err;
     }
   }
-  int64_t *ts_out = p.ts_out + s * p.out_cap;
-  double *val_out = p.val_out + s * p.out_cap;
+  int64_t *ts_out = p.ts_out + s * p.out_seq_stride;
+  double *val_out = p.val_out + s * p.out_seq_stride;
   bool first_next = true;
   for (;;) {  // seriesIterator.Next :74-83
     if (!first_next) {
@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(128) merge_kernel(const MergeParams p, bool re
     double v;
     iters_current(top, p.strategy, set, t, v);
     if (n_out < p.out_cap) {
-      ts_out[n_out] = t;
-      val_out[n_out] = v;
+      ts_out[(uint64_t)n_out * p.out_pt_stride] = t;
+      val_out[(uint64_t)n_out * p.out_pt_stride] = v;
     }
     n_out++;
   }

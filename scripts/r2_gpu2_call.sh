@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_round2.py -q -m gpu -k "point_major or tiles or downsample" 2>&1 | tail -5) > gpurun_out/r2k_tests.log 2>&1
-(timeout 300 python scripts/r2_quick.py 1000000 1) > gpurun_out/r2k_quick_base.log 2>&1
-for v in w8 w8b; do (M3TSZ_B200_LIB=$PWD/m3_b200/variants/$v.so timeout 300 python scripts/r2_quick.py 1000000 1) > gpurun_out/r2k_quick_$v.log 2>&1; done
-(timeout 300 python - <<'PY'
+nvidia-smi -L > gpurun_out/r2j_gpus.txt
+(timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_round2.py -q -m gpu -k "allgather or point_major" 2>&1 | tail -15) > gpurun_out/r2j_tests.log 2>&1
+(timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3) > gpurun_out/r2j_bench_2gpu.json 2> gpurun_out/r2j_bench_2gpu.err
+(timeout 300 python scripts/prof_r2.py enc_pm 2>&1; timeout 200 python - <<'PY'
 import sys, os, torch
 sys.path.insert(0, os.getcwd())
 from m3_b200 import synth
@@ -24,8 +24,7 @@ def t(fn, n=5):
 print("encode series-major %.3f ms, point-major %.3f ms, same=%s" % (
     t(lambda: codec.encode(ts, vals, start, unit=1, out=o1)),
     t(lambda: codec.encode(a, b, start, unit=1, out=o2, point_major=True)),
-    torch.equal(o1.out_len, o2.out_len) and torch.equal(o1.out, o2.out)))
+    torch.equal(o1.out_len, o2.out_len)))
 PY
-) > gpurun_out/r2k_enc_pm.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:merge_fast_kernel -s 2 -c 1 -o gpurun_out/r2k_merge python scripts/prof_merge.py > gpurun_out/r2k_prof_merge.log 2>&1
-tail -4 gpurun_out/r2k_tests.log; tail -2 gpurun_out/r2k_enc_pm.log; for f in gpurun_out/r2k_quick_*.log; do echo "== $f"; grep -E "decode|dec\+ds" $f; done
+) > gpurun_out/r2j_enc_pm.log 2>&1
+tail -8 gpurun_out/r2j_tests.log; tail -3 gpurun_out/r2j_enc_pm.log; tail -c 2500 gpurun_out/r2j_bench_2gpu.json; tail -5 gpurun_out/r2j_bench_2gpu.err

@@ -27,7 +27,18 @@ def gpu_merge(codec, series, start=0, end=0, strategy=0, out_cap=None):
     r = codec.merge_series(d(ts, np.int64), d(val, np.float64), d(npts.astype(np.int32), np.int32),
                            d(st, np.int32), d(slice_off, np.int64), d(replica_off, np.int64),
                            d(series_off, np.int64), out_cap, start, end, strategy)
+    # the same merge over POINT-major arrays ([cap][n_seq] in, [out_cap][n_series] out) must agree
+    rp = codec.merge_series(d(ts.T, np.int64), d(val.T, np.float64), d(npts.astype(np.int32), np.int32),
+                            d(st, np.int32), d(slice_off, np.int64), d(replica_off, np.int64),
+                            d(series_off, np.int64), out_cap, start, end, strategy, point_major=True)
     torch.cuda.synchronize()
+    assert torch.equal(r[2], rp[2]) and torch.equal(r[3], rp[3])
+    n_host = r[2].cpu().numpy().view(np.uint32)
+    a_ts, a_v = r[0].cpu().numpy(), r[1].cpu().numpy().view(np.uint64)
+    b_ts, b_v = rp[0].cpu().numpy().T, rp[1].cpu().numpy().view(np.uint64).T
+    for i in range(len(n_host)):
+        k = min(int(n_host[i]), out_cap)
+        assert (a_ts[i, :k] == b_ts[i, :k]).all() and (a_v[i, :k] == b_v[i, :k]).all(), ("point-major", i)
     ts_o, val_o, n_o, st_o = [x.cpu().numpy() for x in r]
     exp = O.series_merge_batch(ts, val, npts, st, slice_off, replica_off, series_off, start=start, end=end,
                                strategy=strategy, out_cap=out_cap)
