@@ -798,7 +798,10 @@ def run_ours(args):
     allgather = None
     if world > 1 and extras:
         from m3_b200.sharded import fetch_allgather_decoded
-        allgather = fetch_allgather_decoded(codec, pk, P, dist, dev, barrier)
+        try:
+            allgather = fetch_allgather_decoded(codec, pk, P, dist, dev, barrier)
+        except Exception as e:  # a side measurement must not take the headline down with it
+            allgather = {"error": "%s: %s" % (type(e).__name__, e)}
 
     # ---- e2e: the same batch through the *_host C ABI with pinned host buffers ----
     e2e = fetch = None

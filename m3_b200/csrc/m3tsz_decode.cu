@@ -33,6 +33,9 @@ namespace m3tsz {
 #ifndef M3_DEC_MIN_BLOCKS
 #define M3_DEC_MIN_BLOCKS 4  // 4 x 4 warps with ~110 registers beat 5 blocks squeezed into 96 (profiles/r02_decode_history.md)
 #endif
+#ifndef M3_DS_MERGED_VOTE
+#define M3_DS_MERGED_VOTE 0  // bit 0: MODE 1, bit 1: MODE 2 take the merged hot/advance vote (see the hot path)
+#endif
 #ifndef M3_DEC_MIN_BLOCKS_DS
 #define M3_DEC_MIN_BLOCKS_DS 5  // fused-downsample kernels: 5 x 4 warps at 96 registers (7.94 vs 8.25 ms at 4 blocks)
 #endif
@@ -489,7 +492,8 @@ struct DsAcc {
   // mn == +inf && mx == -inf, written out as NaN / NaN
   double sum, mn, mx;
   uint32_t cnt;      // datapoints in the open window (NaNs counted, gauge.go:85)
-  uint32_t cnt_gen;  // cnt as of the last general-path visit (cnt != cnt_gen: hot datapoints since)
+  uint32_t n_sync;   // s.n when cnt was last brought up to date: s.n - n_sync = hot datapoints since (all of
+                     // them in the open window), folded into cnt at the next commit / general-path visit
   int64_t last_t;    // MODE 2: lastAt / last (gauge.go:74-81)
   uint64_t last_v;
 };
@@ -502,6 +506,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
   // MODE 0: plain decode, series-major output [series][point]; 3: plain decode, point-major output
   // [point][series] (every step's 32 lanes store 32 consecutive elements: coalesced 256-byte rows);
   // 1: fused downsample (sum, count, min, max); 2: + last / lastAt
+  constexpr bool MERGED = (MODE == 1 && (M3_DS_MERGED_VOTE & 1)) || (MODE == 2 && (M3_DS_MERGED_VOTE & 2));
   constexpr bool DS = (MODE == 1 || MODE == 2), LAST = (MODE == 2), PLAIN = (MODE == 0 || MODE == 3),
                  PM = (MODE == 3);
   constexpr int CHK = (MODE == 0) ? M3_DEC_CHK : M3_DEC_CHK_WIDE;
@@ -579,7 +584,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
   acc.mn = __longlong_as_double(0x7ff0000000000000ll);
   acc.mx = __longlong_as_double((long long)0xfff0000000000000ull);
   acc.cnt = 0;
-  acc.cnt_gen = 0;
+  acc.n_sync = 0;
   acc.last_t = 0;
   acc.last_v = 0;
   const int64_t range_end = p.range_start + (int64_t)p.n_windows * p.window;
@@ -614,14 +619,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
   auto ds_reset = [&]() {
     acc.sum = 0.0;
     acc.cnt = 0;
-    acc.cnt_gen = 0;
     acc.mn = kPosInf;
     acc.mx = kNegInf;
   };
-  auto ds_add = [&](uint64_t vbits) {  // Gauge.updateTotals without `last` (gauge.go:85-101)
+  auto ds_add = [&](uint64_t vbits) {  // Gauge.updateTotals without `last` and `count` (gauge.go:85-101)
     const double dv = __longlong_as_double((long long)vbits);
-    acc.cnt++;
-    if (dv == dv) acc.sum = __dadd_rn(acc.sum, dv);
+    // sum += v unless v is NaN: one compare + one predicated add
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %1, %1;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc.sum) : "d"(dv));
     if (dv > acc.mx) acc.mx = dv;
     if (dv < acc.mn) acc.mn = dv;
   };
@@ -765,7 +769,24 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
         }
         const uint64_t field = M3_FIELD64(c);
         c += (uint32_t)n;
-        if (__all_sync(FULL_MASK, hot || !active)) {
+        // Fused downsample: this datapoint's time relative to the end of the open window.  A lane whose
+        // datapoint opens the next window (adv) commits in place; one vote covers the common step where
+        // nobody advances, a second one the steps where some lanes do.  (Finished lanes keep d < 0.)
+        int64_t d_next = 0;
+        bool adv = false;
+        bool take, some_adv = false;
+        if (DS && MERGED) {
+          d_next = (int64_t)((uint64_t)acc.d + (uint64_t)s.prev_delta);
+          adv = (int32_t)((uint64_t)d_next >> 32) >= 0;  // sign of the high word
+          take = __all_sync(FULL_MASK, (hot && !adv) || !active);
+          if (!take) {
+            take = __all_sync(FULL_MASK, hot || !active);
+            some_adv = take;
+          }
+        } else {
+          take = __all_sync(FULL_MASK, hot || !active);
+        }
+        if (take) {
           // every live lane: unconditional update (finished lanes compute garbage
           // they never read again)
           s.pos += c;
@@ -792,30 +813,35 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
             s.n += (uint32_t)active;
             continue;
           } else {
-            // this datapoint's time relative to the end of the open window
-            acc.d = (int64_t)((uint64_t)acc.d + (uint64_t)s.prev_delta);
-            const bool adv = (int32_t)((uint64_t)acc.d >> 32) >= 0;  // sign of the high word
-            if (__any_sync(FULL_MASK, adv)) {
-              if (adv) {  // it opens the next window: commit the one it leaves
-                if (LAST && acc.cnt != acc.cnt_gen) {  // `last` of in-order datapoints = the previous one
-                  acc.last_t = (int64_t)((uint64_t)acc.d - (uint64_t)s.prev_delta + (uint64_t)acc.w_end);
-                  acc.last_v = s.prev_bits;
-                }
-                ds_store();
-                acc.cur_w++;
-                acc.hi_w = acc.cur_w;
-                acc.o += p.n_series;
-                acc.w_end += p.window;
-                acc.d -= p.window;
-                ds_reset();
+            if (MERGED) {
+              acc.d = d_next;
+            } else {
+              acc.d = (int64_t)((uint64_t)acc.d + (uint64_t)s.prev_delta);
+              adv = (int32_t)((uint64_t)acc.d >> 32) >= 0;
+              some_adv = __any_sync(FULL_MASK, adv);
+            }
+            if (some_adv && adv) {  // it opens the next window: commit the one it leaves
+              const uint32_t hot_n = s.n - acc.n_sync;  // hot datapoints since cnt was last updated
+              if (LAST && hot_n) {  // `last` of in-order datapoints = the previous one
+                acc.last_t = (int64_t)((uint64_t)acc.d - (uint64_t)s.prev_delta + (uint64_t)acc.w_end);
+                acc.last_v = s.prev_bits;
               }
+              acc.cnt += hot_n;
+              acc.n_sync = s.n;
+              ds_store();
+              acc.cur_w++;
+              acc.hi_w = acc.cur_w;
+              acc.o += p.n_series;
+              acc.w_end += p.window;
+              acc.d -= p.window;
+              ds_reset();
             }
             s.prev_xor = xr;
             s.prev_bits ^= xr;
             lz_tz(xr, plz, ptz);
             // finished lanes committed their window when they stopped: what they add here is never read
             ds_add(s.prev_bits);
-            s.n++;  // finished lanes published n_points / status when they stopped
+            s.n++;  // also this window's count: cnt += s.n - n_sync at the next commit / general visit
             continue;
           }
         }
@@ -826,10 +852,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
         if (DS && pre_ok)  // leaving the hot path: prev_time was carried in acc.d
           s.prev_time = (int64_t)((uint64_t)acc.d + (uint64_t)acc.w_end);
         pre_ok = false;  // the group's pre-check does not survive a general-path datapoint
-        if (LAST && acc.cnt != acc.cnt_gen) {  // hot datapoints since the last visit: the newest is `last`
-          acc.last_t = s.prev_time;
-          acc.last_v = s.prev_bits;
-          acc.cnt_gen = acc.cnt;
+        if (DS) {  // fold the hot datapoints since the last visit into the open window's count
+          const uint32_t hot_n = s.n - acc.n_sync;
+          if (LAST && hot_n) {  // ... and the newest of them is `last`
+            acc.last_t = s.prev_time;
+            acc.last_v = s.prev_bits;
+          }
+          acc.cnt += hot_n;
         }
         bool ok = fast_en && (cw + DEC_FAST_WORDS <= safe) && (s.prev_time != 0);
         uint32_t c = 1;  // bits consumed before the payload
@@ -1037,10 +1066,11 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
               acc.last_t = t;
               acc.last_v = v;
             }
+            acc.cnt++;
             ds_add(v);
           }
-          acc.cnt_gen = acc.cnt;
         }
+        acc.n_sync = s.n;  // everything up to here is accounted for
         if (!live && active) {
           // this lane is done: commit its open window and publish its counters now, so that the
           // hot path may run its unconditional updates on finished lanes without harm

@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/r2j_gpus.txt
-(timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_round2.py -q -m gpu -k "allgather or point_major" 2>&1 | tail -15) > gpurun_out/r2j_tests.log 2>&1
+(timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_round2.py tests/test_gpu_merge.py -q -m gpu -k "allgather or point_major or merge" 2>&1 | tail -15) > gpurun_out/r2j_tests.log 2>&1
 (timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3) > gpurun_out/r2j_bench_2gpu.json 2> gpurun_out/r2j_bench_2gpu.err
 (timeout 300 python scripts/prof_r2.py enc_pm 2>&1; timeout 200 python - <<'PY'
 import sys, os, torch

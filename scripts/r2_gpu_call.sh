@@ -1,31 +1,5 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_gpu_round2.py -q -m gpu -k "point_major or tiles or downsample" 2>&1 | tail -5) > gpurun_out/r2k_tests.log 2>&1
-(timeout 300 python scripts/r2_quick.py 1000000 1) > gpurun_out/r2k_quick_base.log 2>&1
-for v in w8 w8b; do (M3TSZ_B200_LIB=$PWD/m3_b200/variants/$v.so timeout 300 python scripts/r2_quick.py 1000000 1) > gpurun_out/r2k_quick_$v.log 2>&1; done
-(timeout 300 python - <<'PY'
-import sys, os, torch
-sys.path.insert(0, os.getcwd())
-from m3_b200 import synth
-from m3_b200.codec import BatchCodec
-S, P = 1_000_000, 1440
-codec = BatchCodec(0, True)
-ts, vals, start = synth.gaussian_walk(S, P, "cuda", seed=1)
-a, b = ts.t().contiguous(), vals.t().contiguous()
-stride = ((64 + 9 * P) + 63) // 64 * 64
-o1 = codec.encode(ts, vals, start, unit=1, out_stride=stride)
-o2 = codec.encode(a, b, start, unit=1, out_stride=stride, point_major=True)
-def t(fn, n=5):
-    fn(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n): fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n
-print("encode series-major %.3f ms, point-major %.3f ms, same=%s" % (
-    t(lambda: codec.encode(ts, vals, start, unit=1, out=o1)),
-    t(lambda: codec.encode(a, b, start, unit=1, out=o2, point_major=True)),
-    torch.equal(o1.out_len, o2.out_len) and torch.equal(o1.out, o2.out)))
-PY
-) > gpurun_out/r2k_enc_pm.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:merge_fast_kernel -s 2 -c 1 -o gpurun_out/r2k_merge python scripts/prof_merge.py > gpurun_out/r2k_prof_merge.log 2>&1
-tail -4 gpurun_out/r2k_tests.log; tail -2 gpurun_out/r2k_enc_pm.log; for f in gpurun_out/r2k_quick_*.log; do echo "== $f"; grep -E "decode|dec\+ds" $f; done
+(timeout 300 python scripts/r2_quick.py 1000000 1) > gpurun_out/r2m_quick_base.log 2>&1
+for v in dsm0 dsb4; do (M3TSZ_B200_LIB=$PWD/m3_b200/variants/$v.so timeout 300 python scripts/r2_quick.py 1000000 1) > gpurun_out/r2m_quick_$v.log 2>&1; done
+(timeout 300 python -m pytest tests/test_gpu_round2.py tests/test_gpu_parity_at_size.py -q -m gpu -k "downsample or tiles or gauge" 2>&1 | tail -4) > gpurun_out/r2m_tests.log 2>&1
+for f in gpurun_out/r2m_quick_*.log; do echo "== $f"; grep -E "dec\+ds" $f; done; tail -3 gpurun_out/r2m_tests.log

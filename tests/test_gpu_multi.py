@@ -21,7 +21,7 @@ WORKER = textwrap.dedent("""
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
-    S, P, G, CH = 5000, 300, 4096, 1000   # 5 chunks, the last one ragged (96 series)
+    S, P, G, CH = 5000, 300, 4096, 1024   # 4 chunks of 1024 series
     codec = BatchCodec(lr, True)
     data = [synth.gaussian_walk(S, P, dev, seed=50 + r) for r in range(world)]
     ts, vals, start = data[rank]
@@ -36,9 +36,9 @@ WORKER = textwrap.dedent("""
             out = allgather_decoded(codec, comm, world, pk.packed, pk.offsets, lengths, G, P, CH)
         torch.cuda.synchronize()
         assert bool((out[3] == 0).all()) and bool((out[2] == P).all())
-        for r in range(world):
-            assert torch.equal(out[0][r], data[r][0][:G]), (rank, r)
-            assert torch.equal(out[1][r].view(torch.int64), data[r][1][:G].view(torch.int64)), (rank, r)
+        for r in range(world):  # chunk-major result: series s of rank r = [s // CH, r, s % CH]
+            assert torch.equal(out[0][:, r].reshape(G, P), data[r][0][:G]), (rank, r)
+            assert torch.equal(out[1][:, r].reshape(G, P).view(torch.int64), data[r][1][:G].view(torch.int64)), (rank, r)
     dist.barrier()
     if rank == 0:
         print("ALLGATHER_DECODED_OK")
