@@ -553,13 +553,15 @@ void m3tsz_iter_pool_destroy(m3tsz_iter_pool *pool);
  * encode / decode need no collective; only a query that spans shards needs every
  * shard's DECODED blocks on every GPU.  m3tsz_allgather_decoded decodes the first
  * gather_series streams of the local shard chunk by chunk and all-gathers chunk k-1
- * over NCCL / NVLink while chunk k is decoded (ring of two staging buffers, one grouped
- * ncclAllGather per chunk).  Every rank passes the same gather_series / max_points /
+ * over NCCL / NVLink while chunk k+1 is decoded: every chunk is decoded straight into this
+ * rank's block of the gathered arrays and gathered IN PLACE (one grouped ncclAllGather per
+ * chunk, no staging copies).  Every rank passes the same gather_series / max_points /
  * chunk_series (gather_series a multiple of chunk_series; 0 = 32768).  Outputs (on every
- * rank) are CHUNK-major, the layout the collective writes without a second pass:
+ * rank); the datapoint arrays are CHUNK-major, the layout the collective writes without a
+ * second pass:
  *   d_ts_all / d_val_all : [n_chunks][n_ranks][chunk_series][max_points]; series s of rank r
  *                          sits at (((s / C) * n_ranks + r) * C + s % C) * max_points, C = chunk_series
- *   d_n_points_all / d_status_all : [n_chunks][n_ranks][chunk_series]
+ *   d_n_points_all / d_status_all : [n_ranks][gather_series]
  * nccl_comm is an ncclComm_t of n_ranks ranks (the caller's, or one made with
  * m3tsz_nccl_comm_create from an id broadcast out of band).  NCCL is resolved at run
  * time (dlopen of the libnccl.so.2 the process has loaded); without it the calls

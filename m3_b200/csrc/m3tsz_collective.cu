@@ -3,8 +3,8 @@
 // shard trivially (the reference hash-partitions them, src/dbnode/sharding/shardset.go:157-173),
 // so encode and decode run with no collective; this entry point decodes the local shard chunk
 // by chunk and all-gathers chunk k-1 over NCCL / NVLink while chunk k is being decoded
-// (two streams, a ring of two staging buffers): one grouped ncclAllGather per chunk straight into
-// the gathered arrays, which are therefore CHUNK-major: [chunk][rank][chunk_series][point].
+// (two streams, no staging): every chunk is decoded into its final place and all-gathered in place,
+// the gathered arrays are therefore CHUNK-major: [chunk][rank][chunk_series][point].
 //
 // NCCL is resolved at run time (dlopen "libnccl.so.2": the instance the process already
 // loaded, e.g. torch's), so libm3tsz_b200.so has no link-time NCCL dependency and single-GPU
@@ -32,6 +32,7 @@ struct Nccl {
   int (*GroupEnd)() = nullptr;
   int (*Broadcast)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
   int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+  int (*CommUserRank)(void *, int *) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool ok = false;
 };
@@ -52,9 +53,10 @@ Nccl &nccl() {
     t.GroupEnd = (int (*)())dlsym(t.lib, "ncclGroupEnd");
     t.Broadcast = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(t.lib, "ncclBroadcast");
     t.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(t.lib, "ncclAllGather");
+    t.CommUserRank = (int (*)(void *, int *))dlsym(t.lib, "ncclCommUserRank");
     t.GetErrorString = (const char *(*)(int))dlsym(t.lib, "ncclGetErrorString");
     t.ok = t.GetUniqueId && t.CommInitRank && t.CommDestroy && t.GroupStart && t.GroupEnd && t.Broadcast &&
-           t.AllGather;
+           t.AllGather && t.CommUserRank;
     return t;
   }();
   return n;
@@ -119,68 +121,63 @@ int m3tsz_allgather_decoded(m3tsz_ctx *ctx, const m3tsz_options *opts, void *ncc
   if (chunk_series > gather_series) chunk_series = gather_series;
   if (gather_series % chunk_series != 0) return M3TSZ_ERR_INVALID_ARG;  // whole chunks (see the layout)
   cudaStream_t user = (cudaStream_t)stream, dec = ctx->stream, com = ctx->stream2;
-  // staging ring: two slots of (ts, val, n, status) for chunk_series series
-  void *st_ts[2], *st_val[2], *st_n[2], *st_st[2];
-  int rc;
-  for (int i = 0; i < 2; i++) {
-    const int b = 16 + i * 10;
-    if ((rc = ensure(ctx, b + 0, chunk_series * max_points * 8, &st_ts[i]))) return rc;
-    if ((rc = ensure(ctx, b + 1, chunk_series * max_points * 8, &st_val[i]))) return rc;
-    if ((rc = ensure(ctx, b + 2, chunk_series * 4, &st_n[i]))) return rc;
-    if ((rc = ensure(ctx, b + 3, chunk_series * 4, &st_st[i]))) return rc;
-  }
-  cudaEvent_t ev_dec[2], ev_com[2], ev_start;
-  for (int i = 0; i < 2; i++) {
-    CK(cudaEventCreateWithFlags(&ev_dec[i], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ev_com[i], cudaEventDisableTiming));
-  }
+  int rank = -1;
+  int rc = n.CommUserRank(nccl_comm, &rank);
+  if (rc != 0 || rank < 0 || rank >= n_ranks) return nccl_fail(ctx, rc ? rc : 5, "ncclCommUserRank");
+  cudaEvent_t ev_dec[2], ev_start;
+  for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&ev_dec[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
   // everything queued on the caller's stream so far happens before the pipeline
   CK(cudaEventRecord(ev_start, user));
   CK(cudaStreamWaitEvent(dec, ev_start, 0));
   CK(cudaStreamWaitEvent(com, ev_start, 0));
-  const uint64_t n_chunks = (gather_series + chunk_series - 1) / chunk_series;
+  // No staging: chunk k is decoded straight into this rank's block of chunk k of the gathered arrays
+  // ([chunk][rank][chunk_series][point]) and all-gathered IN PLACE (sendbuff = recvbuff + rank * count), so
+  // the decodes run ahead on one stream while the gathers follow on the other.  n_points / status are
+  // [rank][gather_series]: decoded into this rank's row, gathered once at the end.
+  const uint64_t n_chunks = gather_series / chunk_series, C = chunk_series;
+  uint32_t *my_n = d_n_points_all + (uint64_t)rank * gather_series;
+  int32_t *my_st = d_status_all + (uint64_t)rank * gather_series;
   int status = M3TSZ_OK;
   for (uint64_t k = 0; k < n_chunks && status == M3TSZ_OK; k++) {
     const int slot = (int)(k & 1);
-    const uint64_t s0 = k * chunk_series, ns = (s0 + chunk_series <= gather_series) ? chunk_series : gather_series - s0;
-    if (k >= 2) CK(cudaStreamWaitEvent(dec, ev_com[slot], 0));  // the gather of chunk k-2 has drained this slot
+    const uint64_t s0 = k * C;
+    const uint64_t blk = (k * (uint64_t)n_ranks) * C * max_points;       // chunk k of the gathered arrays
+    const uint64_t mine = blk + (uint64_t)rank * C * max_points;          // this rank's block in it
     m3tsz_decode_extras ex;
     memset(&ex, 0, sizeof(ex));
     ex.d_lengths = d_lengths ? d_lengths + s0 : nullptr;
-    status = m3tsz_decode_batch_ex(ctx, opts, d_streams, streams_bytes, d_offsets + s0, ns, (int64_t *)st_ts[slot],
-                                   (double *)st_val[slot], max_points, (uint32_t *)st_n[slot],
-                                   (int32_t *)st_st[slot], nullptr, nullptr, d_lengths ? &ex : nullptr, dec);
+    status = m3tsz_decode_batch_ex(ctx, opts, d_streams, streams_bytes, d_offsets + s0, C, d_ts_all + mine,
+                                   d_val_all + mine, max_points, my_n + s0, my_st + s0, nullptr, nullptr,
+                                   d_lengths ? &ex : nullptr, dec);
     if (status != M3TSZ_OK) break;
     CK(cudaEventRecord(ev_dec[slot], dec));
     CK(cudaStreamWaitEvent(com, ev_dec[slot], 0));
-    // one ncclAllGather per array and chunk (grouped): chunk k of the gathered arrays is the
-    // contiguous block [rank][chunk_series][max_points] at k * n_ranks * chunk_series * max_points
     // (grouped ncclBroadcasts with strided placement -- a [rank][series][point] result -- measured
-    // 316 GB/s per GPU at N = 2 against 470+ for ncclAllGather, so the layout follows the collective)
-    const uint64_t co = k * (uint64_t)n_ranks * chunk_series;  // first series slot of this chunk
+    // 316 GB/s per GPU at N = 2, staged ncclAllGather 388: the layout follows the collective)
     int nrc = n.GroupStart();
-    if (nrc == 0) nrc = n.AllGather(st_ts[slot], d_ts_all + co * max_points, ns * max_points * 8, 0 /* ncclInt8 */, nccl_comm, com);
-    if (nrc == 0) nrc = n.AllGather(st_val[slot], d_val_all + co * max_points, ns * max_points * 8, 0, nccl_comm, com);
-    if (nrc == 0) nrc = n.AllGather(st_n[slot], d_n_points_all + co, ns * 4, 0, nccl_comm, com);
-    if (nrc == 0) nrc = n.AllGather(st_st[slot], d_status_all + co, ns * 4, 0, nccl_comm, com);
+    if (nrc == 0) nrc = n.AllGather(d_ts_all + mine, d_ts_all + blk, C * max_points * 8, 0 /* ncclInt8 */, nccl_comm, com);
+    if (nrc == 0) nrc = n.AllGather(d_val_all + mine, d_val_all + blk, C * max_points * 8, 0, nccl_comm, com);
     const int erc = n.GroupEnd();
     if (nrc != 0 || erc != 0) {
       status = nccl_fail(ctx, nrc ? nrc : erc, "ncclAllGather (decoded blocks)");
       break;
     }
     ctx->launches++;
-    CK(cudaEventRecord(ev_com[slot], com));
+  }
+  if (status == M3TSZ_OK) {
+    int nrc = n.GroupStart();
+    if (nrc == 0) nrc = n.AllGather(my_n, d_n_points_all, gather_series * 4, 0, nccl_comm, com);
+    if (nrc == 0) nrc = n.AllGather(my_st, d_status_all, gather_series * 4, 0, nccl_comm, com);
+    const int erc = n.GroupEnd();
+    if (nrc != 0 || erc != 0) status = nccl_fail(ctx, nrc ? nrc : erc, "ncclAllGather (n_points / status)");
   }
   // the caller's stream continues after the whole pipeline
   cudaEventRecord(ev_start, com);
   cudaStreamWaitEvent(user, ev_start, 0);
   cudaEventRecord(ev_start, dec);
   cudaStreamWaitEvent(user, ev_start, 0);
-  for (int i = 0; i < 2; i++) {
-    cudaEventDestroy(ev_dec[i]);
-    cudaEventDestroy(ev_com[i]);
-  }
+  for (int i = 0; i < 2; i++) cudaEventDestroy(ev_dec[i]);
   cudaEventDestroy(ev_start);
   return status;
 }

@@ -61,6 +61,18 @@ __host__ __device__ __forceinline__ int initial_time_unit(int64_t start, int uni
 // Go shift semantics: x >> n == 0 and x << n == 0 for n >= 64.
 __device__ __forceinline__ uint64_t shr64(uint64_t x, int n) { return n >= 64 ? 0ull : x >> n; }
 __device__ __forceinline__ uint64_t shl64(uint64_t x, int n) { return n >= 64 ? 0ull : x << n; }
+// PTX shifts: amounts above 63 (incl. "negative" ones read as unsigned) are clamped and shift everything
+// out -- defined behaviour, so no guard compare + select around the hot path's shifts
+__device__ __forceinline__ uint64_t shr64_clamp(uint64_t x, uint32_t n) {
+  uint64_t r;
+  asm("shr.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n));
+  return r;
+}
+__device__ __forceinline__ uint64_t shl64_clamp(uint64_t x, uint32_t n) {
+  uint64_t r;
+  asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n));
+  return r;
+}
 
 // encoding.SignExtend (encoding.go:45-49) for 1 <= n <= 64
 __device__ __forceinline__ int64_t sign_extend(uint64_t v, int n) {
@@ -70,7 +82,8 @@ __device__ __forceinline__ int64_t sign_extend(uint64_t v, int n) {
 
 // encoding.LeadingAndTrailingZeros (encoding.go:33-43): (64, 0) for v == 0
 __device__ __forceinline__ void lz_tz(uint64_t v, int &lz, int &tz) {
-  const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  uint32_t hi, lo;  // unpacked in PTX: "hi != 0" must stay a 32-bit test (not v >= 2^32: two compares)
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
   lz = hi ? __clz((int)hi) : 32 + __clz((int)lo);  // 64 for v == 0
   const int tlo = __clz((int)__brev(lo)), thi = 32 + __clz((int)__brev(hi));
   tz = lo ? tlo : (hi ? thi : 0);

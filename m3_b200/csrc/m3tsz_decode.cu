@@ -14,6 +14,7 @@
 // Format: SURVEY.md Appendix A; reference decode path
 //   m3tsz/iterator.go:81-219, m3tsz/timestamp_iterator.go:80-326,
 //   m3tsz/float_encoder_iterator.go:105-165, istream.go:73-115.
+#include <cstdlib>
 #include "m3tsz_common.cuh"
 #include "m3tsz_kernels.h"
 
@@ -33,8 +34,11 @@ namespace m3tsz {
 #ifndef M3_DEC_MIN_BLOCKS
 #define M3_DEC_MIN_BLOCKS 4  // 4 x 4 warps with ~110 registers beat 5 blocks squeezed into 96 (profiles/r02_decode_history.md)
 #endif
-#ifndef M3_DS_MERGED_VOTE
-#define M3_DS_MERGED_VOTE 0  // bit 0: MODE 1, bit 1: MODE 2 take the merged hot/advance vote (see the hot path)
+#ifndef M3_DEC_RING64_PLAIN
+#define M3_DEC_RING64_PLAIN 0  // ... not series-major decode (more shared-memory wavefronts: 8.55 -> 8.84 ms)
+#endif
+#ifndef M3_DEC_RING64
+#define M3_DEC_RING64 1  // fused-downsample and point-major kernels read the ring as 8-byte pairs (see the parse)
 #endif
 #ifndef M3_DEC_MIN_BLOCKS_DS
 #define M3_DEC_MIN_BLOCKS_DS 5  // fused-downsample kernels: 5 x 4 warps at 96 registers (7.94 vs 8.25 ms at 4 blocks)
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
   // MODE 0: plain decode, series-major output [series][point]; 3: plain decode, point-major output
   // [point][series] (every step's 32 lanes store 32 consecutive elements: coalesced 256-byte rows);
   // 1: fused downsample (sum, count, min, max); 2: + last / lastAt
-  constexpr bool MERGED = (MODE == 1 && (M3_DS_MERGED_VOTE & 1)) || (MODE == 2 && (M3_DS_MERGED_VOTE & 2));
+  constexpr bool RING64 = ((MODE == 1 || MODE == 2 || MODE == 3) && M3_DEC_RING64) || M3_DEC_RING64_PLAIN;
   constexpr bool DS = (MODE == 1 || MODE == 2), LAST = (MODE == 2), PLAIN = (MODE == 0 || MODE == 3),
                  PM = (MODE == 3);
   constexpr int CHK = (MODE == 0) ? M3_DEC_CHK : M3_DEC_CHK_WIDE;
@@ -624,8 +628,13 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
   };
   auto ds_add = [&](uint64_t vbits) {  // Gauge.updateTotals without `last` and `count` (gauge.go:85-101)
     const double dv = __longlong_as_double((long long)vbits);
-    // sum += v unless v is NaN: one compare + one predicated add
-    asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %1, %1;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc.sum) : "d"(dv));
+    if (dv == dv) acc.sum = __dadd_rn(acc.sum, dv);
+    if (dv > acc.mx) acc.mx = dv;
+    if (dv < acc.mn) acc.mn = dv;
+  };
+  auto ds_add_no_nan = [&](uint64_t vbits) {  // ... when no lane of the warp holds a NaN
+    const double dv = __longlong_as_double((long long)vbits);
+    acc.sum = __dadd_rn(acc.sum, dv);
     if (dv > acc.mx) acc.mx = dv;
     if (dv < acc.mn) acc.mn = dv;
   };
@@ -719,6 +728,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
       pre_ok = pre_ok && acc.in_open && acc.cur_w == acc.hi_w && s.prev_delta > 0 && s.prev_delta <= p.window &&
                (uint32_t)acc.cur_w + (uint32_t)CHK < p.n_windows;
     }
+    // one vote per group: the per-datapoint vote below then only looks at the header bits.  The flag is
+    // warp-uniform: a general-path datapoint (taken by the whole warp) clears it for the rest of the group.
+    bool group_ok = __all_sync(FULL_MASK, pre_ok || !live);
 
 #pragma unroll
     for (int rr = 0; rr < CHK; rr++) {
@@ -729,18 +741,40 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
       bool emitted = false;
       // ---------------- parse: the 128-bit window at the current word ----------------
       const uint32_t sh = s.pos & 31u;
-      // two aligned quads (8 words) hold the window; pick words j..j+3 (j = cw & 3): the
-      // j & 2 level with selects on the raw words, the j & 1 level fused with the byte swap
-      // (PRMT picks the swapped bytes of its first or its second operand)
-      const uint4 *qp = reinterpret_cast<const uint4 *>(ring_lane) + ((cw >> 2) & (DEC_QUADS - 1)) * 32;
-      const uint4 qa = qp[0], qb = qp[32];
-      const bool j2 = (cw & 2u) != 0;
-      const uint32_t u0 = j2 ? qa.z : qa.x, u1 = j2 ? qa.w : qa.y, u2 = j2 ? qb.x : qa.z,
-                     u3 = j2 ? qb.y : qa.w, u4 = j2 ? qb.z : qb.x;
-      const uint32_t psel = 0x0123u + (cw & 1u) * 0x4444u;  // 0x0123: swap(a), 0x4567: swap(b)
-      const uint32_t w0 = __byte_perm(u0, u1, psel), w1 = __byte_perm(u1, u2, psel),
-                     w2 = __byte_perm(u2, u3, psel);
-      const uint32_t w3 = __byte_perm(u3, u4, psel);
+      // the window = words cw .. cw+3 of the lane's ring column (16-byte cells, [quad][lane]), as the five
+      // words u0..u4 from the even word e = cw & ~1 on; the byte swap then picks word e+i or e+i+1 (PRMT
+      // on its first or its second operand).  Selector and addresses come from the bit position with
+      // multiply-adds (FMA pipe): the kernels are ALU-pipe-bound (rt 2 cycles per warp instruction).
+      const uint32_t r3 = s.pos >> 3;
+      const uint32_t psel = 0x0123u + (r3 & 4u) * 0x1111u;  // 0x0123: swap(a), 0x4567: swap(b)
+      uint32_t u0, u1, u2, u3, u4;
+      if (RING64) {
+        // two 8-byte pairs + one word (pair p = cw >> 1 sits at quad p >> 1, half p & 1: pair p+1 is 8 bytes
+        // on, or 504 on in the next quad's cell; pair p+2 is always one quad = 512 bytes on, the mirror quad
+        // covering the wrap): no selects (6 ALU instructions fewer per datapoint), but 12 shared-memory
+        // wavefronts instead of 8 (2-way / 4-way bank conflicts) -- pays where the L1 pipe has room: the fused
+        // downsample (7.93 -> 7.43 ms), point-major decode with 64 KB of L1 (7.28 -> 7.20); not series-major
+        // decode, whose sector stores already fill that pipe (8.55 -> 8.84)
+        const uint32_t t8 = r3 & 8u;  // (p & 1) * 8
+        const uint32_t a0 = ring_lane_addr + ((s.pos << 2) & ((DEC_QUADS - 1) * 512u)) + t8;
+        const uint32_t a1 = a0 + t8 * 62u;  // + 8 below: +8 or +504
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(u0), "=r"(u1) : "r"(a0));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+8];" : "=r"(u2), "=r"(u3) : "r"(a1));
+        asm volatile("ld.shared.u32 %0, [%1+512];" : "=r"(u4) : "r"(a0));
+      } else {
+        // two conflict-free LDS.128 (quads q, q+1) and one select level on (cw & 2)
+        const uint4 *qp = reinterpret_cast<const uint4 *>(ring_lane) + ((cw >> 2) & (DEC_QUADS - 1)) * 32;
+        const uint4 qa = qp[0], qb = qp[32];
+        const bool j2 = (cw & 2u) != 0;
+        u0 = j2 ? qa.z : qa.x, u1 = j2 ? qa.w : qa.y, u2 = j2 ? qb.x : qa.z, u3 = j2 ? qb.y : qa.w,
+        u4 = j2 ? qb.z : qb.x;
+      }
+      // (prmt.b32 directly: __byte_perm would mask the selector with 0x7777 first)
+      uint32_t w0, w1, w2, w3;
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(w0) : "r"(u0), "r"(u1), "r"(psel));
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(w1) : "r"(u1), "r"(u2), "r"(psel));
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(w2) : "r"(u2), "r"(u3), "r"(psel));
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(w3) : "r"(u3), "r"(u4), "r"(psel));
       // 96-bit window at the bit position: (h, h1, h2); a field at offset c <= 32 is two more funnels
       const uint32_t h = __funnelshift_l(w1, w0, sh), h1 = __funnelshift_l(w2, w1, sh),
                      h2 = __funnelshift_l(w3, w2, sh);
@@ -751,7 +785,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
       {
         uint32_t x = h << 1;
         uint32_t c = 1;
-        const bool hot = pre_ok && (INT_OPT ? ((h >> 30) == 1u) : !(h >> 31));  // '0' zero DoD [+ '1' no update]
+        // '0' zero DoD [+ '1' no update]: top bits 01 <=> signed h >= 0x40000000 (one compare)
+        const bool hot = INT_OPT ? ((int32_t)h >= 0x40000000) : ((int32_t)h >= 0);
         if (INT_OPT) {
           x <<= 1;
           c = 2;
@@ -769,31 +804,16 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
         }
         const uint64_t field = M3_FIELD64(c);
         c += (uint32_t)n;
-        // Fused downsample: this datapoint's time relative to the end of the open window.  A lane whose
-        // datapoint opens the next window (adv) commits in place; one vote covers the common step where
-        // nobody advances, a second one the steps where some lanes do.  (Finished lanes keep d < 0.)
-        int64_t d_next = 0;
-        bool adv = false;
-        bool take, some_adv = false;
-        if (DS && MERGED) {
-          d_next = (int64_t)((uint64_t)acc.d + (uint64_t)s.prev_delta);
-          adv = (int32_t)((uint64_t)d_next >> 32) >= 0;  // sign of the high word
-          take = __all_sync(FULL_MASK, (hot && !adv) || !active);
-          if (!take) {
-            take = __all_sync(FULL_MASK, hot || !active);
-            some_adv = take;
-          }
-        } else {
-          take = __all_sync(FULL_MASK, hot || !active);
-        }
-        if (take) {
+        const bool take = __all_sync(FULL_MASK, hot || !active);
+        if (group_ok && take) {
           // every live lane: unconditional update (finished lanes compute garbage
           // they never read again)
           s.pos += c;
           // xor = (top n bits of the field) << tz; nothing for the zero code, an empty contained
           // window (previous XOR zero) or a malformed uncontained header (lz + n > 64: the
           // reference shifts everything out)
-          const uint64_t xr = (n == 0 || tz < 0) ? 0ull : ((field >> (64 - n)) << tz);
+          // (clamping PTX shifts: n == 0 shifts right by 64, tz < 0 shifts left by > 63 -- both give 0)
+          const uint64_t xr = shl64_clamp(shr64_clamp(field, 64u - (uint32_t)n), (uint32_t)tz);
           if (PLAIN) {
             s.prev_time = (int64_t)((uint64_t)s.prev_time + (uint64_t)s.prev_delta);
             s.prev_xor = xr;
@@ -813,34 +833,40 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
             s.n += (uint32_t)active;
             continue;
           } else {
-            if (MERGED) {
-              acc.d = d_next;
-            } else {
-              acc.d = (int64_t)((uint64_t)acc.d + (uint64_t)s.prev_delta);
-              adv = (int32_t)((uint64_t)acc.d >> 32) >= 0;
-              some_adv = __any_sync(FULL_MASK, adv);
-            }
-            if (some_adv && adv) {  // it opens the next window: commit the one it leaves
-              const uint32_t hot_n = s.n - acc.n_sync;  // hot datapoints since cnt was last updated
-              if (LAST && hot_n) {  // `last` of in-order datapoints = the previous one
-                acc.last_t = (int64_t)((uint64_t)acc.d - (uint64_t)s.prev_delta + (uint64_t)acc.w_end);
-                acc.last_v = s.prev_bits;
+            // this datapoint's time relative to the end of the open window; a lane whose datapoint opens
+            // the next window (adv: d >= 0, the sign of the high word) commits in place.  NaN values ride on
+            // the same vote: without one in the warp the accumulate needs no NaN select (gauge.go:85-101).
+            acc.d = (int64_t)((uint64_t)acc.d + (uint64_t)s.prev_delta);
+            int32_t d_lo, d_hi;  // (unpacked in PTX: a 64-bit compare would be two instructions)
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(d_lo), "=r"(d_hi) : "l"(acc.d));
+            const bool adv = d_hi >= 0;
+            const uint64_t nb = s.prev_bits ^ xr;
+            const double nbd = __longlong_as_double((long long)nb);
+            if (__any_sync(FULL_MASK, adv || nbd != nbd)) {
+              if (adv) {  // it opens the next window: commit the one it leaves
+                const uint32_t hot_n = s.n - acc.n_sync;  // hot datapoints since cnt was last updated
+                if (LAST && hot_n) {  // `last` of in-order datapoints = the previous one
+                  acc.last_t = (int64_t)((uint64_t)acc.d - (uint64_t)s.prev_delta + (uint64_t)acc.w_end);
+                  acc.last_v = s.prev_bits;
+                }
+                acc.cnt += hot_n;
+                acc.n_sync = s.n;
+                ds_store();
+                acc.cur_w++;
+                acc.hi_w = acc.cur_w;
+                acc.o += p.n_series;
+                acc.w_end += p.window;
+                acc.d -= p.window;
+                ds_reset();
               }
-              acc.cnt += hot_n;
-              acc.n_sync = s.n;
-              ds_store();
-              acc.cur_w++;
-              acc.hi_w = acc.cur_w;
-              acc.o += p.n_series;
-              acc.w_end += p.window;
-              acc.d -= p.window;
-              ds_reset();
+              ds_add(nb);
+            } else {
+              ds_add_no_nan(nb);
             }
             s.prev_xor = xr;
-            s.prev_bits ^= xr;
+            s.prev_bits = nb;
             lz_tz(xr, plz, ptz);
-            // finished lanes committed their window when they stopped: what they add here is never read
-            ds_add(s.prev_bits);
+            // (finished lanes committed their window when they stopped: what they add here is never read)
             s.n++;  // also this window's count: cnt += s.n - n_sync at the next commit / general visit
             continue;
           }
@@ -849,9 +875,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
 
       // ---------------- general path (any mix of cases) ----------------
       {
-        if (DS && pre_ok)  // leaving the hot path: prev_time was carried in acc.d
+        if (DS && group_ok && live)  // leaving the hot path: prev_time was carried in acc.d
           s.prev_time = (int64_t)((uint64_t)acc.d + (uint64_t)acc.w_end);
-        pre_ok = false;  // the group's pre-check does not survive a general-path datapoint
+        group_ok = false;  // the group's pre-check does not survive a general-path datapoint
         if (DS) {  // fold the hot datapoints since the last visit into the open window's count
           const uint32_t hot_n = s.n - acc.n_sync;
           if (LAST && hot_n) {  // ... and the newest of them is `last`
@@ -1084,7 +1110,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
         }
       }
     }
-    if (DS && pre_ok)  // the group stayed hot: materialise prev_time for the next pre-check
+    if (DS && group_ok && live)  // the group stayed hot: materialise prev_time for the next pre-check
       s.prev_time = (int64_t)((uint64_t)acc.d + (uint64_t)acc.w_end);
 
     // ---------------- store the group: each lane writes its own series ----------------
@@ -1145,13 +1171,34 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
 template <bool INT_OPT, int MODE>
 static cudaError_t launch_one(const DecodeParams &p, cudaStream_t stream) {
   constexpr size_t warp_smem = DEC_WARP_SMEM_PLAIN;
-#ifdef M3_DEC_PAD_SMEM
-  constexpr size_t smem = warp_smem * DEC_WARPS + M3_DEC_PAD_SMEM;  // diagnostic: caps resident blocks
-#else
-  constexpr size_t smem = warp_smem * DEC_WARPS;
-#endif
+  size_t smem = warp_smem * DEC_WARPS;
+  // tuning knob: M3TSZ_DEC_CAP_BLOCKS=N pads the block's shared memory so that at most N blocks are
+  // resident per SM (228 KB per SM, 1 KB reserved per block)
+  static const int cap_blocks = [] {
+    const char *e = getenv("M3TSZ_DEC_CAP_BLOCKS");
+    return e ? atoi(e) : 0;
+  }();
+  if (cap_blocks > 0) {
+    const size_t per = (228u * 1024u) / (size_t)cap_blocks - 1024u;
+    if (per > smem) smem = per & ~(size_t)1023;
+    if (smem > 227u * 1024u) smem = 227u * 1024u;
+  }
   cudaError_t e = cudaFuncSetAttribute(decode_kernel<INT_OPT, MODE>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  // Shared-memory carveout = resident blocks x 35.8 KB; the rest of the SM's 228 KB is L1, which holds the
+  // fills in flight (cp.async.ca allocates a line per request).  Measured at 1 M x 1440 (ms, carveout 132 /
+  // 164 / 196 / 228 KB = 3 / 4 / 5 / 6 blocks): point-major int-optimised 8.15 / 7.28 / 7.60 / 9.53, float
+  // mode 7.91 / 6.92 / 7.49 / 9.47 (the driver's own choice for its 76 registers was 228); fused downsample
+  // 8.60 / 7.64 / 7.23 / 8.00.  So: plain decode 4 blocks + 64 KB of L1, fused downsample 5 blocks + 32 KB.
+  // M3TSZ_DEC_CARVEOUT_KB overrides (tuning).
+  static const int carveout_env = [] {
+    const char *c = getenv("M3TSZ_DEC_CARVEOUT_KB");
+    return c ? atoi(c) : 0;
+  }();
+  const int carveout_kb = carveout_env > 0 ? carveout_env : ((MODE == 1 || MODE == 2) ? 196 : 164);
+  e = cudaFuncSetAttribute(decode_kernel<INT_OPT, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           carveout_kb * 100 / 228);
   if (e != cudaSuccess) return e;
   const uint64_t per_block = (uint64_t)DEC_WARPS * 32ull;
   const uint64_t blocks = (p.n_series + per_block - 1) / per_block;

@@ -14,6 +14,7 @@
 //   m3tsz/encoder.go:90-250, m3tsz/timestamp_encoder.go:72-259,
 //   m3tsz/float_encoder_iterator.go:69-103, m3tsz/int_sig_bits_tracker.go:35-91,
 //   m3tsz/m3tsz.go:78-119, ostream.go:133-221, scheme.go:198-220.
+#include <cstdlib>
 #include <cub/device/device_scan.cuh>
 
 #include "m3tsz_common.cuh"
@@ -32,9 +33,20 @@ constexpr int ENC_IN_T = 8;     // datapoints per input tile (double buffered, c
 #endif
 constexpr int ENC_OUT_W = M3_ENC_OUT_W;   // output tile words per lane
 constexpr int ENC_GUARD = 10;   // words a single datapoint (no annotation) may add
-constexpr int ENC_IN_TILE_DWORDS = ENC_IN_T * ENC_STRIDE;   // one array (ts or val), one buffer
 constexpr int ENC_OUT_TILE_WORDS = ENC_OUT_W * ENC_STRIDE;
-constexpr size_t ENC_WARP_SMEM = 4 * (size_t)ENC_IN_TILE_DWORDS * 8 + (size_t)ENC_OUT_TILE_WORDS * 4;
+#ifndef M3_ENC_IN_T_PM
+#define M3_ENC_IN_T_PM 4  // rows per input tile of the point-major input stage (IN = 1): 9.60 / 9.10 / 9.58 ms for 8 / 4 / 2
+#endif
+// input stage IN: 0 series-major tiles (8 rows: one 64-byte segment per series and array), 1 point-major
+// tiles, 2 Gauge aggregates read directly (no input tiles)
+template <int IN>
+__host__ __device__ constexpr int enc_in_t() {
+  return IN == 1 ? M3_ENC_IN_T_PM : ENC_IN_T;
+}
+template <int IN>
+__host__ __device__ constexpr size_t enc_warp_smem() {
+  return ((IN == 0 || IN == 1) ? 4 * (size_t)(enc_in_t<IN>() * ENC_STRIDE) * 8 : 0) + (size_t)ENC_OUT_TILE_WORDS * 4;
+}
 
 struct EncLane {
   uint32_t carry, sh, k, words_out;
@@ -614,11 +626,13 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   const int warp = threadIdx.x >> 5;
   // the direct input stages (IN != 0) need no input tiles: only the output tile lives in shared memory
   constexpr bool STAGED = (IN == 0 || IN == 1);  // inputs go through the shared-memory tiles
-  constexpr size_t WARP_SMEM = STAGED ? ENC_WARP_SMEM : (size_t)ENC_OUT_TILE_WORDS * 4;
+  constexpr int IN_T = enc_in_t<IN>();  // datapoints per input tile
+  constexpr int IN_TILE_DW = IN_T * ENC_STRIDE;  // one array (ts or val), one buffer
+  constexpr size_t WARP_SMEM = enc_warp_smem<IN>();
   uint8_t *wbase = reinterpret_cast<uint8_t *>(smem) + warp * WARP_SMEM;
   // in_tiles: [buffer][array (0 ts, 1 val)][row][lane]
   uint64_t *in_tiles = reinterpret_cast<uint64_t *>(wbase);
-  uint32_t *out_tile = STAGED ? reinterpret_cast<uint32_t *>(in_tiles + 4 * ENC_IN_TILE_DWORDS)
+  uint32_t *out_tile = STAGED ? reinterpret_cast<uint32_t *>(in_tiles + 4 * IN_TILE_DW)
                               : reinterpret_cast<uint32_t *>(wbase);
 
   const uint64_t n_batches = (p.n_series + 31) >> 5;
@@ -739,27 +753,27 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
     __syncwarp();
   };
 
-  // asynchronous staging of input tile `tile` (rows tile*ENC_IN_T ..) into buffer tile&1:
+  // asynchronous staging of input tile `tile` (rows tile*IN_T ..) into buffer tile&1:
   // lanes 0-7 / 8-15: ts / value rows of series 2i, lanes 16-23 / 24-31: of series 2i+1
-  const int st_r = lane & (ENC_IN_T - 1);
+  const int st_r = lane & (IN_T - 1);
   const int st_arr = (lane >> 3) & 1;
   const int st_jo = lane >> 4;
   const bool uniform_n = __all_sync(FULL_MASK, !valid || n_pts == max_pts) && __all_sync(FULL_MASK, valid);
   auto stage = [&](uint32_t tile) {
-    const uint32_t row0 = tile * ENC_IN_T;
+    const uint32_t row0 = tile * IN_T;
     if (row0 >= max_pts) return;
     if (IN == 1) {
       // point-major inputs: a row of the tile is 32 consecutive elements of the array -- every lane
       // copies its own column (8 rows x 2 arrays), sources coalesced across the warp, no shuffles
       const uint64_t *st = reinterpret_cast<const uint64_t *>(p.ts) + (uint64_t)row0 * p.n_series + sidx;
       const uint64_t *sv = reinterpret_cast<const uint64_t *>(p.val) + (uint64_t)row0 * p.n_series + sidx;
-      const uint32_t d0 = enc_smem_addr(in_tiles + ((tile & 1u) * 2u) * ENC_IN_TILE_DWORDS + lane);
+      const uint32_t d0 = enc_smem_addr(in_tiles + ((tile & 1u) * 2u) * IN_TILE_DW + lane);
       const uint32_t lim = (valid && s.err == 0) ? n_pts : 0u;
 #pragma unroll
-      for (int r = 0; r < ENC_IN_T; r++) {
+      for (int r = 0; r < IN_T; r++) {
         if (row0 + (uint32_t)r < lim) {
           enc_cp_async8(d0 + (uint32_t)(r * ENC_STRIDE) * 8u, st);
-          enc_cp_async8(d0 + (uint32_t)(ENC_IN_TILE_DWORDS + r * ENC_STRIDE) * 8u, sv);
+          enc_cp_async8(d0 + (uint32_t)(IN_TILE_DW + r * ENC_STRIDE) * 8u, sv);
         }
         st += p.n_series;
         sv += p.n_series;
@@ -769,10 +783,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
     const uint64_t *src = (st_arr ? reinterpret_cast<const uint64_t *>(p.val)
                                   : reinterpret_cast<const uint64_t *>(p.ts)) +
                           (warp_s0 + st_jo) * p.points_stride + row0 + st_r;
-    const uint32_t dst0 = enc_smem_addr(in_tiles + ((tile & 1u) * 2u + (uint32_t)st_arr) * ENC_IN_TILE_DWORDS +
+    const uint32_t dst0 = enc_smem_addr(in_tiles + ((tile & 1u) * 2u + (uint32_t)st_arr) * IN_TILE_DW +
                                         st_r * ENC_STRIDE + st_jo);
     const uint64_t step = 2ull * p.points_stride;
-    if (uniform_n && row0 + ENC_IN_T <= max_pts) {
+    if (uniform_n && row0 + IN_T <= max_pts) {
 #pragma unroll
       for (int i = 0; i < 16; i++) {
         enc_cp_async8(dst0 + (uint32_t)i * 16u, src);
@@ -833,16 +847,16 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
     const bool active = valid && s.err == 0 && iter < n_pts && !(IN == 2 && sk_pf);
 
     // ---- input pipeline: request tile t+1, wait for tile t ----
-    if (STAGED && (iter & (ENC_IN_T - 1)) == 0) {
+    if (STAGED && (iter & (IN_T - 1)) == 0) {
       __syncwarp();  // everyone is done reading the buffer about to be overwritten
-      stage(iter / ENC_IN_T + 1);
+      stage(iter / IN_T + 1);
       asm volatile("cp.async.commit_group;\n" ::: "memory");
       asm volatile("cp.async.wait_group 1;\n" ::: "memory");
       __syncwarp();
       // row 0 of the tile that just landed; rows 1..7 are fetched one datapoint ahead below
-      const uint64_t *tile = in_tiles + (((iter / ENC_IN_T) & 1u) * 2u) * ENC_IN_TILE_DWORDS + lane;
+      const uint64_t *tile = in_tiles + (((iter / IN_T) & 1u) * 2u) * IN_TILE_DW + lane;
       t_pf = (int64_t)tile[0];
-      fb_pf = tile[ENC_IN_TILE_DWORDS];
+      fb_pf = tile[IN_TILE_DW];
       in_next = tile + ENC_STRIDE;
     }
 
@@ -912,9 +926,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
       const int64_t t = t_pf;
       const uint64_t fb = fb_pf;
       if (STAGED) {
-        if ((iter & (ENC_IN_T - 1)) != ENC_IN_T - 1) {
+        if ((iter & (IN_T - 1)) != IN_T - 1) {
           t_pf = (int64_t)in_next[0];
-          fb_pf = in_next[ENC_IN_TILE_DWORDS];
+          fb_pf = in_next[IN_TILE_DW];
           in_next += ENC_STRIDE;
         }
       } else {  // rotate the two-deep prefetch; request row iter + 2
@@ -1101,7 +1115,16 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
 
 template <int IN>
 constexpr size_t enc_block_smem() {
-  return ((IN == 0 || IN == 1) ? ENC_WARP_SMEM : (size_t)ENC_OUT_TILE_WORDS * 4) * ENC_WARPS;
+  return enc_warp_smem<IN>() * ENC_WARPS;
+}
+
+// tuning knob: M3TSZ_ENC_CARVEOUT_KB=K asks for a K KB shared-memory carveout (the rest of 228 KB is L1)
+static int enc_carveout_kb() {
+  static const int kb = [] {
+    const char *c = getenv("M3TSZ_ENC_CARVEOUT_KB");
+    return c ? atoi(c) : 0;
+  }();
+  return kb;
 }
 
 template <bool INT_OPT, bool PACKED, int IN>
@@ -1114,6 +1137,11 @@ static cudaError_t launch_encode_one(const EncodeParams &p, cudaStream_t stream)
   cudaError_t e = cudaFuncSetAttribute(encode_kernel<INT_OPT, PACKED, IN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  if (enc_carveout_kb() > 0) {
+    e = cudaFuncSetAttribute(encode_kernel<INT_OPT, PACKED, IN>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             enc_carveout_kb() * 100 / 228);
+    if (e != cudaSuccess) return e;
+  }
   if (PACKED) {
     const uint64_t resident = encode_packed_resident_blocks();
     if (resident == 0) return cudaErrorInvalidValue;
@@ -1132,6 +1160,8 @@ uint64_t encode_packed_resident_blocks() {
   int best = 0;
   auto probe = [&](auto kernel, size_t sm) {
     int n = 0;
+    if (enc_carveout_kb() > 0)
+      cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, enc_carveout_kb() * 100 / 228);
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) == cudaSuccess &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, ENC_WARPS * 32, sm) == cudaSuccess && n > best)
       best = n;

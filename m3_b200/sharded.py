@@ -74,8 +74,8 @@ def make_nccl_comm(codec, dist_mod, dev):
 
 def allgather_decoded(codec, comm, world, streams, offsets, lengths, gather_series, max_points, chunk_series, out=None):
     """Decode the first `gather_series` local streams and all-gather the decoded blocks; returns
-    chunk-major (ts [K, world, C, P], values, n_points [K, world, C], status [K, world, C]) on every
-    rank, K = gather_series / chunk_series: series s of rank r = [s // C, r, s % C]."""
+    (ts [K, world, C, P], values [K, world, C, P], n_points [world, G], status [world, G]) on every rank,
+    K = gather_series / chunk_series: the datapoints of series s of rank r are [s // C, r, s % C]."""
     import ctypes as C
     from . import capi
     dev = codec.device
@@ -85,8 +85,8 @@ def allgather_decoded(codec, comm, world, streams, offsets, lengths, gather_seri
     if out is None:
         out = (torch.empty((K, world, CH, P), dtype=torch.int64, device=dev),
                torch.empty((K, world, CH, P), dtype=torch.float64, device=dev),
-               torch.empty((K, world, CH), dtype=torch.int32, device=dev),
-               torch.empty((K, world, CH), dtype=torch.int32, device=dev))
+               torch.empty((world, G), dtype=torch.int32, device=dev),
+               torch.empty((world, G), dtype=torch.int32, device=dev))
     n_series = lengths.numel() if lengths is not None else offsets.numel() - 1
     rc = capi.lib().m3tsz_allgather_decoded(
         codec.ctx.handle, C.byref(codec.opts), comm, world, C.c_void_p(streams.data_ptr()), streams.numel(),
@@ -147,7 +147,7 @@ def fetch_allgather_decoded(codec, pk, P, dist_mod, dev, barrier, budget_bytes=N
             "nvlink_gbs_per_gpu": recv / (t * 1e-3) / 1e9, "nvlink_peer_peak_gbs": 770.0,
             "frac_of_nvlink": recv / (t * 1e-3) / 1e9 / 770.0,
             "gathered_dps": world * world * G * P / (t * 1e-3),
-            "api": "m3tsz_allgather_decoded (decode chunk k || ncclAllGather of chunk k-1, chunk-major result)",
+            "api": "m3tsz_allgather_decoded (decode chunk k+1 || in-place ncclAllGather of chunk k, chunk-major result, no staging)",
             "note": "config 5 in full (8 x 1M x 1440 x 16 B = 184 GB per GPU) exceeds HBM: the call gathers the "
                     "first G series of every shard; the pipeline is bound by the gather (16 B/dp over NVLink), "
                     "the decode hides behind it"}

@@ -36,7 +36,7 @@ WORKER = textwrap.dedent("""
             out = allgather_decoded(codec, comm, world, pk.packed, pk.offsets, lengths, G, P, CH)
         torch.cuda.synchronize()
         assert bool((out[3] == 0).all()) and bool((out[2] == P).all())
-        for r in range(world):  # chunk-major result: series s of rank r = [s // CH, r, s % CH]
+        for r in range(world):  # chunk-major result: series s of rank r = [s // CH, r, s mod CH]
             assert torch.equal(out[0][:, r].reshape(G, P), data[r][0][:G]), (rank, r)
             assert torch.equal(out[1][:, r].reshape(G, P).view(torch.int64), data[r][1][:G].view(torch.int64)), (rank, r)
     dist.barrier()
