@@ -66,7 +66,7 @@ enum {
   M3TSZ_ERR_VARINT_OVERFLOW = 11,  /* Go encoding/binary errOverflow */
   M3TSZ_ERR_UNEXPECTED_EOF = 12,   /* io.ErrUnexpectedEOF */
   M3TSZ_ERR_OUT_OF_ORDER = 13,     /* errOutOfOrderIterator, encoding/iterators.go:229-236 */
-  M3TSZ_ERR_TOO_MANY_ITERATORS = 14, /* > 8 replicas per series or readers per block slice */
+  M3TSZ_ERR_TOO_MANY_ITERATORS = 14, /* > 12 replicas per series or readers per block slice */
   M3TSZ_ERR_CHECKSUM_MISMATCH = 15, /* errSeekChecksumMismatch, persist/fs/seek.go:50-51, read.go:395-397 */
   /* library-level conditions */
   M3TSZ_ERR_CAPACITY = 100,        /* more datapoints / bytes than the caller's buffer holds */

@@ -781,8 +781,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
 #define M3_FIELD64(c_) \
   (((uint64_t)__funnelshift_lc(h1, h, (c_)) << 32) | (uint64_t)__funnelshift_lc(h2, h1, (c_)))
 
-      // ---- hot candidate: zero delta-of-delta, float XOR code ----
-      {
+      // ---- hot candidate: zero delta-of-delta, float XOR code (skipped once the group left the hot path) ----
+      if (group_ok) {
         uint32_t x = h << 1;
         uint32_t c = 1;
         // '0' zero DoD [+ '1' no update]: top bits 01 <=> signed h >= 0x40000000 (one compare)
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, (MODE == 1 || MODE == 2) ? M3_
         const uint64_t field = M3_FIELD64(c);
         c += (uint32_t)n;
         const bool take = __all_sync(FULL_MASK, hot || !active);
-        if (group_ok && take) {
+        if (take) {
           // every live lane: unconditional update (finished lanes compute garbage
           // they never read again)
           s.pos += c;

@@ -18,7 +18,9 @@
 
 namespace m3tsz {
 
-constexpr int MRG_K = 8;  // max replicas per series and max readers per slice
+constexpr int MRG_K = 12;  // max replicas per series and max readers per slice: up to 12 elements Go's sort.Slice
+                           // (the reference's tie order, iterators.go) is a stable insertion sort; beyond that it is
+                           // pdqsort and the order of equal timestamps is an implementation detail of the Go runtime
 constexpr int64_t kTimeMax = 0x7fffffffffffffffLL;
 
 struct Iters {  // iterators.go:45-59 (ids instead of interface values)

@@ -125,6 +125,30 @@ def test_random_replicas_and_blocks(codec, strategy):
     assert ((st_o == 100) == ((est == 0) & (en > 16))).all()
 
 
+@pytest.mark.parametrize("strategy", [0, 2])
+def test_many_replicas_and_readers(codec, strategy):
+    """up to 12 replicas per series and 12 unmerged readers per block slice (the limit of the merge:
+    the reference's sort.Slice is a stable insertion sort up to 12 elements), 13 is refused"""
+    rng = np.random.default_rng(300 + strategy)
+    series = []
+    for s in range(40):
+        n_rep = int(rng.integers(5, 13))
+        base = np.sort(rng.choice(np.arange(1, 400), size=int(rng.integers(20, 120)), replace=False))
+        replicas = []
+        for r in range(n_rep):
+            keep = base[rng.random(len(base)) < 0.8]
+            pts = [(float(k) if rng.random() < 0.7 else float(k * 10 + r), at(int(k))) for k in keep]
+            n_readers = int(rng.integers(1, 13)) if r == 0 else 1
+            replicas.append([[pts[i::n_readers] for i in range(n_readers)]])
+        series.append(replicas)
+    got, exp = gpu_merge(codec, series, strategy=strategy)
+    assert_same(got, exp)
+    # 13 replicas: refused with the documented status, like the oracle
+    pts = [(1.0, at(1)), (2.0, at(2))]
+    got, exp = gpu_merge(codec, [[[[pts]] for _ in range(13)]], strategy=strategy)
+    assert (got[3] == exp[3]).all() and int(got[3][0]) == 14
+
+
 def test_fetch_path_decode_then_merge(codec):
     """RF=3 fetch: each replica of each series = 2 blocks of real M3TSZ streams (one
     replica misses a few writes); decode all streams in one launch, merge in one launch."""
