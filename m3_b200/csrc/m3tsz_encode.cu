@@ -956,11 +956,11 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
         const uint64_t x = s.prev_bits ^ fb;
         int cl, ct;
         lz_tz(x, cl, ct);  // (64, 0) for x == 0
-        const bool zero = (x == 0);  // only possible without the int optimisation
+        const bool zero = !INT_OPT && (x == 0);  // int-optimised: a repeat is not a hot datapoint (fb != prev_bits)
         const bool cont = !zero && cl >= s.plz && ct >= s.ptz;
         const int nm = 64 - cl - ct;
         // payload left-aligned: (x >> ptz) << (64 - plen) == x << plz, (x >> ct) << (64 - nm) == x << cl
-        const uint64_t P = shl64(x, cont ? s.plz : cl);
+        const uint64_t P = shl64_clamp(x, (uint32_t)(cont ? s.plz : cl));  // (x == 0: cl = 64 shifts everything out)
         const int plen = zero ? 0 : (cont ? 64 - s.plz - s.ptz : nm);
         const uint32_t hdr = zero ? (pre << 1)
                                   : (cont ? ((pre << 2) | 2u)

@@ -1,0 +1,31 @@
+#!/usr/bin/env python3
+"""Static SASS mnemonic counts per kernel of the built library -> profiles/r02_sass_mnemonics.txt
+(memory / vote / FP64 / async-copy instructions: what proves which hardware paths the kernels use)."""
+import collections, os, re, subprocess, sys
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+lib = os.path.join(ROOT, "m3_b200", "libm3tsz_b200.so")
+sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+names = {}
+cur = None
+counts = collections.OrderedDict()
+for line in sass.splitlines():
+    m = re.search(r"Function : (\S+)", line)
+    if m:
+        cur = m.group(1)
+        counts[cur] = collections.Counter()
+        continue
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P[0-9T]+\s+)?([A-Z0-9_.]+)", line)
+    if m and cur:
+        counts[cur][m.group(1)] += 1
+        counts[cur]["__total"] += 1
+keep = re.compile(r"^(LDGSTS|LDS|STS|STG|LDG|ATOM|ATOMG|RED|VOTE|SHFL|DADD|DSETP|DMUL|DEPBAR|LDGDEPBAR|NANOSLEEP|UBLKCP|UTMALDG|SYNCS|HMMA|UTCMMA)")
+out = ["SASS mnemonic counts per kernel of libm3tsz_b200.so (cuobjdump -sass; static counts, round 2 final build).",
+       "No tensor-core or TMA instructions by design: this is a bit-manipulation path (DESIGN.md §3.2 explains why",
+       "cp.async.bulk does not fit the [quad][lane] ring); LDGSTS = cp.async, STG.E.ENL2.256 = Blackwell 256-bit stores.", ""]
+for fn, c in counts.items():
+    dem = subprocess.run(["cu++filt", fn], capture_output=True, text=True).stdout.strip() or fn
+    items = [f"{k} x{v}" for k, v in c.items() if keep.match(k)]
+    out.append(dem)
+    out.append(f"    total {c['__total']} instructions; " + ", ".join(items))
+open(os.path.join(ROOT, "profiles", "r02_sass_mnemonics.txt"), "w").write("\n".join(out) + "\n")
+print(len(counts), "kernels")
