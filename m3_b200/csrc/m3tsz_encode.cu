@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
       const uint64_t *st = reinterpret_cast<const uint64_t *>(p.ts) + (uint64_t)row0 * p.n_series + sidx;
       const uint64_t *sv = reinterpret_cast<const uint64_t *>(p.val) + (uint64_t)row0 * p.n_series + sidx;
       const uint32_t d0 = enc_smem_addr(in_tiles + ((tile & 1u) * 2u) * IN_TILE_DW + lane);
-      const uint32_t lim = (valid && s.err == 0) ? n_pts : 0u;
+      const uint32_t lim = s.err == 0 ? n_pts : 0u;  // (0 for a lane without a series)
 #pragma unroll
       for (int r = 0; r < IN_T; r++) {
         if (row0 + (uint32_t)r < lim) {
@@ -844,7 +844,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
   const uint64_t *in_next = in_tiles + lane;  // this lane's ts cell of the row to fetch next (value: + one tile)
   for (;;) {
     if (iter >= max_pts) break;  // warp-uniform (n_pts is 0 for lanes without a series)
-    const bool active = valid && s.err == 0 && iter < n_pts && !(IN == 2 && sk_pf);
+    const bool active = s.err == 0 && iter < n_pts && !(IN == 2 && sk_pf);  // (n_pts is 0 without a series)
 
     // ---- input pipeline: request tile t+1, wait for tile t ----
     if (STAGED && (iter & (IN_T - 1)) == 0) {
