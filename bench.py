@@ -429,6 +429,10 @@ def run_e2e(args, codec, ts, vals, start, P, int_opt, rank, world, dev, barrier,
     per_series_pinned = P * 16
     budget = 0.4 * available_host_bytes() / max(1, world) - 3 * chunk * P * 16
     Se = int(max(chunk, min(want, S, budget // per_series_pinned)))
+    if world > 1:  # every rank runs the same batch (the aggregate below counts Se per rank)
+        se_t = torch.tensor([Se], dtype=torch.int64, device=dev)
+        dist.all_reduce(se_t, op=dist.ReduceOp.MIN)
+        Se = int(se_t.item())
     Se = (Se // chunk) * chunk if Se >= chunk else Se
     n_chunks = (Se + chunk - 1) // chunk
     bounds = [(c * chunk, min(Se, (c + 1) * chunk)) for c in range(n_chunks)]

@@ -31,6 +31,9 @@ constexpr int ENC_IN_T = 8;     // datapoints per input tile (double buffered, c
 #ifndef M3_ENC_MIN_BLOCKS
 #define M3_ENC_MIN_BLOCKS 4
 #endif
+#ifndef M3_ENC_MIN_BLOCKS_PM
+#define M3_ENC_MIN_BLOCKS_PM 4  // point-major input stage (smaller tiles: more blocks fit)
+#endif
 constexpr int ENC_OUT_W = M3_ENC_OUT_W;   // output tile words per lane
 constexpr int ENC_GUARD = 10;   // words a single datapoint (no annotation) may add
 constexpr int ENC_OUT_TILE_WORDS = ENC_OUT_W * ENC_STRIDE;
@@ -620,7 +623,8 @@ __device__ __forceinline__ void enc_cp_async8(uint32_t dst, const void *src) {
 //         series = (tile_start + (i+1)*tile_step, Gauge.ValueOf(agg)) unless window i is empty
 //         (count == 0: skipped) -- the tile aggregation's re-encode without a gather pass.
 template <bool INT_OPT, bool PACKED, int IN>
-__global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kernel(const EncodeParams p) {
+__global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_PM : M3_ENC_MIN_BLOCKS)
+    encode_kernel(const EncodeParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -841,6 +845,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
     load_row(1, t_pf1, fb_pf1, sk_pf1);
   }
   bool steady = false;  // same s/ms/us/ns unit as the batch's and not the first datapoint
+  bool hot_ok = false;  // steady, and float mode when int-optimised: both only change on the slow path
   const uint64_t *in_next = in_tiles + lane;  // this lane's ts cell of the row to fetch next (value: + one tile)
   for (;;) {
     if (iter >= max_pts) break;  // warp-uniform (n_pts is 0 for lanes without a series)
@@ -942,8 +947,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
       // hot candidate: same (valid s/ms/us/ns) unit, zero delta-of-delta, not the
       // first datapoint, a float-mode XOR code (value is certainly not int-like)
       const int64_t delta = (int64_t)((uint64_t)t - (uint64_t)s.prev_time);
-      bool hot = active && room && steady && delta == s.prev_delta;
-      if (INT_OPT) hot = hot && s.is_float && fb != s.prev_bits && !maybe_int(v);
+      bool hot = active && room && hot_ok && delta == s.prev_delta;
+      if (INT_OPT) hot = hot && fb != s.prev_bits && !maybe_int(v);
       Tier2 c2;
       if (__all_sync(FULL_MASK, hot || !active)) {
         // every live lane: '0' (zero DoD) [+ '1' no-update] + XOR code, one merge.  The state update is
@@ -1002,6 +1007,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, M3_ENC_MIN_BLOCKS) encode_kern
           }
           // the fast tiers' slow-changing preconditions: the unit only changes here
           steady = !p.units && p.unit == s.unit && (s.unit >= 1 && s.unit <= 4) && s.n_enc > 0;
+          hot_ok = steady && (!INT_OPT || s.is_float);
         }
       }
     }

@@ -110,6 +110,10 @@ def fetch_allgather_decoded(codec, pk, P, dist_mod, dev, barrier, budget_bytes=N
     budget = int(0.6 * free) if budget_bytes is None else budget_bytes
     per_series = world * P * 16 + 2 * P * 16 // 8  # gathered + staging share
     G = int(max(1024, min(S, budget // max(1, per_series))))
+    # every rank must gather the same number of series: agree on the smallest budget
+    g = torch.tensor([G], dtype=torch.int64, device=dev)
+    dist_mod.all_reduce(g, op=dist_mod.ReduceOp.MIN)
+    G = int(g.item())
     chunk = min(G, 32768)
     G = (G // chunk) * chunk
     comm = make_nccl_comm(codec, dist_mod, dev)

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-(timeout 300 python scripts/r2_enc_pm.py) > gpurun_out/r2w_encpm.log 2>&1
-(timeout 1200 python -m pytest tests -q -m gpu -x 2>&1 | tail -4) > gpurun_out/r2w_tests.log 2>&1
-(timeout 300 python scripts/r2_quick.py 1000000 1 2>&1 | grep -E "encode|decode|dec\+ds") > gpurun_out/r2w_quick.log 2>&1
-tail -2 gpurun_out/r2w_encpm.log; tail -3 gpurun_out/r2w_tests.log; cat gpurun_out/r2w_quick.log
+(timeout 300 python scripts/r2_enc_pm.py) > gpurun_out/r2x_encpm_base.log 2>&1
+(M3TSZ_B200_LIB=$PWD/m3_b200/variants/encpm6.so timeout 300 python scripts/r2_enc_pm.py) > gpurun_out/r2x_encpm_6.log 2>&1
+(M3TSZ_ENC_CARVEOUT_KB=228 M3TSZ_B200_LIB=$PWD/m3_b200/variants/encpm6.so timeout 300 python scripts/r2_enc_pm.py) > gpurun_out/r2x_encpm_6_co228.log 2>&1
+for f in gpurun_out/r2x_*.log; do echo == $f; tail -1 $f; done
