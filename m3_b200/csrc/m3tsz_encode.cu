@@ -947,8 +947,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
       // hot candidate: same (valid s/ms/us/ns) unit, zero delta-of-delta, not the
       // first datapoint, a float-mode XOR code (value is certainly not int-like)
       const int64_t delta = (int64_t)((uint64_t)t - (uint64_t)s.prev_time);
-      bool hot = active && room && hot_ok && delta == s.prev_delta;
-      if (INT_OPT) hot = hot && fb != s.prev_bits && !maybe_int(v);
+      // (the int-likeness filter runs on the FP64 pipe for every lane: no divergent region around it)
+      const bool not_int = !INT_OPT || !maybe_int(v);
+      bool hot = (active & room & hot_ok & not_int) && delta == s.prev_delta;
+      if (INT_OPT) hot = hot && fb != s.prev_bits;
       Tier2 c2;
       if (__all_sync(FULL_MASK, hot || !active)) {
         // every live lane: '0' (zero DoD) [+ '1' no-update] + XOR code, one merge.  The state update is
