@@ -288,6 +288,18 @@ int m3tsz_encode_batch_packed(m3tsz_ctx *ctx, const m3tsz_options *opts, const i
                               uint64_t slot_bytes, uint32_t align, uint8_t *d_packed,
                               uint64_t packed_capacity, uint64_t *d_offsets, uint64_t *d_out_len,
                               int32_t *d_status, uint64_t *d_total_bytes, void *stream);
+/* ... with the optional extras of m3tsz_encode_batch_ex: point-major inputs
+ * (extras->point_major_input: d_ts / d_val are [points_stride][n_series], no per-datapoint
+ * units / annotations), LastEncoded values, stream bit lengths. */
+int m3tsz_encode_batch_packed_ex(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *d_ts,
+                                 const double *d_val, uint64_t n_series, uint64_t points_stride,
+                                 const uint32_t *d_n_points, const int64_t *d_start, int32_t unit,
+                                 const uint8_t *d_units, const uint64_t *d_ann_series_off,
+                                 const m3tsz_annotation_entry *d_ann_entries, const uint8_t *d_ann_bytes,
+                                 uint64_t slot_bytes, uint32_t align, uint8_t *d_packed,
+                                 uint64_t packed_capacity, uint64_t *d_offsets, uint64_t *d_out_len,
+                                 int32_t *d_status, uint64_t *d_total_bytes,
+                                 const m3tsz_encode_extras *extras, void *stream);
 
 /* Packs the per-series slots written by m3tsz_encode_batch into one contiguous
  * buffer (the fileset data-file layout, src/dbnode/persist/fs/write.go): fills

@@ -80,7 +80,7 @@ EXPORTED_SYMBOLS = [
     "m3tsz_compact_streams", "m3tsz_encode_batch_host", "m3tsz_decode_downsample_batch",
     "m3tsz_decode_downsample_batch_host", "m3tsz_merge_series_batch", "m3tsz_checksum_batch",
     "m3tsz_decode_batch_ex", "m3tsz_decode_downsample_last_batch", "m3tsz_encode_bound_units",
-    "m3tsz_encode_batch_packed", "m3tsz_prom_convert_batch", "m3tsz_aggregate_tiles_batch",
+    "m3tsz_encode_batch_packed", "m3tsz_encode_batch_packed_ex", "m3tsz_prom_convert_batch", "m3tsz_aggregate_tiles_batch",
     "m3tsz_encode_batch_ex", "m3tsz_fetch_batch_host", "m3tsz_merge_series_batch_ex", "m3tsz_nccl_unique_id", "m3tsz_nccl_comm_create",
     "m3tsz_nccl_comm_destroy", "m3tsz_allgather_decoded",
     "m3tsz_encoder_create", "m3tsz_encoder_destroy", "m3tsz_encoder_reset", "m3tsz_encoder_encode",
@@ -131,6 +131,9 @@ def lib():
     L.m3tsz_encode_batch_ex.restype = C.c_int
     L.m3tsz_encode_batch_ex.argtypes = [vp, po, vp, vp, u64, u64, vp, vp, i32, vp, vp, vp, vp, vp, u64,
                                         vp, vp, C.POINTER(EncodeExtras), vp]
+    L.m3tsz_encode_batch_packed_ex.restype = C.c_int
+    L.m3tsz_encode_batch_packed_ex.argtypes = [vp, po, vp, vp, u64, u64, vp, vp, i32, vp, vp, vp, vp, u64, u32,
+                                               vp, u64, vp, vp, vp, vp, C.POINTER(EncodeExtras), vp]
     L.m3tsz_encoder_create.restype = C.c_int
     L.m3tsz_encoder_create.argtypes = [vp, po, i64, pv]
     L.m3tsz_encoder_destroy.restype = None

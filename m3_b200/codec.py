@@ -218,10 +218,11 @@ class BatchCodec:
 
     def encode_packed(self, ts, values, start, unit=capi.UNIT_S, n_points=None, units=None,
                       annotations=None, align=64, capacity: Optional[int] = None, slot_bytes=0,
-                      out: Optional["PackedResult"] = None) -> "PackedResult":
+                      out: Optional["PackedResult"] = None, point_major=False) -> "PackedResult":
         """Encodes straight into one packed buffer (no slots, no compaction pass).  Streams are
-        placed in completion order: stream s = packed[offsets[s] : offsets[s] + out_len[s]]."""
-        S, P = ts.shape
+        placed in completion order: stream s = packed[offsets[s] : offsets[s] + out_len[s]].
+        point_major: ts / values are [P, S] (step-major)."""
+        S, P = (ts.shape[1], ts.shape[0]) if point_major else ts.shape
         dev = self.device
         if out is None:
             if capacity is None:
@@ -236,12 +237,15 @@ class BatchCodec:
         a_off = a_ent = a_bytes = None
         if annotations is not None:
             a_off, a_ent, a_bytes = annotations
-        rc = capi.lib().m3tsz_encode_batch_packed(
+        ex = capi.EncodeExtras()
+        ex.point_major_input = 1 if point_major else 0
+        rc = capi.lib().m3tsz_encode_batch_packed_ex(
             self.ctx.handle, C.byref(self.opts), _ptr(ts), _ptr(values), S, P, _ptr(n_points),
             _ptr(start), int(unit), _ptr(units), _ptr(a_off), _ptr(a_ent), _ptr(a_bytes),
             int(slot_bytes), int(align), _ptr(out.packed), out.packed.numel(), _ptr(out.offsets),
-            _ptr(out.out_len), _ptr(out.status), _ptr(out.total), _cuda_stream_ptr(dev))
-        self.ctx.check(rc, "m3tsz_encode_batch_packed")
+            _ptr(out.out_len), _ptr(out.status), _ptr(out.total), C.byref(ex) if point_major else None,
+            _cuda_stream_ptr(dev))
+        self.ctx.check(rc, "m3tsz_encode_batch_packed_ex")
         return out
 
     def compact(self, enc: EncodeResult, align=64, capacity: Optional[int] = None):

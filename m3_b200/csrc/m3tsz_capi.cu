@@ -296,6 +296,21 @@ int m3tsz_encode_batch_packed(m3tsz_ctx *ctx, const m3tsz_options *opts, const i
                               uint64_t slot_bytes, uint32_t align, uint8_t *d_packed,
                               uint64_t packed_capacity, uint64_t *d_offsets, uint64_t *d_out_len,
                               int32_t *d_status, uint64_t *d_total_bytes, void *stream) {
+  return m3tsz_encode_batch_packed_ex(ctx, opts, d_ts, d_val, n_series, points_stride, d_n_points, d_start, unit,
+                                      d_units, d_ann_series_off, d_ann_entries, d_ann_bytes, slot_bytes, align,
+                                      d_packed, packed_capacity, d_offsets, d_out_len, d_status, d_total_bytes,
+                                      nullptr, stream);
+}
+
+int m3tsz_encode_batch_packed_ex(m3tsz_ctx *ctx, const m3tsz_options *opts, const int64_t *d_ts,
+                                 const double *d_val, uint64_t n_series, uint64_t points_stride,
+                                 const uint32_t *d_n_points, const int64_t *d_start, int32_t unit,
+                                 const uint8_t *d_units, const uint64_t *d_ann_series_off,
+                                 const m3tsz_annotation_entry *d_ann_entries, const uint8_t *d_ann_bytes,
+                                 uint64_t slot_bytes, uint32_t align, uint8_t *d_packed,
+                                 uint64_t packed_capacity, uint64_t *d_offsets, uint64_t *d_out_len,
+                                 int32_t *d_status, uint64_t *d_total_bytes, const m3tsz_encode_extras *extras,
+                                 void *stream) {
   if (!ctx || !valid_opts(opts) || !d_total_bytes) return M3TSZ_ERR_INVALID_ARG;
   if (!(align == 1 || align == 4 || align == 8 || align == 16 || align == 32 || align == 64))
     return M3TSZ_ERR_INVALID_ARG;
@@ -343,10 +358,18 @@ int m3tsz_encode_batch_packed(m3tsz_ctx *ctx, const m3tsz_options *opts, const i
   p.packed_cursor = reinterpret_cast<unsigned long long *>(d_total_bytes);
   p.batch_counter = reinterpret_cast<unsigned long long *>(ctr);
   p.align = align;
+  if (extras) {
+    p.last_value = extras->d_last_value;
+    p.out_bits = extras->d_out_bits;
+    if (extras->point_major_input) {
+      if (d_units || d_ann_series_off) return M3TSZ_ERR_INVALID_ARG;
+      p.in_mode = 1;
+    }
+  }
   {
     // optional start-up phase spread of the persistent warps (tuning knob; measured on a B200 at
     // 1M x 1440: 0 / 250 / 500 / 800 ns per datapoint -> 13.0 / 13.2 / 13.4 / 13.6 ms, so it is off:
-    // the copy phase costs warp residency, not DRAM contention -- profiles/r02_encode_history.md)
+    // the copy phase costs warp residency, not DRAM contention -- profiles/r02_decode_history.md)
     static const long ns_per_dp = [] {
       const char *e = getenv("M3TSZ_ENC_STAGGER_NS_PER_DP");
       return e ? atol(e) : 0L;

@@ -1176,6 +1176,8 @@ uint64_t encode_packed_resident_blocks() {
   };
   probe(encode_kernel<true, true, 0>, enc_block_smem<0>());
   probe(encode_kernel<false, true, 0>, enc_block_smem<0>());
+  probe(encode_kernel<true, true, 1>, enc_block_smem<1>());
+  probe(encode_kernel<false, true, 1>, enc_block_smem<1>());
   probe(encode_kernel<true, true, 2>, enc_block_smem<2>());
   probe(encode_kernel<false, true, 2>, enc_block_smem<2>());
   return (uint64_t)sms * (uint64_t)best;
@@ -1188,7 +1190,7 @@ uint64_t encode_packed_scratch_slots(uint64_t n_series) {
   return blocks * per_block;
 }
 
-// in_mode 0: series-major inputs; 1: point-major inputs (segments output only); 2: Gauge aggregates
+// in_mode 0: series-major inputs; 1: point-major inputs; 2: Gauge aggregates
 // (packed output only)
 cudaError_t launch_encode(const EncodeParams &p, bool int_optimized, cudaStream_t stream) {
   if (p.in_mode == 2) {
@@ -1196,7 +1198,8 @@ cudaError_t launch_encode(const EncodeParams &p, bool int_optimized, cudaStream_
     return int_optimized ? launch_encode_one<true, true, 2>(p, stream) : launch_encode_one<false, true, 2>(p, stream);
   }
   if (p.in_mode == 1) {
-    if (p.packed) return cudaErrorInvalidValue;
+    if (p.packed)
+      return int_optimized ? launch_encode_one<true, true, 1>(p, stream) : launch_encode_one<false, true, 1>(p, stream);
     return int_optimized ? launch_encode_one<true, false, 1>(p, stream)
                          : launch_encode_one<false, false, 1>(p, stream);
   }

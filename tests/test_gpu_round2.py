@@ -301,6 +301,34 @@ def test_encode_packed_byte_identical(codecs, int_opt, align):
         assert (got_ts[s, : n_points[s]] == ts[s, : n_points[s]]).all()
 
 
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_encode_packed_point_major_inputs(codecs, int_opt):
+    """packed output from point-major ([point][series]) inputs, ragged lengths: every stream equals the
+    series-major segment encode (the packed placement is completion order: compare through the index)"""
+    from m3_b200 import synth
+    codec = codecs[int_opt]
+    S, P = 40_003, 97
+    ts, vals, start = synth.gaussian_walk(S, P, "cuda", seed=9)
+    vals[::7] = torch.round(vals[::7] * 100) / 100  # some int-like series
+    n_points = torch.randint(0, P + 1, (S,), dtype=torch.int32, device="cuda")
+    n_points[:64] = P
+    enc = codec.encode(ts, vals, start, unit=O.UNIT_S, n_points=n_points)
+    r = codec.encode_packed(ts.t().contiguous(), vals.t().contiguous(), start, unit=O.UNIT_S, n_points=n_points,
+                            point_major=True)
+    torch.cuda.synchronize()
+    assert torch.equal(r.status, enc.status) and torch.equal(r.out_len, enc.out_len)
+    off, ln = r.offsets.cpu().numpy(), r.out_len.cpu().numpy()
+    packed, slots = r.packed.cpu().numpy(), enc.out.cpu().numpy()
+    for s_ in list(range(0, S, 53)) + [S - 1]:
+        assert (packed[off[s_]: off[s_] + ln[s_]] == slots[s_, : ln[s_]]).all(), s_
+    # and the device-side checksums of ALL streams agree
+    a, st_a = codec.segment_checksums(r.packed, r.offsets, lengths=r.out_len)
+    flat_off = torch.arange(S, dtype=torch.int64, device="cuda") * enc.out.shape[1]
+    b, st_b = codec.segment_checksums(enc.out.view(-1), flat_off, lengths=enc.out_len)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+
+
 def test_encode_packed_many_batches_and_capacity(codecs):
     """More batches than resident warps (the persistent loop reuses its slots) + overflow."""
     from m3_b200 import synth
