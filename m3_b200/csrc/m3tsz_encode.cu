@@ -31,6 +31,9 @@ constexpr int ENC_IN_T = 8;     // datapoints per input tile (double buffered, c
 #ifndef M3_ENC_MIN_BLOCKS
 #define M3_ENC_MIN_BLOCKS 4
 #endif
+#ifndef M3_ENC_UNROLL_PM
+#define M3_ENC_UNROLL_PM 0  // 1: unroll the datapoint loop over one input tile (measured: 8.74 -> 9.54 ms, 9.6 K instructions)
+#endif
 #ifndef M3_ENC_MIN_BLOCKS_PM
 #define M3_ENC_MIN_BLOCKS_PM 4  // point-major input stage (smaller tiles: more blocks fit)
 #endif
@@ -847,12 +850,24 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
   bool steady = false;  // same s/ms/us/ns unit as the batch's and not the first datapoint
   bool hot_ok = false;  // steady, and float mode when int-optimised: both only change on the slow path
   const uint64_t *in_next = in_tiles + lane;  // this lane's ts cell of the row to fetch next (value: + one tile)
-  for (;;) {
-    if (iter >= max_pts) break;  // warp-uniform (n_pts is 0 for lanes without a series)
+  // Optional (-DM3_ENC_UNROLL_PM=1): the point-major stage walks a tile with a statically unrolled inner loop
+  // (the phase of `iter` inside the tile is the unroll index, so the tile tests below are compile-time).
+  // Measured slower (9.54 vs 8.74 ms: four copies of the three tiers do not pay for seven instructions).
+  constexpr int UNR = (IN == 1 && M3_ENC_UNROLL_PM) ? IN_T : 1;
+  bool more = true;
+  while (more) {
+#pragma unroll
+  for (int ph = 0; ph < UNR; ph++) {
+    if (iter >= max_pts) {  // warp-uniform (n_pts is 0 for lanes without a series)
+      more = false;
+      break;
+    }
+    const bool tile_first = UNR > 1 ? (ph == 0) : ((iter & (IN_T - 1)) == 0);
+    const bool tile_last = UNR > 1 ? (ph == IN_T - 1) : ((iter & (IN_T - 1)) == IN_T - 1);
     const bool active = s.err == 0 && iter < n_pts && !(IN == 2 && sk_pf);  // (n_pts is 0 without a series)
 
     // ---- input pipeline: request tile t+1, wait for tile t ----
-    if (STAGED && (iter & (IN_T - 1)) == 0) {
+    if (STAGED && tile_first) {
       __syncwarp();  // everyone is done reading the buffer about to be overwritten
       stage(iter / IN_T + 1);
       asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -931,7 +946,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
       const int64_t t = t_pf;
       const uint64_t fb = fb_pf;
       if (STAGED) {
-        if ((iter & (IN_T - 1)) != IN_T - 1) {
+        if (!tile_last) {
           t_pf = (int64_t)in_next[0];
           fb_pf = in_next[IN_TILE_DW];
           in_next += ENC_STRIDE;
@@ -1014,7 +1029,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
       }
     }
     iter++;
-  }
+  }  // ph
+  }  // while (more)
   if (STAGED) asm volatile("cp.async.wait_all;\n" ::: "memory");
 
   // ---- tail: end-of-stream marker + zero padding (scheme.go:198-211) ----
