@@ -15,7 +15,9 @@
 //   m3tsz/float_encoder_iterator.go:69-103, m3tsz/int_sig_bits_tracker.go:35-91,
 //   m3tsz/m3tsz.go:78-119, ostream.go:133-221, scheme.go:198-220.
 #include <cstdlib>
+#include <cstring>
 #include <cub/device/device_scan.cuh>
+#include <cuda.h>  // CUtensorMap (types only: the encoder is resolved through cudaGetDriverEntryPoint)
 
 #include "m3tsz_common.cuh"
 #include "m3tsz_kernels.h"
@@ -45,13 +47,43 @@ constexpr int ENC_OUT_TILE_WORDS = ENC_OUT_W * ENC_STRIDE;
 #endif
 // input stage IN: 0 series-major tiles (8 rows: one 64-byte segment per series and array), 1 point-major
 // tiles, 2 Gauge aggregates read directly (no input tiles)
+#ifndef M3_ENC_BULK_PM
+// 1: the point-major input stage (IN = 1) fills its tiles with TMA 1-D bulk copies (cp.async.bulk, one 256-byte
+// row of 32 series per copy, issued by one lane, completion on a per-warp mbarrier) whenever a batch is a full
+// warp of equally long series and the arrays / row pitch are 16-byte aligned; other batches keep the lane-local
+// 8-byte cp.async fills.  A tile row is then 32 datapoints exactly (no padding column: bulk destinations must be
+// 16-byte aligned and the lane-local reads are conflict-free either way).
+// 2: the same tiles by TMA TENSOR copies: the arrays are described as 2-D tensors [points][series] of 8-byte
+// elements (cuTensorMapEncodeTiled, box = IN_T rows x 32 series), so one cp.async.bulk.tensor.2d per array moves a
+// whole tile; rows past the end and series past n_series are zero-filled by the hardware, which makes ragged
+// batches and the last partial tile the same code.  Needs 16-byte aligned arrays and an even n_series < 2^31,
+// else the cp.async fills.
+#define M3_ENC_BULK_PM 0
+#endif
 template <int IN>
 __host__ __device__ constexpr int enc_in_t() {
   return IN == 1 ? M3_ENC_IN_T_PM : ENC_IN_T;
 }
 template <int IN>
+__host__ __device__ constexpr int enc_bulk() {
+  return IN == 1 ? M3_ENC_BULK_PM : 0;
+}
+// the two tensor maps of the point-major input arrays (M3_ENC_BULK_PM == 2), a __grid_constant__ kernel parameter
+struct EncTensorMaps {
+  alignas(64) CUtensorMap ts;
+  alignas(64) CUtensorMap val;
+  int ok;  // 0: not built (unaligned arrays, odd n_series, no driver entry point): cp.async fills
+};
+// datapoints (8-byte cells) per input tile row
+template <int IN>
+__host__ __device__ constexpr int enc_in_stride() {
+  return enc_bulk<IN>() ? 32 : ENC_STRIDE;
+}
+template <int IN>
 __host__ __device__ constexpr size_t enc_warp_smem() {
-  return ((IN == 0 || IN == 1) ? 4 * (size_t)(enc_in_t<IN>() * ENC_STRIDE) * 8 : 0) + (size_t)ENC_OUT_TILE_WORDS * 4;
+  const size_t raw = ((IN == 0 || IN == 1) ? 4 * (size_t)(enc_in_t<IN>() * enc_in_stride<IN>()) * 8 : 0) +
+                     (size_t)ENC_OUT_TILE_WORDS * 4 + (enc_bulk<IN>() ? 16 : 0);  // (+ two mbarriers per warp)
+  return enc_bulk<IN>() == 2 ? ((raw + 127) & ~(size_t)127) : raw;  // tensor copies land on 128-byte boundaries
 }
 
 struct EncLane {
@@ -606,6 +638,43 @@ __device__ __forceinline__ uint32_t enc_smem_addr(const void *p) {
 __device__ __forceinline__ void enc_cp_async8(uint32_t dst, const void *src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
 }
+// ---- TMA 1-D bulk copies + mbarrier (M3_ENC_BULK_PM) ----
+__device__ __forceinline__ void enc_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void enc_mbar_init_fence() {
+  // make the initialised barriers visible to the async proxy (the bulk copies' complete_tx)
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void enc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned), completion counted
+// in bytes on the mbarrier
+__device__ __forceinline__ void enc_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// one box of a 2-D tensor (tensor map in param space) -> shared memory; c0 = innermost coordinate
+__device__ __forceinline__ void enc_tma_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void enc_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "ENC_MBAR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra ENC_MBAR_DONE;\n\t"
+      "bra ENC_MBAR_WAIT;\n"
+      "ENC_MBAR_DONE:\n\t}"
+      ::"r"(bar), "r"(parity)
+      : "memory");
+}
 
 // PACKED = false: one warp per 32-series batch, every series writes its own slot
 //   p.out + s * p.out_stride (fixed stride).
@@ -627,20 +696,45 @@ __device__ __forceinline__ void enc_cp_async8(uint32_t dst, const void *src) {
 //         (count == 0: skipped) -- the tile aggregation's re-encode without a gather pass.
 template <bool INT_OPT, bool PACKED, int IN>
 __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_PM : M3_ENC_MIN_BLOCKS)
-    encode_kernel(const EncodeParams p) {
-  extern __shared__ __align__(16) uint32_t smem[];
+    encode_kernel(const EncodeParams p
+#if M3_ENC_BULK_PM == 2
+                  ,
+                  const __grid_constant__ EncTensorMaps tmaps
+#endif
+    ) {
+  extern __shared__ __align__(128) uint32_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   // the direct input stages (IN != 0) need no input tiles: only the output tile lives in shared memory
   constexpr bool STAGED = (IN == 0 || IN == 1);  // inputs go through the shared-memory tiles
   constexpr int IN_T = enc_in_t<IN>();  // datapoints per input tile
-  constexpr int IN_TILE_DW = IN_T * ENC_STRIDE;  // one array (ts or val), one buffer
+  constexpr int IN_STRIDE = enc_in_stride<IN>();  // cells per tile row
+  constexpr int IN_TILE_DW = IN_T * IN_STRIDE;  // one array (ts or val), one buffer
+  constexpr int BULK = enc_bulk<IN>();  // 0 cp.async fills, 1 1-D bulk copies per row, 2 one 2-D tensor copy per array
   constexpr size_t WARP_SMEM = enc_warp_smem<IN>();
   uint8_t *wbase = reinterpret_cast<uint8_t *>(smem) + warp * WARP_SMEM;
   // in_tiles: [buffer][array (0 ts, 1 val)][row][lane]
   uint64_t *in_tiles = reinterpret_cast<uint64_t *>(wbase);
   uint32_t *out_tile = STAGED ? reinterpret_cast<uint32_t *>(in_tiles + 4 * IN_TILE_DW)
                               : reinterpret_cast<uint32_t *>(wbase);
+
+  // BULK: two mbarriers per warp (one per tile buffer) behind the output tile; `bulk_seq` counts the tiles this
+  // warp has requested through them (buffer = seq & 1, phase parity = (seq >> 1) & 1), across batches
+  const uint32_t mbar0 = BULK ? enc_smem_addr(out_tile + ENC_OUT_TILE_WORDS) : 0u;
+  uint32_t bulk_seq = 0;
+#if M3_ENC_BULK_PM == 2
+  const bool bulk_args = BULK && tmaps.ok != 0;
+#else
+  const bool bulk_args = BULK && ((((uintptr_t)p.ts | (uintptr_t)p.val) & 15u) == 0) && ((p.n_series & 1ull) == 0);
+#endif
+  if (BULK) {
+    if (lane == 0) {
+      enc_mbar_init(mbar0, 1);
+      enc_mbar_init(mbar0 + 8, 1);
+      enc_mbar_init_fence();
+    }
+    __syncwarp();
+  }
 
   const uint64_t n_batches = (p.n_series + 31) >> 5;
   const uint64_t warp_slot = (uint64_t)blockIdx.x * ENC_WARPS + warp;  // PACKED: scratch slot set
@@ -766,9 +860,47 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
   const int st_arr = (lane >> 3) & 1;
   const int st_jo = lane >> 4;
   const bool uniform_n = __all_sync(FULL_MASK, !valid || n_pts == max_pts) && __all_sync(FULL_MASK, valid);
+  // this batch's tiles come by bulk copy: a full warp of series of one length (rows of 32 x 8 bytes, all in range)
+  // (tensor copies zero-fill what is out of range, so they serve every batch)
+  const bool bulk = BULK && bulk_args && (BULK == 2 || uniform_n);
+  const uint32_t tile_base = bulk ? bulk_seq : 0u;  // buffer of tile t: (tile_base + t) & 1
   auto stage = [&](uint32_t tile) {
     const uint32_t row0 = tile * IN_T;
     if (row0 >= max_pts) return;
+#if M3_ENC_BULK_PM == 2
+    if (BULK == 2 && bulk) {
+      if (lane == 0) {
+        const uint32_t g = tile_base + tile;
+        const uint32_t bar = mbar0 + (g & 1u) * 8u;
+        enc_mbar_expect_tx(bar, 2u * (uint32_t)IN_TILE_DW * 8u);  // the whole box counts, in range or not
+        const uint32_t d0 = enc_smem_addr(in_tiles + ((g & 1u) * 2u) * IN_TILE_DW);
+        enc_tma_2d(d0, &tmaps.ts, (int)warp_s0, (int)row0, bar);
+        enc_tma_2d(d0 + (uint32_t)IN_TILE_DW * 8u, &tmaps.val, (int)warp_s0, (int)row0, bar);
+      }
+      return;
+    }
+#endif
+    if (BULK == 1 && bulk) {
+      if (lane == 0) {
+        const uint32_t g = tile_base + tile;
+        const uint32_t bar = mbar0 + (g & 1u) * 8u;
+        const uint32_t nrow = (max_pts - row0 < (uint32_t)IN_T) ? max_pts - row0 : (uint32_t)IN_T;
+        enc_mbar_expect_tx(bar, nrow * 512u);
+        const uint64_t *st = reinterpret_cast<const uint64_t *>(p.ts) + (uint64_t)row0 * p.n_series + warp_s0;
+        const uint64_t *sv = reinterpret_cast<const uint64_t *>(p.val) + (uint64_t)row0 * p.n_series + warp_s0;
+        const uint32_t d0 = enc_smem_addr(in_tiles + ((g & 1u) * 2u) * IN_TILE_DW);
+#pragma unroll
+        for (int r = 0; r < IN_T; r++) {
+          if ((uint32_t)r < nrow) {
+            enc_bulk_g2s(d0 + (uint32_t)(r * IN_STRIDE) * 8u, st, 256u, bar);
+            enc_bulk_g2s(d0 + (uint32_t)(IN_TILE_DW + r * IN_STRIDE) * 8u, sv, 256u, bar);
+          }
+          st += p.n_series;
+          sv += p.n_series;
+        }
+      }
+      return;
+    }
     if (IN == 1) {
       // point-major inputs: a row of the tile is 32 consecutive elements of the array -- every lane
       // copies its own column (8 rows x 2 arrays), sources coalesced across the warp, no shuffles
@@ -779,8 +911,8 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
 #pragma unroll
       for (int r = 0; r < IN_T; r++) {
         if (row0 + (uint32_t)r < lim) {
-          enc_cp_async8(d0 + (uint32_t)(r * ENC_STRIDE) * 8u, st);
-          enc_cp_async8(d0 + (uint32_t)(IN_TILE_DW + r * ENC_STRIDE) * 8u, sv);
+          enc_cp_async8(d0 + (uint32_t)(r * IN_STRIDE) * 8u, st);
+          enc_cp_async8(d0 + (uint32_t)(IN_TILE_DW + r * IN_STRIDE) * 8u, sv);
         }
         st += p.n_series;
         sv += p.n_series;
@@ -791,7 +923,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
                                   : reinterpret_cast<const uint64_t *>(p.ts)) +
                           (warp_s0 + st_jo) * p.points_stride + row0 + st_r;
     const uint32_t dst0 = enc_smem_addr(in_tiles + ((tile & 1u) * 2u + (uint32_t)st_arr) * IN_TILE_DW +
-                                        st_r * ENC_STRIDE + st_jo);
+                                        st_r * IN_STRIDE + st_jo);
     const uint64_t step = 2ull * p.points_stride;
     if (uniform_n && row0 + IN_T <= max_pts) {
 #pragma unroll
@@ -810,7 +942,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
 
   if (STAGED) {
     stage(0);
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    if (!(BULK && bulk)) asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
   // direct input stages: element `row` of this lane's series
   auto load_row = [&](uint32_t row, int64_t &t_o, uint64_t &v_o, bool &skip_o) {
@@ -870,14 +1002,19 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
     if (STAGED && tile_first) {
       __syncwarp();  // everyone is done reading the buffer about to be overwritten
       stage(iter / IN_T + 1);
-      asm volatile("cp.async.commit_group;\n" ::: "memory");
-      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+      const uint32_t g = tile_base + iter / IN_T;  // (tile_base is 0 unless this batch is bulk-filled)
+      if (BULK && bulk) {
+        enc_mbar_wait(mbar0 + (g & 1u) * 8u, (g >> 1) & 1u);  // every lane: the tile's bytes have landed
+      } else {
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+      }
       __syncwarp();
       // row 0 of the tile that just landed; rows 1..7 are fetched one datapoint ahead below
-      const uint64_t *tile = in_tiles + (((iter / IN_T) & 1u) * 2u) * IN_TILE_DW + lane;
+      const uint64_t *tile = in_tiles + ((g & 1u) * 2u) * IN_TILE_DW + lane;
       t_pf = (int64_t)tile[0];
       fb_pf = tile[IN_TILE_DW];
-      in_next = tile + ENC_STRIDE;
+      in_next = tile + IN_STRIDE;
     }
 
     // ---- make room in the output tile ----
@@ -949,7 +1086,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
         if (!tile_last) {
           t_pf = (int64_t)in_next[0];
           fb_pf = in_next[IN_TILE_DW];
-          in_next += ENC_STRIDE;
+          in_next += IN_STRIDE;
         }
       } else {  // rotate the two-deep prefetch; request row iter + 2
         t_pf = t_pf1;
@@ -1032,6 +1169,7 @@ __global__ void __launch_bounds__(ENC_WARPS * 32, (IN == 1) ? M3_ENC_MIN_BLOCKS_
   }  // ph
   }  // while (more)
   if (STAGED) asm volatile("cp.async.wait_all;\n" ::: "memory");
+  if (BULK && bulk) bulk_seq += (max_pts + (uint32_t)IN_T - 1u) / (uint32_t)IN_T;  // every requested tile was waited for
 
   // ---- tail: end-of-stream marker + zero padding (scheme.go:198-211) ----
   uint64_t total_bits = 0;
@@ -1151,6 +1289,44 @@ static int enc_carveout_kb() {
   return kb;
 }
 
+#if M3_ENC_BULK_PM == 2
+// Tensor maps of the point-major input arrays: ts / val as [points_stride][n_series] tensors of 8-byte elements,
+// box = enc_in_t<1>() rows x 32 series, no swizzle, zero fill outside.  ok = 0 when the arrays cannot be described
+// (then the kernel keeps its cp.async fills).
+static void enc_build_tensor_maps(const EncodeParams &p, EncTensorMaps &tm) {
+  memset(&tm, 0, sizeof(tm));
+  typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                      CUtensorMapFloatOOBfill);
+  static encode_tiled_fn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<encode_tiled_fn>(f);
+  }();
+  if (!fn || getenv("M3TSZ_ENC_NO_TMA")) return;
+  if (p.in_mode != 1 || !p.ts || !p.val) return;
+  if ((((uintptr_t)p.ts | (uintptr_t)p.val) & 15u) != 0) return;
+  if ((p.n_series & 1ull) != 0 || p.n_series >= (1ull << 31) || p.points_stride == 0 ||
+      p.points_stride >= (1ull << 31))
+    return;
+  const cuuint64_t dims[2] = {(cuuint64_t)p.n_series, (cuuint64_t)p.points_stride};
+  const cuuint64_t strides[1] = {(cuuint64_t)p.n_series * 8ull};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)enc_in_t<1>()};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult a = fn(&tm.ts, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<int64_t *>(p.ts), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult b = fn(&tm.val, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<double *>(p.val), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  tm.ok = (a == CUDA_SUCCESS && b == CUDA_SUCCESS) ? 1 : 0;
+}
+#endif
+
 template <bool INT_OPT, bool PACKED, int IN>
 static cudaError_t launch_encode_one(const EncodeParams &p, cudaStream_t stream) {
   constexpr size_t smem = enc_block_smem<IN>();
@@ -1171,7 +1347,13 @@ static cudaError_t launch_encode_one(const EncodeParams &p, cudaStream_t stream)
     if (resident == 0) return cudaErrorInvalidValue;
     if (blocks > resident) blocks = resident;
   }
+#if M3_ENC_BULK_PM == 2
+  EncTensorMaps tm;
+  enc_build_tensor_maps(p, tm);  // (ok = 0 for the other input stages)
+  encode_kernel<INT_OPT, PACKED, IN><<<(unsigned)blocks, ENC_WARPS * 32, smem, stream>>>(p, tm);
+#else
   encode_kernel<INT_OPT, PACKED, IN><<<(unsigned)blocks, ENC_WARPS * 32, smem, stream>>>(p);
+#endif
   return cudaGetLastError();
 }
 

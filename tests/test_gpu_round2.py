@@ -712,3 +712,59 @@ def test_point_major_encode_byte_identical(codecs, int_opt):
         dps, err = O.decode_all(oa[s, : la[s]].tobytes(), int_opt)
         exp = O.encode_series([d[0] for d in dps], [d[1] for d in dps], start, O.UNIT_S, int_opt)
         assert oc[s, : lc[s]].tobytes() == exp, s
+
+
+@pytest.mark.parametrize("int_opt", [True, False])
+@pytest.mark.parametrize("S,P", [(64, 1), (64, 130), (518, 7), (4098, 130), (33_000, 61)])
+def test_point_major_encode_even_series_counts(codecs, int_opt, S, P):
+    """Point-major inputs with an EVEN series count (16-byte aligned row pitch: the shape the tensor-copy input
+    stage of a -DM3_ENC_BULK_PM=2 build describes with a tensor map; odd counts take the cp.async fills): full and
+    ragged warps, point counts that end inside a tile, ragged lengths, segment and packed output, and array bases
+    that are only 8-byte aligned.  Every stream equals the series-major encode (itself oracle-pinned)."""
+    rng = np.random.default_rng(1000 + S + P)
+    ts, vals, start = _mixed(rng, S, P)
+    codec = codecs[int_opt]
+    d_ts, d_vals = torch.from_numpy(ts).cuda(), torch.from_numpy(vals).cuda()
+    d_start = torch.full((S,), start, dtype=torch.int64, device="cuda")
+    pm_ts, pm_vals = d_ts.t().contiguous(), d_vals.t().contiguous()
+    for ragged in (False, True):
+        d_n = None
+        if ragged:
+            n_points = rng.integers(0, P + 1, size=S).astype(np.int32)
+            n_points[: min(S, 96)] = P  # whole warps of full length next to ragged ones
+            d_n = torch.from_numpy(n_points).cuda()
+        a = codec.encode(d_ts, d_vals, d_start, unit=O.UNIT_S, n_points=d_n)
+        b = codec.encode(pm_ts, pm_vals, d_start, unit=O.UNIT_S, n_points=d_n, point_major=True)
+        r = codec.encode_packed(pm_ts, pm_vals, d_start, unit=O.UNIT_S, n_points=d_n, point_major=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a.status, b.status) and torch.equal(a.out_len, b.out_len)
+        assert torch.equal(a.status, r.status) and torch.equal(a.out_len, r.out_len)
+        la, oa, ob = a.out_len.cpu().numpy(), a.out.cpu().numpy(), b.out.cpu().numpy()
+        off, packed = r.offsets.cpu().numpy(), r.packed.cpu().numpy()
+        step = max(1, S // 600)
+        for s in list(range(0, S, step)) + [S - 1]:
+            assert (oa[s, : la[s]] == ob[s, : la[s]]).all(), (s, ragged)
+            assert (packed[off[s]: off[s] + la[s]] == oa[s, : la[s]]).all(), (s, ragged)
+        # all streams through the device-side checksums
+        flat = torch.arange(S, dtype=torch.int64, device="cuda") * a.out.shape[1]
+        ca, _ = codec.segment_checksums(a.out.view(-1), flat, lengths=a.out_len)
+        cb, _ = codec.segment_checksums(b.out.view(-1), flat, lengths=b.out_len)
+        cr, _ = codec.segment_checksums(r.packed, r.offsets, lengths=r.out_len)
+        torch.cuda.synchronize()
+        assert torch.equal(ca, cb) and torch.equal(ca, cr), ragged
+    # bases that are 8- but not 16-byte aligned (views one element into a larger allocation)
+    big_t = torch.empty(P * S + 1, dtype=torch.int64, device="cuda")
+    big_v = torch.empty(P * S + 1, dtype=torch.float64, device="cuda")
+    u_ts, u_vals = big_t[1:].view(P, S), big_v[1:].view(P, S)
+    u_ts.copy_(pm_ts)
+    u_vals.copy_(pm_vals)
+    assert u_ts.data_ptr() % 16 == 8
+    a = codec.encode(d_ts, d_vals, d_start, unit=O.UNIT_S)
+    c = codec.encode(u_ts, u_vals, d_start, unit=O.UNIT_S, point_major=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a.out_len, c.out_len) and torch.equal(a.status, c.status)
+    flat = torch.arange(S, dtype=torch.int64, device="cuda") * a.out.shape[1]
+    ca, _ = codec.segment_checksums(a.out.view(-1), flat, lengths=a.out_len)
+    cc, _ = codec.segment_checksums(c.out.view(-1), flat, lengths=c.out_len)
+    torch.cuda.synchronize()
+    assert torch.equal(ca, cc)

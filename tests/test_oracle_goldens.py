@@ -420,6 +420,67 @@ def test_convert_to_int_float():
         assert O.lib().m3o_convert_from_int_float(val, m) == x
 
 
+def _go_itoa_pad(dec, num_dec):
+    s = str(dec)
+    return s + "0" * (num_dec - len(s)) if len(s) < num_dec else s
+
+
+@pytest.mark.parametrize("num_dig,num_dec,neg", [
+    (0, 0, False), (1, 0, False), (2, 0, False), (10, 0, False), (18, 0, False),   # TestCountConversions :34-40
+    (0, 6, False), (1, 6, False), (3, 6, False), (5, 6, False), (7, 6, False),      # TestTimerConversions :42-48
+    (0, 1, False), (0, 3, False), (1, 3, False), (3, 3, False), (5, 3, False), (7, 3, False),  # SmallGauge :50-57
+    (1, 0, True), (3, 0, True), (1, 2, True), (3, 2, True),                         # NegativeGauge :71-76
+])
+def test_convert_to_int_float_reference_int_families(num_dig, num_dec, neg):
+    """m3tsz_test.go:102-136 (validateIntConversions), the reference's own property test restated family by
+    family: decimal strings "<dig>.<dec>" parsed to float64 convert to the integer "<dig><dec padded>" with a
+    multiplier <= numDec, starting from curMaxMult = numDec."""
+    r = random.Random(1000 * num_dig + 10 * num_dec + int(neg))
+    dig_mod, dec_mod = 10 ** num_dig, 10 ** num_dec
+    sign = -1.0 if neg else 1.0
+    for _ in range(1000):
+        dig, dec = r.getrandbits(62) % dig_mod, r.getrandbits(62) % dec_mod
+        if num_dec == 0:
+            val = sign * float(dig)
+            iv, m, isf, err = O.convert_to_int_float(val, num_dec)
+            assert err == 0 and not isf and iv == val and m <= 0, (dig, dec)
+        else:
+            val = float("%d.%d" % (dig, dec))
+            expected = int(str(dig) + _go_itoa_pad(dec, num_dec))
+            iv, m, isf, err = O.convert_to_int_float(sign * val, num_dec)
+            assert err == 0 and not isf and iv == sign * float(expected) and m <= num_dec, (dig, dec, iv, m)
+
+
+@pytest.mark.parametrize("num_dig,num_dec", [(0, 16), (1, 16), (5, 16),   # TestPreciseGaugeConversions :59-63
+                                             (9, 2), (10, 3), (11, 3)])    # TestLargeGaugeConversions :65-69
+def test_convert_to_int_float_reference_float_families(num_dig, num_dec):
+    """m3tsz_test.go:138-183 (testFloatConversions / validateConvertFloat): either the value stays a float
+    (returned unchanged, multiplier 0) or the integer found reproduces it to within 10^-mult."""
+    r = random.Random(77 * num_dig + num_dec)
+    dig_mod, dec_mod = 10 ** num_dig, 10 ** num_dec
+    for _ in range(1000):
+        dig, dec = r.getrandbits(62) % dig_mod, r.getrandbits(62) % dec_mod
+        val = float(str(dig) + "." + _go_itoa_pad(dec, num_dec))
+        v, m, isf, err = O.convert_to_int_float(val, 0)
+        assert err == 0
+        if isf:
+            assert v == val and m == 0
+        else:
+            assert abs(val - v / 10.0 ** m) < 1.0 / 10.0 ** m, (val, v, m)
+
+
+def test_convert_to_int_float_inf_nan_and_from():
+    """m3tsz_test.go:78-100: TestConvertFromIntFloat, TestInfNan (every curMaxMult), TestInvalidMult."""
+    for val, mult, exp in ((1.0, 0, 1.0), (2.0, 0, 2.0), (10.0, 1, 1.0), (200.0, 2, 2.0)):
+        assert O.lib().m3o_convert_from_int_float(val, mult) == exp
+    for cur in (0, 3, 6):
+        for bad in (float("inf"), float("-inf")):
+            assert O.convert_to_int_float(bad, cur) == (bad, 0, True, 0)
+        v, m, isf, err = O.convert_to_int_float(float("nan"), cur)
+        assert v != v and m == 0 and isf and err == 0
+    assert O.convert_to_int_float(1.0, 7)[3] != 0
+
+
 def test_xxh64_known_answers():
     # XXH64 seed 0 published test values
     assert O.lib().m3o_xxh64(None, 0) == 0xEF46DB3751D8E999
