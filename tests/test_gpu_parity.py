@@ -538,3 +538,56 @@ def test_full_size_roundtrip_properties(codecs, int_opt):
         _, ovals, oerr, _ = oracle_decode(o_out[k, : o_len[k]].tobytes(), int_opt)
         assert oerr == 0 and (g_dec[k] == ovals).all()
     assert total >= int(enc.out_len.sum().item())
+
+
+def test_convert_to_int_float_reference_families_on_device(codecs):
+    """Row A8: the value families of the reference's own convertToIntFloat property tests
+    (m3tsz_test.go:34-76: counts up to 18 digits, timers with 6 decimals, small / precise / large / negative
+    gauges), one family per series and one family per warp, through the int-optimised ENCODE KERNEL: byte-identical
+    to the oracle (whose classifier passes those property tests on the CPU, tests/test_oracle_goldens.py), and the
+    decode of the device streams equals the oracle's decode."""
+    fams = [(0, 0, 1), (1, 0, 1), (2, 0, 1), (10, 0, 1), (18, 0, 1),
+            (0, 6, 1), (1, 6, 1), (3, 6, 1), (5, 6, 1), (7, 6, 1),
+            (0, 1, 1), (0, 3, 1), (1, 3, 1), (3, 3, 1), (5, 3, 1), (7, 3, 1),
+            (0, 16, 1), (1, 16, 1), (5, 16, 1), (9, 2, 1), (10, 3, 1), (11, 3, 1),
+            (1, 0, -1), (3, 0, -1), (1, 2, -1), (3, 2, -1)]
+    import random
+    r = random.Random(2024)
+    START = 1599955200 * SEC
+    P = 120
+    n_f = len(fams)
+    S = n_f * 2 + n_f * 32  # two mixed-warp series + one whole warp per family
+    vals = np.zeros((S, P), dtype=np.float64)
+
+    def draw(num_dig, num_dec, sign):
+        dig, dec = r.getrandbits(62) % 10 ** num_dig, r.getrandbits(62) % 10 ** num_dec
+        if num_dec == 0:
+            return sign * float(dig)
+        d = str(dec)
+        if num_dec >= 16:  # testFloatConversions pads the decimals to numDec digits
+            d = d + "0" * (num_dec - len(d))
+        return sign * float("%d.%s" % (dig, d))
+
+    for s in range(S):
+        f = fams[s % n_f] if s < 2 * n_f else fams[(s - 2 * n_f) // 32]
+        vals[s] = [draw(*f) for _ in range(P)]
+    ts = np.tile(START + np.arange(1, P + 1, dtype=np.int64) * 10 * SEC, (S, 1))
+    codec = codecs[True]
+    o_out, o_len, o_st = O.encode_batch(ts, vals, START, O.UNIT_S, True, n_threads=8)
+    assert (o_st == 0).all()
+    enc = codec.encode(torch.from_numpy(ts).cuda(), torch.from_numpy(vals).cuda(),
+                       torch.full((S,), START, dtype=torch.int64, device="cuda"), unit=O.UNIT_S)
+    torch.cuda.synchronize()
+    g_len, g_out = enc.out_len.cpu().numpy(), enc.out.cpu().numpy()
+    assert (enc.status.cpu().numpy() == 0).all()
+    for s in range(S):
+        assert g_len[s] == o_len[s], (s, g_len[s], o_len[s])
+        assert (g_out[s, : g_len[s]] == o_out[s, : o_len[s]]).all(), s
+    packed, offsets = codec.compact(enc, align=1)
+    dec = codec.decode(packed, offsets, P)
+    torch.cuda.synchronize()
+    assert (dec.status.cpu().numpy() == 0).all() and (dec.n_points.cpu().numpy() == P).all()
+    gv = dec.values.cpu().numpy().view(np.uint64)
+    for s in range(0, S, 7):
+        _, ovals, oerr, _ = oracle_decode(o_out[s, : o_len[s]].tobytes(), True)
+        assert oerr == 0 and (gv[s] == ovals.view(np.uint64)).all(), s
