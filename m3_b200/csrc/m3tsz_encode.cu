@@ -43,7 +43,11 @@ constexpr int ENC_OUT_W = M3_ENC_OUT_W;   // output tile words per lane
 constexpr int ENC_GUARD = 10;   // words a single datapoint (no annotation) may add
 constexpr int ENC_OUT_TILE_WORDS = ENC_OUT_W * ENC_STRIDE;
 #ifndef M3_ENC_IN_T_PM
-#define M3_ENC_IN_T_PM 4  // rows per input tile of the point-major input stage (IN = 1): 9.60 / 9.10 / 9.58 ms for 8 / 4 / 2
+// rows per input tile of the point-major input stage (IN = 1).  With the cp.async fills: 9.60 / 9.10 / 9.58 ms for
+// 8 / 4 / 2 rows (a smaller tile leaves more L1 to the fills).  With tensor copies (M3_ENC_BULK_PM = 2, which do not
+// allocate L1 lines) one copy per array costs the same whatever the box: 8.65 ms with 8 rows, 9.06 with 4 (the
+// cp.async build of the same day: 8.73).
+#define M3_ENC_IN_T_PM 8
 #endif
 // input stage IN: 0 series-major tiles (8 rows: one 64-byte segment per series and array), 1 point-major
 // tiles, 2 Gauge aggregates read directly (no input tiles)
@@ -57,8 +61,9 @@ constexpr int ENC_OUT_TILE_WORDS = ENC_OUT_W * ENC_STRIDE;
 // elements (cuTensorMapEncodeTiled, box = IN_T rows x 32 series), so one cp.async.bulk.tensor.2d per array moves a
 // whole tile; rows past the end and series past n_series are zero-filled by the hardware, which makes ragged
 // batches and the last partial tile the same code.  Needs 16-byte aligned arrays and an even n_series < 2^31,
-// else the cp.async fills.
-#define M3_ENC_BULK_PM 0
+// else the cp.async fills.  Measured at 1 M x 1440 (profiles/r02_decode_history.md): 0 -> 8.73 ms (4-row tiles),
+// 2 -> 8.65 ms with 8-row tiles / 9.06 with 4-row tiles; the full GPU suite is green on the build with 2.
+#define M3_ENC_BULK_PM 2
 #endif
 template <int IN>
 __host__ __device__ constexpr int enc_in_t() {

@@ -20,8 +20,11 @@ for line in sass.splitlines():
         counts[cur]["__total"] += 1
 keep = re.compile(r"^(LDGSTS|LDS|STS|STG|LDG|ATOM|ATOMG|RED|VOTE|SHFL|DADD|DSETP|DMUL|DEPBAR|LDGDEPBAR|NANOSLEEP|UBLKCP|UTMALDG|SYNCS|HMMA|UTCMMA)")
 out = ["SASS mnemonic counts per kernel of libm3tsz_b200.so (cuobjdump -sass; static counts, round 2 final build).",
-       "No tensor-core or TMA instructions by design: this is a bit-manipulation path (DESIGN.md §3.2 explains why",
-       "cp.async.bulk does not fit the [quad][lane] ring); LDGSTS = cp.async, STG.E.ENL2.256 = Blackwell 256-bit stores.", ""]
+       "No tensor-core instructions by design: this is a bit-manipulation path.  TMA where a tile is a rectangle of the",
+       "array: the point-major encode input stage (encode_kernel<., ., 1>) fills its tiles with UTMALDG.2D tensor copies",
+       "completed on mbarriers (SYNCS.ARRIVE.TRANS64 = arrive.expect_tx, SYNCS.PHASECHK.TRANS64.TRYWAIT = try_wait.parity);",
+       "the decoders' [quad][lane] ring is filled lane-locally (DESIGN.md §3.2 explains why bulk copies do not fit it).",
+       "LDGSTS = cp.async, STG.E.ENL2.256 = Blackwell 256-bit stores.", ""]
 for fn, c in counts.items():
     dem = subprocess.run(["cu++filt", fn], capture_output=True, text=True).stdout.strip() or fn
     items = [f"{k} x{v}" for k, v in c.items() if keep.match(k)]
