@@ -323,14 +323,12 @@ def test_dod_overflow(delta_h, unit, overflow):
 
 # ---------------------------------------------------------------- round trips (roundtrip_test.go)
 def _gen_float_val(r, num_dig, num_dec):
-    # src/dbnode/x/... testgen.GenerateFloatVal: random int with numDig digits / 10^numDec
-    # (semantics: value with <= num_dig integer digits and num_dec decimals)
-    dig = 10 ** num_dig
-    dec = 10 ** num_dec
-    v = float(r.randrange(dig))
-    if num_dec > 0:
-        v += float(r.randrange(dec)) / float(dec)
-    return v
+    # src/dbnode/encoding/testgen/gen.go:30-44 (GenerateFloatVal): "<dig>.<dec>" parsed as float64, the decimal
+    # part NOT zero-padded (dec = 5 with numDec = 3 gives x.5)
+    dig = r.getrandbits(62) % 10 ** num_dig
+    if num_dec == 0:
+        return float(dig)
+    return float("%d.%d" % (dig, r.getrandbits(62) % 10 ** num_dec))
 
 
 def _roundtrip(dps, int_opt):
@@ -383,6 +381,42 @@ def test_roundtrip_generated(num_dig, num_dec, neg, mixsign, int_opt):
             v = _gen_float_val(r, num_dig, num_dec)
             if neg or (mixsign and r.random() < 0.5):
                 v = -v
+            dps.append((t, v))
+        _roundtrip(dps, int_opt)
+
+
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_roundtrip_mixed(int_opt):
+    """roundtrip_test.go:88-95,237-262 (TestMixedRoundTrip / generateMixedDatapoints): steps of up to two hours,
+    the value switches between 5-digit integers (10 %), 3.16-digit floats (18 %) and a repeat of the last one."""
+    r = random.Random(4242)
+    for _ in range(8):
+        t = 1427162462 * SEC
+        end = 1427162400 * SEC + 2 * 3600 * SEC
+        v = _gen_float_val(r, 3, 16)
+        dps = [(t, v)]
+        for _i in range(1, 1000):
+            t += SEC * r.randrange(7200)
+            if r.random() < 0.1:
+                v = _gen_float_val(r, 5, 0)
+            elif r.random() < 0.2:
+                v = _gen_float_val(r, 3, 16)
+            if t >= end:
+                break
+            dps.append((t, v))
+        _roundtrip(dps, int_opt)
+    # the same value process at a one-minute cadence, so that streams are long enough to go through
+    # int -> float -> int mode changes many times
+    for _ in range(4):
+        t = 1427162462 * SEC
+        v = _gen_float_val(r, 3, 16)
+        dps = [(t, v)]
+        for _i in range(1, 600):
+            t += 10 * SEC
+            if r.random() < 0.1:
+                v = _gen_float_val(r, 5, 0)
+            elif r.random() < 0.2:
+                v = _gen_float_val(r, 3, 16)
             dps.append((t, v))
         _roundtrip(dps, int_opt)
 
