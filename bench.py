@@ -20,6 +20,7 @@ runs configs[1].
             both PCIe directions stay busy)
   roofline= the decode kernel: algorithmic bytes (compressed bytes + index entries in,
             16 B/dp out) / its average duration inside the timed region
+            (roofline_encode = the same accounting for the encode kernel of the step)
   cpu_baseline = the CPU oracle (plain-C restatement of the reference's Go codec; no Go
             toolchain in this image) on the host cores this process may use, bounded sample
 
@@ -841,6 +842,16 @@ def run_ours(args):
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dec_ms_max,
                 "bytes_per_dp": alg_bytes / (S * P)}
 
+    # the other (larger) half of the step, same accounting: 16 B/dp + start in; streams + (length, status) out
+    enc_alg_bytes = S * P * 16 + S * 8 + compressed_bytes + S * 12
+    enc_achieved = enc_alg_bytes / (enc_ms * 1e-3) / 1e9
+    roofline_encode = {"bound": "hbm",
+                       "kernel": "m3tsz::encode_kernel<%s,false,1> (point-major inputs staged by TMA tensor copies, "
+                                 "per-series segments)" % ("true" if int_opt else "false"),
+                       "achieved": enc_achieved, "peak": peak, "unit": "GB/s", "frac": enc_achieved / peak,
+                       "algorithmic_bytes_per_launch": enc_alg_bytes, "kernel_ms": enc_ms,
+                       "note": "issue-bound, not HBM-bound (profiles/r02c_encode_pm_tma_400kx1440.ncu_summary.txt)"}
+
     cpu = None
     if not args.no_cpu_baseline:
         cv, info = cpu_oracle_throughput(S, P, int_opt, budget_s=args.cpu_seconds)
@@ -863,7 +874,7 @@ def run_ours(args):
                           "decode_from_packed_ms": decp_ms,
                           "step_packed_ms": encp_ms + decp_ms,
                           "note": "encode with one packed output buffer (m3tsz_encode_batch_packed) + decode of it"},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_fetch": fetch, "gpu_launches": launches,
+        "roofline": roofline, "roofline_encode": roofline_encode, "cpu_baseline": cpu, "e2e": e2e, "e2e_fetch": fetch, "gpu_launches": launches,
         "clocks": clocks, "fetch_allgather": allgather,
     }
     line.update(side)
