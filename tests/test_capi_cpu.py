@@ -79,3 +79,83 @@ def test_xxh64_matches_oracle_on_long_inputs():
     for n in (1, 3, 4, 7, 8, 31, 32, 33, 63, 64, 100, 1000):
         b = bytes(r.randrange(256) for _ in range(n))
         assert xxh64(b) == O.lib().m3o_xxh64(b, n)
+
+
+def _split_top_level(args):
+    """Splits an argument list at top-level commas (parentheses / braces / brackets nest)."""
+    out, depth, cur = [], 0, ""
+    for ch in args:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def _balanced(text, open_idx):
+    """text[open_idx] == '(' -> the text between it and its matching ')'."""
+    depth = 0
+    for i in range(open_idx, len(text)):
+        if text[i] == "(":
+            depth += 1
+        elif text[i] == ")":
+            depth -= 1
+            if depth == 0:
+                return text[open_idx + 1: i]
+    raise AssertionError("unbalanced call at %d" % open_idx)
+
+
+def _header_prototypes():
+    hdr = open(os.path.join(ROOT, "include", "m3tsz_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+    protos = {}
+    for m in re.finditer(r"\b(m3tsz_[a-z_0-9]+)\s*\(", hdr):
+        args = _balanced(hdr, m.end() - 1).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(_split_top_level(args))
+    return protos, hdr
+
+
+def test_go_shim_in_integration_md_matches_the_header():
+    """INTEGRATION.md's cgo shim cannot be compiled here (no Go toolchain), so it is checked mechanically: every
+    C function it calls is declared in include/m3tsz_b200.h with the same number of arguments, every C constant
+    and C type it names exists there, and the per-datapoint interface methods of encoding.Encoder /
+    ReaderIterator (encoding/types.go:39-91,180-203) are all implemented."""
+    protos, hdr = _header_prototypes()
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    go = "\n".join(re.findall(r"```go\n(.*?)```", md, flags=re.S))
+    assert len(go) > 4000
+    go_nc = re.sub(r"//[^\n]*", "", go)
+    calls = list(re.finditer(r"\bC\.(m3tsz_[a-z_0-9]+)\s*\(", go_nc))
+    assert len(calls) >= 25
+    seen = set()
+    for m in calls:
+        name = m.group(1)
+        assert name in protos, "INTEGRATION.md calls undeclared %s" % name
+        n_args = len(_split_top_level(_balanced(go_nc, m.end() - 1)))
+        assert n_args == protos[name], (name, n_args, protos[name])
+        seen.add(name)
+    # the streaming handles a shim binds method for method
+    for need in ("m3tsz_encoder_create", "m3tsz_encoder_encode", "m3tsz_encoder_stream", "m3tsz_encoder_len",
+                 "m3tsz_encoder_reset", "m3tsz_encoder_discard", "m3tsz_encoder_last_encoded",
+                 "m3tsz_iter_create", "m3tsz_iter_reset", "m3tsz_iter_next", "m3tsz_iter_current",
+                 "m3tsz_iter_err"):
+        assert need in protos, need
+        assert need in seen, "the shim never calls %s" % need
+    for const in set(re.findall(r"\bC\.(M3TSZ_[A-Z_0-9]+)\b", go_nc)):
+        assert re.search(r"\b%s\b" % const, hdr), const
+    for typ in set(re.findall(r"\bC\.(m3tsz_[a-z_0-9]+)\b(?!\s*\()", go_nc)):
+        assert re.search(r"\b%s\b" % typ, hdr), typ
+    # interface coverage (method names of encoding.Encoder and encoding.ReaderIterator)
+    for method in ("Encode", "Stream", "NumEncoded", "LastEncoded", "LastAnnotationChecksum", "Empty", "Len",
+                   "Reset", "Close", "Discard", "DiscardReset", "SetSchema"):
+        assert re.search(r"func \(e \*Encoder\) %s\(" % method, go), "Encoder.%s" % method
+    for method in ("Next", "Current", "Err", "Close", "Reset"):
+        assert re.search(r"func \(\w+ \*ReaderIterator\) %s\(" % method, go), "ReaderIterator.%s" % method
