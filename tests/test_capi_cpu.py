@@ -123,6 +123,48 @@ def _header_prototypes():
     return protos, hdr
 
 
+def _header_param_types():
+    """function -> [C type of every parameter], qualifiers and parameter names dropped."""
+    _, hdr = _header_prototypes()
+    out = {}
+    for m in re.finditer(r"\b(m3tsz_[a-z_0-9]+)\s*\(", hdr):
+        args = _balanced(hdr, m.end() - 1).strip()
+        types = []
+        if args not in ("", "void"):
+            for a in _split_top_level(args):
+                a = re.sub(r"\s+", " ", a.strip())
+                mm = re.match(r"^(.*?)(\b\w+)$", a)
+                t = mm.group(1).strip() if mm and not a.endswith("*") else a
+                types.append(re.sub(r"\bconst\b", "", t).replace(" ", ""))
+        out[m.group(1)] = types
+    return out
+
+
+def test_go_shim_argument_types_match_the_header():
+    """Every argument of the shim that carries an explicit C conversion -- `C.T(x)` for scalars,
+    `(*C.T)(&x[0])` / `(*C.T)(unsafe.Pointer(..))` for buffers -- converts to the type the header declares for that
+    parameter."""
+    types = _header_param_types()
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    go = re.sub(r"//[^\n]*", "", "\n".join(re.findall(r"```go\n(.*?)```", md, flags=re.S)))
+    checked = 0
+    for m in re.finditer(r"\bC\.(m3tsz_[a-z_0-9]+)\s*\(", go):
+        name = m.group(1)
+        for arg, want in zip(_split_top_level(_balanced(go, m.end() - 1)), types[name]):
+            scalar = re.match(r"^C\.(\w+)\(", arg)
+            pointer = re.match(r"^\(\*C\.(\w+)\)\(", arg)
+            if scalar:
+                assert want == scalar.group(1), (name, arg, want)
+                checked += 1
+            elif pointer:
+                assert want == pointer.group(1) + "*", (name, arg, want)
+                checked += 1
+            elif arg == "nil" or arg.startswith("&"):
+                assert want.endswith("*"), (name, arg, want)
+                checked += 1
+    assert checked >= 70
+
+
 def test_go_shim_in_integration_md_matches_the_header():
     """INTEGRATION.md's cgo shim cannot be compiled here (no Go toolchain), so it is checked mechanically: every
     C function it calls is declared in include/m3tsz_b200.h with the same number of arguments, every C constant
