@@ -117,3 +117,94 @@ def test_oracle_encoded_gaussian_walk_and_mode_switches(int_opt):
         assert st[0] == 0
         got = _same(out[0, : ln[0]].tobytes(), int_opt)
         assert [g[0] for g in got] == ts.tolist()
+
+
+# ------------------------------------------------------------------------------------------------------
+# the independent ENCODER: same bytes as the oracle's encoder
+# ------------------------------------------------------------------------------------------------------
+def _oracle_encode(start, dps, int_opt):
+    e = O.Encoder(start, int_opt)
+    for t, v, u, a in dps:
+        assert e.encode(t, v, u, a) == 0
+    return e.stream()
+
+
+def test_independent_encoder_reproduces_the_golden_streams():
+    assert len(G["streams"]) == 4
+    for s in G["streams"]:  # encoder_test.go:207-393: the reference's own bytes, not the oracle's
+        dps = [(p["ts"], float(p["value"]), p["unit"], bytes.fromhex(p["annotation"])) for p in s["datapoints"]]
+        assert I.encode(s["encoder_start"], dps, s["int_optimized"]) == bytes.fromhex(s["bytes"]), s["name"]
+        got = I.decode(bytes.fromhex(s["bytes"]), s["int_optimized"])
+        assert [(g[0], g[1]) for g in got] == [(p["ts"], _bits(float(p["value"]))) for p in s["datapoints"]]
+        assert [g[3].hex() for g in got] == s["decoded_annotations"]
+
+
+@pytest.mark.parametrize("int_opt", [True, False])
+@pytest.mark.parametrize("with_markers", [False, True])
+def test_independent_encoder_matches_oracle_bytes_on_families(int_opt, with_markers):
+    r = random.Random(7 + int(int_opt) * 2 + int(with_markers))
+    start = 1427162400 * SEC
+    fams = [(12, 0), (7, 6), (0, 1), (2, 16), (5, 3), (3, 0), (18, 0), (1, 2), (0, 6), (4, 4), (9, 2), (0, 0)]
+    for num_dig, num_dec in fams:
+        for rep in range(4):
+            t = 1427162462 * SEC
+            dps = []
+            for i in range(300):
+                v = 1.0 if i == 0 else _gen(r, num_dig, num_dec)
+                if rep == 1 and r.random() < 0.5:
+                    v = -v
+                if rep == 2 and dps and r.random() < 0.3:
+                    v = dps[-1][1]
+                if rep == 3 and r.random() < 0.15:  # another family now and then: mode / multiplier / sig changes
+                    v = _gen(r, *fams[r.randrange(len(fams))])
+                unit, ann = O.UNIT_S, b""
+                if with_markers:
+                    unit = O.UNIT_MS if i == 0 else (O.UNIT_US if i == 10 else (O.UNIT_NS if 200 <= i < 210 else O.UNIT_S))
+                    ann = b"foo" if i < 5 else (b"bar" if i < 7 else (b"long annotation " * 9 if i == 10 else b""))
+                dps.append((t, v, unit, ann))
+                t += SEC * r.randrange(1200) + (r.randrange(1000) * 1000 if with_markers and i >= 10 else 0)
+            assert I.encode(start, dps, int_opt) == _oracle_encode(start, dps, int_opt), (num_dig, num_dec, rep)
+
+
+@pytest.mark.parametrize("int_opt", [True, False])
+def test_independent_encoder_matches_oracle_bytes_on_walks_and_specials(int_opt):
+    rng = np.random.default_rng(11)
+    start = 1599955200 * SEC
+    for s in range(40):
+        P = 400
+        ts = start + np.arange(1, P + 1, dtype=np.int64) * 60 * SEC
+        if s % 5 == 0:
+            vals = 100.0 + np.cumsum(rng.normal(size=P))
+        elif s % 5 == 1:
+            vals = np.round(np.cumsum(rng.normal(size=P) * 10.0 ** rng.integers(0, 12))).astype(np.float64)
+        elif s % 5 == 2:
+            vals = np.concatenate([np.round(rng.normal(size=100) * 50, 1), np.round(rng.normal(size=100) * 50, 4),
+                                   rng.normal(size=100), np.round(rng.normal(size=100) * 1000)])
+        elif s % 5 == 3:
+            vals = np.round(rng.normal(size=P) * 5, int(rng.integers(0, 7)))
+            sp = [np.nan, np.inf, -np.inf, -0.0, 2.0 ** 63, -2.0 ** 63, 1e300, -1e300, 5e-324, 0.0, 9.2e18, 1e13, 1e13 - 1]
+            vals[::29] = (sp * 2)[: len(vals[::29])]
+        else:  # jittered timestamps: every delta-of-delta bucket
+            vals = np.round(rng.normal(size=P) * 100, 2)
+            ts = start + np.cumsum(rng.choice([1, 10, 60, 300, 3000, 100000], size=P)).astype(np.int64) * SEC
+        dps = [(int(t), float(v), O.UNIT_S, b"") for t, v in zip(ts, vals)]
+        mine = I.encode(start, dps, int_opt)
+        out, ln, st = O.encode_batch(ts[None, :], vals[None, :], start, O.UNIT_S, int_opt)
+        assert st[0] == 0
+        assert mine == out[0, : ln[0]].tobytes(), s
+
+
+def test_independent_pair_reencodes_the_production_fixtures_byte_identically():
+    """encoder_benchmark_test.go:36-47: ten int-optimised production streams (ms unit, markers, int mode, repeats).
+    Independent decoder -> independent encoder (the stream's own start, per-datapoint unit and annotations replayed)
+    gives back the reference's bytes: the int-optimised encoder pinned against reference-produced bytes without the
+    C oracle in the loop."""
+    n = 0
+    for b64 in G["fixtures_b64"]["streams"]:
+        data = base64.b64decode(b64)
+        got = I.decode(data, True)
+        start = struct.unpack(">q", data[:8])[0]
+        dps = [(t, struct.unpack("<d", struct.pack("<Q", vb))[0], u, a) for t, vb, u, a in got]
+        assert I.encode(start, dps, True) == data
+        n += len(dps)
+    assert n == 7197
