@@ -208,3 +208,34 @@ def test_independent_pair_reencodes_the_production_fixtures_byte_identically():
         assert I.encode(start, dps, True) == data
         n += len(dps)
     assert n == 7197
+
+
+def test_independent_convert_to_int_float_matches_oracle():
+    """m3tsz.go:78-119 restated twice (C oracle, pure Python): same (value, multiplier, isFloat) for every current
+    multiplier on the reference's families, on +-ulp neighbours of k / 10^m (where Modf / Nextafter decide) and on
+    random bit patterns."""
+    r = random.Random(31)
+    vals = []
+    for num_dig, num_dec in [(0, 0), (2, 0), (10, 0), (18, 0), (0, 6), (3, 6), (7, 6), (0, 1), (1, 3), (5, 3), (2, 16),
+                             (9, 2), (11, 3), (13, 0), (12, 1)]:
+        for _ in range(300):
+            v = _gen(r, num_dig, num_dec)
+            vals += [v, -v]
+    base = np.array([(r.getrandbits(r.randrange(1, 50)) + 1) / 10.0 ** r.randrange(0, 7) for _ in range(3000)])
+    bits = base.view(np.int64)
+    for j in (-3, -2, -1, 1, 2, 3, 9, 40):
+        vals += (bits + j).view(np.float64).tolist()
+    vals += base.tolist() + (-base).tolist()
+    rb = np.random.default_rng(5).integers(0, 2 ** 63, size=4000, dtype=np.int64).view(np.float64)
+    vals += rb.tolist() + (-rb).tolist()
+    vals += [0.0, -0.0, float("inf"), float("-inf"), 2.0 ** 63, -2.0 ** 63, 1e13, 1e13 - 0.5, 9999999999999.9, 1e300, -1e300]
+    n = 0
+    for v in vals:
+        for cur in range(7):
+            ov, om, of, err = O.convert_to_int_float(v, cur)
+            assert err == 0
+            iv, im, isf = I.convert_to_int_float(v, cur)
+            assert (im, isf) == (om, of), (v, cur)
+            assert iv == ov or (iv != iv and ov != ov), (v, cur, iv, ov)
+            n += 1
+    assert n > 250000
