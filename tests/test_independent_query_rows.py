@@ -6,6 +6,7 @@ oracle itself is pinned by the reference's gauge_test.go / prom_converter_test.g
 the tables do not enumerate: NaN / Inf inside windows, out-of-order timestamps, empty windows, points outside the
 range, negative values, resets in the middle of a resolution window)."""
 import math
+import struct
 
 import numpy as np
 import pytest
@@ -17,7 +18,8 @@ SEC = 10 ** 9
 
 def gauge_windows(ts, vals, start, window, n_windows):
     """one aggregation.Gauge per window (gauge.go:45-106)"""
-    nan = float("nan")
+    nan = struct.unpack("<d", struct.pack("<Q", 0x7FF8000000000001))[0]  # Go's math.NaN() (math/bits.go uvnan):
+    # a window that only saw NaNs hands THIS payload to the tile encoder, whose XOR path keeps payload bits
     w = [dict(sum=0.0, count=0, mn=nan, mx=nan, last=0.0, last_at=None) for _ in range(n_windows)]
     for t, v in zip(ts, vals):
         i = (t - start) // window  # floor: timestamps before the range give negative windows
@@ -128,3 +130,34 @@ def test_prom_convert_matches_oracle(seed):
         for (rt, rv), ot, ov in zip(ref, o_ts.tolist(), o_v.tolist()):
             assert rt == ot
             assert np.float64(rv).view(np.uint64) == np.float64(ov).view(np.uint64) or (rv != rv and ov != ov)
+
+
+@pytest.mark.parametrize("agg", [O.AGG_LAST, O.AGG_MIN, O.AGG_MAX, O.AGG_MEAN, O.AGG_COUNT, O.AGG_SUM])
+def test_tile_aggregation_matches_oracle_and_independent_encoder(agg):
+    """row N3 (storage.TileAggregator compute): one datapoint per non-empty Step window at the window's END
+    (aggregator/list.go:541-543), value = Gauge.ValueOf(type) (gauge.go:144-165); and the re-encoded stream: the
+    oracle's encoder against the independent encoder of tests/indep_m3tsz.py on those tiles."""
+    import indep_m3tsz as I
+    rng = np.random.default_rng(300 + agg)
+    start, step, n_windows = 1599955200 * SEC, 300 * SEC, 48
+    for _ in range(25):
+        n = int(rng.integers(0, 500))
+        ts = np.sort(start + rng.integers(0, n_windows * step, size=n))
+        vals = np.round(rng.normal(size=n) * 50, int(rng.integers(0, 3)))
+        if n:
+            vals[rng.integers(0, n, size=max(1, n // 30))] = np.nan
+        t_o, v_o = O.aggregate_tiles_series(ts, vals, start, step, n_windows, agg)
+        exp = []
+        for i, g in enumerate(gauge_windows(ts.tolist(), vals.tolist(), start, step, n_windows)):
+            if g["count"] == 0:
+                continue
+            value = {O.AGG_LAST: g["last"], O.AGG_MIN: g["mn"], O.AGG_MAX: g["mx"],
+                     O.AGG_MEAN: (g["sum"] / float(g["count"])) if g["count"] else 0.0,
+                     O.AGG_COUNT: float(g["count"]), O.AGG_SUM: g["sum"]}[agg]
+            exp.append((start + (i + 1) * step, value))
+        assert t_o.tolist() == [e[0] for e in exp]
+        for a, (_, b) in zip(v_o.tolist(), exp):
+            assert _eq(a, b)
+        if exp:
+            mine = I.encode(start, [(t, v, O.UNIT_S, b"") for t, v in exp], True)
+            assert mine == O.encode_series(t_o, v_o, start, O.UNIT_S, True)
