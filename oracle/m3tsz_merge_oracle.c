@@ -341,12 +341,19 @@ int64_t m3o_series_merge(const int64_t *ts, const double *val, uint64_t cap, con
   int err = 0;
   for (uint64_t r = 0; r < n_rep; r++) {
     mri_t *it = &reps[r];
-    /* slices of this replica must not hold more than MAXK readers */
+    /* slices of this replica must not hold more than MAXK readers (restatement limit, not a reference error:
+     * only THIS condition stops the loop -- an error of an earlier replica does not, see below) */
+    int too_many = 0;
     for (uint64_t k = replica_off[rep0 + r]; k < replica_off[rep0 + r + 1]; k++)
-      if (slice_off[k + 1] - slice_off[k] > MAXK) err = M3O_ERR_TOO_MANY_ITERATORS;
-    if (err) break;
+      if (slice_off[k + 1] - slice_off[k] > MAXK) too_many = 1;
+    if (too_many) {
+      err = M3O_ERR_TOO_MANY_ITERATORS;
+      break;
+    }
     mri_reset(it, seqs, q0, slice_off, replica_off[rep0 + r], replica_off[rep0 + r + 1]);
     if (!it->m.next(&it->m) || !iters_push(&top, &it->m)) {
+      /* seriesIterator.Reset, series_iterator.go:157-168: `it.err = replica.Err()` -- every failing replica
+       * overwrites the error of the ones before it, and the loop goes on to the remaining replicas */
       if (it->m.err(&it->m)) err = it->m.err(&it->m);
       continue;
     }

@@ -74,6 +74,9 @@ def test_reference_tables_on_gpu(codec):
         ([[[[rng_filter]]]], dict(start=START, end=START + 60 * SEC)),           # FiltersToRange
         ([[[[a]], [[[]]], [[a]]]], dict(start=START, end=START + 60 * SEC)),     # IgnoresEmptyReplicas
         ([[[[([], 55)]]]], dict(start=START, end=START + 60 * SEC)),             # replica with error
+        # several failing replicas: the LAST error is the series' error (series_iterator.go:157-168)
+        ([[[[([], 55)]], [[([], 66)]], [[a]]]], dict(start=START, end=START + 60 * SEC)),
+        ([[[[([], 66)]], [[a]], [[([], 55)]]]], dict(start=START, end=START + 60 * SEC)),
         ([[[[oo]]]], dict(start=START, end=START + 60 * SEC)),                   # out of order (series)
     ]
     for strategy in (0, 1, 2, 3):

@@ -131,6 +131,19 @@ def test_series_does_not_ignore_replicas_with_errors():  # :167-186
     assert out[0] == [] and st == [55]
 
 
+def test_series_last_failing_replica_sets_the_error():
+    """series_iterator.go:157-168 (Reset): `it.err = replica.Err()` is an unconditional assignment inside the loop
+    over ALL replicas -- when several replicas fail, the LAST one's error is the series' error (and the healthy
+    replicas after a failing one are still pushed, although hasNext() then refuses to iterate).  Found by running
+    the device merge kernels on the host against this oracle (tests/test_device_merge_on_host.py): the oracle
+    used to stop at the first failing replica."""
+    v = [(1.0, at(1)), (2.0, at(2))]
+    out, st = merge([[[[([], 55)]], [[([], 66)]], [[v]]]], start=START, end=START + 60 * SEC)
+    assert out[0] == [] and st == [66]
+    out, st = merge([[[[([], 66)]], [[v]], [[([], 55)]]]], start=START, end=START + 60 * SEC)
+    assert out[0] == [] and st == [55]
+
+
 def test_series_error_on_out_of_order():  # :188-213
     v = [(1.0, at(1)), (3.0, at(3)), (2.0, at(2))]
     out, st = merge([[[[v]]]], start=START, end=START + 60 * SEC)
