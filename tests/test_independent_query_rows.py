@@ -91,7 +91,7 @@ def prom_convert(ts, vals, resolution, handle_resets, tolerance=0.0, until=0):
             out.append((_go_div(t, 10 ** 6), v))
         prev_t, prev_v = t, v
         first = False
-    if handle_resets:
+    if handle_resets and not first:  # handleResets is only ever set while looking at the first datapoint (:76-84)
         out.append((_go_div(prev_t, 10 ** 6), cum))
     return out
 
